@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py — FISTA-L1 iterations/s on a dense Float32 A 16384 x 65536 (BASELINE.json
+configs[1]) through librls_b200, with the roofline of the normal-operator kernel and the
+restated-reference CPU baseline beside it.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun)
+  python bench.py --impl reference ...                    (the oracle port on the host cores)
+
+A "step" is one solve!(solver, b): `iterations` (200) FISTA iterations on one right-hand
+side.  `value` times K steps with b already resident in HBM; `e2e` times the same K steps
+through the public API with host buffers (H2D of b and D2H of x inside the timed region).
+N>1 is weak scaling: every rank holds one 16384 x 65536 row shard of a (16384*N) x 65536
+system, one NCCL allreduce of the n-vector per iteration; `value` counts shard-iterations
+(iterations/s x N), so N=1 is plain iterations/s.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M, N_COLS, ITERS = 16384, 65536, 200
+LAMBDA = np.float32(1e-3)
+SEED = 12345
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(s[1]) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, nm in enumerate(names):
+                if len(s) > 5 + k and s[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def cpu_sample(iters=20, m_sub=4096, threads=None):
+    """The oracle's FISTA loop (NumPy -> threaded OpenBLAS sgemv) on a row subsample of the
+    workload; iterations/s are scaled linearly in m to the full 16384 rows."""
+    import oracle as O
+    rng = np.random.default_rng(SEED)
+    A = rng.standard_normal((m_sub, N_COLS), dtype=np.float32) / np.float32(np.sqrt(M))
+    A = np.asfortranarray(A)
+    b = rng.standard_normal(m_sub, dtype=np.float32)
+    S = O.FISTA(A, reg=O.L1Regularization(LAMBDA), iterations=iters + 2, rho=np.float32(0.1), relTol=0.0)
+    S.init(b)
+    S.iterate(); S.iterate()
+    t0 = time.perf_counter()
+    k = 0
+    while S.iterate():
+        k += 1
+    dt = time.perf_counter() - t0
+    its_sub = k / dt
+    return its_sub * (m_sub / M), k, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    m_sub, iters = 4096, 20
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_sample(iters=3, m_sub=m_sub)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        v, k, dt = cpu_sample(iters=iters, m_sub=m_sub)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    sample = (f"{iters} FISTA-L1 iterations per step on a {m_sub}-row subsample of the 16384x65536 Float32 system "
+              f"(oracle loop, NumPy/OpenBLAS two-gemv normal operator); iterations/s scaled by {m_sub}/{M}")
+    line = {"metric": "FISTA-L1 iterations/s on dense A (Float32 16384x65536)", "value": value, "unit": "iterations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * ITERS / value if value > 0 else None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "C2: FISTA + L1Regularization, dense Float32 A 16384x65536, 200 iterations",
+                       "note": "Julia is not installed in this image; the reference arm is the float32-faithful oracle port"},
+            "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import rls_b200 as rls
+    rank, world, local = rls.dist.env_rank()
+    multi = world > 1
+    if multi:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = rls.B200Context.default(local)
+    if multi:
+        rls.dist.init_comm(ctx, rank, world)
+    m_global = M * world
+    scale = 1.0 / np.sqrt(m_global)
+    A = rls.B200Matrix.philox(np.float32, M, N_COLS, seed=SEED, scale=scale, row_offset=rank * M, m_global=m_global, ctx=ctx)
+    # b = A x_true + noise, generated on the device (shard rows of the global b)
+    xt = rls.B200Vector(ctx, np.float32, N_COLS).fill_philox(SEED, stream=11, dist=0)
+    xt_h = xt.to_numpy()
+    xt_h[np.arange(N_COLS) % 100 != 0] = 0                       # 1 % non-zeros
+    xt.upload(xt_h)
+    b_dev = A.mul(xt)
+    noise = rls.B200Vector(ctx, np.float32, M).fill_philox(SEED, stream=12, dist=1, scale=1e-3, offset=rank * M)
+    b_host = (b_dev.to_numpy() + noise.to_numpy()).astype(np.float32)
+    b_dev.upload(b_host)
+    form = args.normal
+    AHA = rls.B200NormalOp(A, form=form)
+    # rho = 0.95 / lambda_max from 30 power iterations, fixed Philox start vector
+    b0 = rls.B200Vector(ctx, np.float32, N_COLS).fill_philox(SEED, stream=13, dist=1)
+    lam_max = AHA.power_iterations(b0, rtol=1e-3, maxiter=30)
+    rho = np.float32(0.95 / lam_max)
+    S = rls.FISTA(A, AHA=AHA, reg=rls.L1Regularization(LAMBDA), iterations=ITERS, rho=rho, relTol=0.0)
+    import ctypes as C
+    capi = rls._capi
+    it = C.c_int32()
+
+    def solve_dev():
+        capi.call("rls_solver_solve", S._handle, b_dev.handle, None, C.byref(it), C.byref(S._scalars))
+
+    def barrier():
+        ctx.sync()
+        if multi:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        ctx.timer_start()
+        for _ in range(steps):
+            fn()
+        ms = ctx.timer_stop()
+        barrier()
+        if multi:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        solve_dev()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ms = timed(solve_dev, args.steps)
+    launches = ctx.launch_count() - l0
+    assert it.value == ITERS
+    its_per_s = args.steps * ITERS / (ms * 1e-3)
+
+    # e2e: the user's call — host b in, host x out, every step
+    x_host = None
+    def solve_host():
+        nonlocal x_host
+        x_host = rls.solve_(S, b_host)
+    for _ in range(2):
+        solve_host()
+    ms_e2e = timed(solve_host, args.steps)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    e2e_its = args.steps * ITERS / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel: the normal-operator apply, timed alone on its stream
+    xv = S._vec("x")
+    res = rls.B200Vector(ctx, np.float32, N_COLS)
+    reps = 40
+    for _ in range(5):
+        AHA.apply(xv, res)
+    ms_k = timed(lambda: AHA.apply(xv, res), reps) / reps
+    alg_bytes = M * N_COLS * 4
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (ms_k * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get(AHA.form)
+        except Exception:
+            traffic = None
+    clocks = sampler.summary()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, k, dt = cpu_sample(iters=20, m_sub=4096)
+        cpu = {"value": v, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{k} FISTA-L1 iterations of the oracle loop (NumPy/OpenBLAS) on a 4096-row subsample in {dt:.1f} s, "
+                         f"scaled by 4096/{M} to the full system; restated reference, Julia is not installed"}
+    if rank == 0:
+        line = {
+            "metric": "FISTA-L1 iterations/s on dense A (Float32 16384x65536 per GPU)",
+            "value": its_per_s * world, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: FISTA + L1Regularization(1f-3), dense Float32 A 16384x65536, 200 iterations per "
+                                   "solve!, rho = 0.95/lambda_max (30 power iterations), relTol = 0",
+                       "normal_operator": AHA.form, "iterations_per_step": ITERS,
+                       "parallelism": "single GPU" if world == 1 else f"row-sharded x{world}: (16384*{world})x65536, one "
+                                      "NCCL allreduce of the 65536-vector per iteration; value = shard-iterations/s",
+                       "l2": "inputs (4.3 GB per GPU) are far larger than L2; no flush needed",
+                       "ms_per_iteration": ms / args.steps / ITERS,
+                       "in_step_gbs": alg_bytes * ITERS * args.steps / (ms * 1e-3) / 1e9},
+            "e2e": {"value": e2e_its * world, "unit": "iterations/s", "h2d_bytes_per_step": int(b_host.nbytes),
+                    "d2h_bytes_per_step": int(x_host.nbytes)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": f"normal operator A'(A x) [{AHA.form}]", "ms_per_launch": ms_k,
+                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--normal", default="auto", choices=["auto", "twopass", "onepass"])
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,275 @@
+/*
+ * rls_b200.h — C ABI of librls_b200.so, the sm_100a (B200) implementation of the
+ * RegularizedLeastSquares.jl iterative-solver inner loop.
+ *
+ * This is the drop-in boundary: a Julia shim (julia/RLSB200.jl)
+ * binds these symbols with `ccall`; the Python host mirror binds them with ctypes.
+ * Plain pointers and sizes only — no torch / CUDA types in any signature.
+ *
+ * Conventions
+ *   - every function returns an int32 status (RLS_OK == 0); on failure
+ *     rls_last_error() returns a NUL-terminated message (thread-local).  Nothing
+ *     aborts or throws across the ABI.  There is NO CPU fallback: without a usable
+ *     sm_100 device rls_ctx_create fails with RLS_ERR_CUDA.
+ *   - matrices are column-major, element (i,j) at i + j*ld (Julia `Matrix`);
+ *     ComplexF32 is interleaved (re,im) float pairs; vectors are contiguous.
+ *   - handles are opaque and own device memory; host pointers are borrowed only
+ *     for the duration of a call.
+ *   - all work of a context is issued on the context's own CUDA stream; calls are
+ *     asynchronous unless they return a host scalar / copy to host memory.
+ *
+ * Each entry point cites the reference interface (file:line under /root/reference)
+ * it replaces.
+ */
+#ifndef RLS_B200_H
+#define RLS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLS_B200_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------ */
+enum {
+  RLS_OK = 0,
+  RLS_ERR_INVALID = 1,      /* bad argument / shape / dtype mismatch              */
+  RLS_ERR_CUDA = 2,         /* CUDA runtime error (message has the CUDA string)   */
+  RLS_ERR_COMM = 3,         /* NCCL error or NCCL not loadable                    */
+  RLS_ERR_UNSUPPORTED = 4,  /* outside the accelerated path (no CPU fallback)     */
+  RLS_ERR_NOMEM = 5
+};
+
+/* ---- element types: eltype(A) on the hot path (SURVEY 8b "Types") ------------ */
+enum { RLS_F32 = 0, RLS_C32 = 1 };
+
+/* ---- solver kinds: src/{FISTA,POGM,OptISTA,CGNR,ADMM}.jl --------------------- */
+enum { RLS_FISTA = 0, RLS_POGM = 1, RLS_OPTISTA = 2, RLS_CGNR = 3, RLS_ADMM = 4 };
+
+/* ---- regularisation sinks: src/proximalMaps/Prox{L1,L2,L21,TV}.jl ------------ */
+enum { RLS_REG_NONE = 0, RLS_REG_L1 = 1, RLS_REG_L2 = 2, RLS_REG_L21 = 3, RLS_REG_TV = 4 };
+
+/* ---- projections: src/proximalMaps/Prox{Real,Positive}.jl (bit mask) --------- */
+enum { RLS_PROJ_REAL = 1, RLS_PROJ_POSITIVE = 2 };
+
+/* ---- normal-operator forms (mul!(res, AHA, x): FISTA.jl:152, CGNR.jl:151, ...) */
+enum {
+  RLS_NORMAL_TWOPASS = 0,   /* y = A x ; g = A' y      (2 sweeps over A)          */
+  RLS_NORMAL_ONEPASS = 1,   /* fused panel kernel      (1 HBM sweep over A)       */
+  RLS_NORMAL_GRAM = 2,      /* g = G x with G = A'A    (reference default form)   */
+  RLS_NORMAL_AUTO = 3
+};
+
+/* ---- ADMM regTrafo (ADMM.jl:63,74) -------------------------------------------- */
+enum { RLS_TRAFO_IDENTITY = 0, RLS_TRAFO_GRADIENT = 1 };
+enum { RLS_VARY_RHO_NONE = 0, RLS_VARY_RHO_BALANCE = 1, RLS_VARY_RHO_PNP = 2 };
+
+/* ---- synthetic data distributions for rls_*_fill_philox ---------------------- */
+enum {
+  RLS_DIST_UNIFORM01 = 0,   /* U[0,1) 24-bit                                       */
+  RLS_DIST_IH4 = 1          /* Irwin–Hall(4) centred, unit variance (≈N(0,1)),
+                               integer-exact so CPU and GPU agree bit for bit      */
+};
+
+typedef struct rls_ctx_s* rls_ctx_t;
+typedef struct rls_mat_s* rls_mat_t;
+typedef struct rls_vec_s* rls_vec_t;
+typedef struct rls_normal_s* rls_normal_t;
+typedef struct rls_solver_s* rls_solver_t;
+
+/* ============================ context ========================================= */
+int32_t rls_abi_version(void);
+const char* rls_last_error(void);
+int32_t rls_device_count(int32_t* count);
+/* one context = one device + one stream (+ optionally one NCCL rank) */
+int32_t rls_ctx_create(int32_t device, rls_ctx_t* out);
+int32_t rls_ctx_destroy(rls_ctx_t ctx);
+int32_t rls_ctx_sync(rls_ctx_t ctx);
+int32_t rls_ctx_device_info(rls_ctx_t ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
+                            int64_t* l2_bytes, int64_t* hbm_bytes);
+/* CUDA-event timer on the context stream (bench.py; torch events cannot see this stream) */
+int32_t rls_timer_start(rls_ctx_t ctx);
+int32_t rls_timer_stop(rls_ctx_t ctx, float* elapsed_ms);
+/* number of kernels this library launched on ctx since creation (bench "gpu_launches") */
+int32_t rls_ctx_launch_count(rls_ctx_t ctx, int64_t* launches);
+/* write > L2 bytes to a scratch buffer (timing hygiene for L2-resident configs) */
+int32_t rls_ctx_flush_l2(rls_ctx_t ctx);
+
+/* ---- row-sharded multi-GPU: one process per GPU, NCCL over NVLink -- */
+/* rank 0 creates the 128-byte id and ships it to the peers with the host's own
+ * transport (torch.distributed / MPI.jl); every rank then joins. */
+int32_t rls_comm_unique_id(void* id128);
+int32_t rls_ctx_comm_init(rls_ctx_t ctx, int32_t rank, int32_t nranks, const void* id128);
+int32_t rls_ctx_comm_info(rls_ctx_t ctx, int32_t* rank, int32_t* nranks);
+/* sum-allreduce of a device vector across ranks (the n-vector A_i' r_i) */
+int32_t rls_vec_allreduce(rls_vec_t v);
+
+/* ============================ vectors ========================================= */
+/* `similar(b, n)` on the device: FISTA.jl:94-103, CGNR.jl:91-100, ADMM.jl:166-184 */
+int32_t rls_vec_create(rls_ctx_t ctx, int32_t dtype, int64_t len, rls_vec_t* out);
+int32_t rls_vec_destroy(rls_vec_t v);
+int32_t rls_vec_len(rls_vec_t v, int64_t* len, int32_t* dtype);
+int32_t rls_vec_upload(rls_vec_t v, const void* host, int64_t len);       /* async on ctx stream if host is pinned */
+int32_t rls_vec_download(rls_vec_t v, void* host, int64_t len);           /* synchronises */
+int32_t rls_vec_copy(rls_vec_t dst, rls_vec_t src);
+int32_t rls_vec_fill(rls_vec_t v, float re, float im);
+int32_t rls_vec_fill_philox(rls_vec_t v, uint64_t seed, uint64_t stream, int32_t dist, float scale,
+                            int64_t offset);
+/* device pointer escape hatch for zero-copy interop (CuArray / torch tensors) */
+int32_t rls_vec_device_ptr(rls_vec_t v, void** ptr);
+/* norm(x), dot(a,b)=conj(a).b : Utils / LinearAlgebra call sites FISTA.jl:118,156,172; CGNR.jl:125,153-171 */
+int32_t rls_vec_nrm2(rls_vec_t v, double* out);
+int32_t rls_vec_asum(rls_vec_t v, double* out);                           /* norm(b,1): NormalizedRegularization.jl:41 */
+int32_t rls_vec_dot(rls_vec_t a, rls_vec_t b, double out_re_im[2]);
+
+/* ============================ matrices ======================================== */
+/* Dense column-major system matrix (or row shard of it).  host==NULL allocates
+ * uninitialised device storage (fill with rls_mat_fill_philox or rls_mat_upload). */
+int32_t rls_mat_create(rls_ctx_t ctx, int32_t dtype, int64_t m, int64_t n, const void* host, int64_t ld,
+                       rls_mat_t* out);
+/* adopt an existing device allocation (CuArray) without copying; not freed by destroy */
+int32_t rls_mat_wrap_device(rls_ctx_t ctx, int32_t dtype, int64_t m, int64_t n, void* dev, int64_t ld,
+                            rls_mat_t* out);
+int32_t rls_mat_destroy(rls_mat_t A);
+int32_t rls_mat_shape(rls_mat_t A, int64_t* m, int64_t* n, int32_t* dtype);
+int32_t rls_mat_upload(rls_mat_t A, const void* host, int64_t ld);
+int32_t rls_mat_download(rls_mat_t A, void* host, int64_t ld);
+/* A[i,j] = scale * dist(philox(seed; counter = (row_offset+i) + j*m_global [, component]))
+ * so that any row shard regenerates exactly its rows of the global matrix. */
+int32_t rls_mat_fill_philox(rls_mat_t A, uint64_t seed, int32_t dist, float scale, int64_t row_offset,
+                            int64_t m_global);
+/* sum |A_ij|^2 : SystemMatrixBasedNormalization, NormalizedRegularization.jl:47-58 + Utils.jl:6-20 */
+int32_t rls_mat_frob2(rls_mat_t A, double* out);
+/* mul!(y, A, x) and mul!(g, adjoint(A), y): FISTA.jl:114, CGNR.jl:132, ADMM.jl:198 */
+int32_t rls_gemv_n(rls_mat_t A, rls_vec_t x, rls_vec_t y);
+int32_t rls_gemv_c(rls_mat_t A, rls_vec_t y, rls_vec_t g);
+
+/* ============================ normal operator ================================= */
+/* AHA: normalOperator(A) (lazy) or A'*A (Gram, FISTA.jl:58).  With a communicator
+ * on ctx, A is this rank's row shard and apply() allreduces the n-vector. */
+int32_t rls_normal_create(rls_mat_t A, int32_t form, rls_normal_t* out);
+/* AHA supplied directly as a dense n×n matrix: createLinearSolver(S; AHA=G) (FISTA.jl:55, CGNR.jl:46) */
+int32_t rls_normal_from_gram(rls_mat_t G, rls_normal_t* out);
+int32_t rls_normal_destroy(rls_normal_t op);
+int32_t rls_normal_form(rls_normal_t op, int32_t* form);
+/* mul!(res, AHA, x): FISTA.jl:152, POGM.jl:181, OptISTA.jl:182, CGNR.jl:151, cg! in ADMM.jl:244 */
+int32_t rls_normal_apply(rls_normal_t op, rls_vec_t x, rls_vec_t res);
+/* power_iterations(AHA, b; rtol, maxiter) Utils.jl:262-287; b0 replaces the randn start vector */
+int32_t rls_power_iterations(rls_normal_t op, rls_vec_t b0, double rtol, int32_t maxiter, double* lambda_max);
+
+/* ============================ proximal maps =================================== */
+/* prox!(reg, x, λ) on a device vector; λ already converted to the real type of x
+ * (Regularization.jl:31).  ProxL1.jl:18-22, ProxL2.jl:18-21, ProxL21.jl:30-35,
+ * ProxTV.jl:89-125 (FGP), ProxPositive.jl:16-20, ProxReal.jl:16-19. */
+int32_t rls_prox_l1(rls_vec_t x, float lambda);
+int32_t rls_prox_l2(rls_vec_t x, float lambda);
+int32_t rls_prox_l21(rls_vec_t x, float lambda, int64_t slices);
+int32_t rls_prox_tv(rls_vec_t x, float lambda, int32_t ndims, const int64_t* shape, int32_t ndirs,
+                    const int32_t* dims_1based, int32_t iterations_tv);
+int32_t rls_prox_positive(rls_vec_t x);
+int32_t rls_prox_real(rls_vec_t x);
+/* GradientOp(T; shape, dims) forward / transpose (LinearOperatorCollection; ProxTV.jl:46, ADMM.jl:74) */
+int32_t rls_grad_rows(int32_t ndims, const int64_t* shape, int32_t ndirs, const int32_t* dims_1based, int64_t* rows);
+int32_t rls_grad_apply(rls_vec_t img, rls_vec_t out, int32_t ndims, const int64_t* shape, int32_t ndirs,
+                       const int32_t* dims_1based);
+int32_t rls_grad_apply_t(rls_vec_t g, rls_vec_t out, int32_t ndims, const int64_t* shape, int32_t ndirs,
+                         const int32_t* dims_1based);
+
+/* ============================ solvers ========================================= */
+#define RLS_MAX_TV_DIMS 4
+
+/* One regularisation term after the Julia-side decorator plumbing has been resolved
+ * (λ(reg) incl. normalisation factor; Regularization/*.jl stays in the host). */
+typedef struct {
+  int32_t kind;              /* RLS_REG_*                                          */
+  int32_t lambda_is_f64;     /* λ typed Float64 upstream: thresholds formed in double then convert(T,·) */
+  double lambda;             /* λ(reg)                                             */
+  int64_t slices;            /* L21                                                */
+  int32_t tv_ndims;          /* TV: image shape / directions / FGP iterations      */
+  int32_t tv_ndirs;
+  int64_t tv_shape[RLS_MAX_TV_DIMS];
+  int32_t tv_dims[RLS_MAX_TV_DIMS];
+  int32_t tv_iterations;
+  int32_t trafo;             /* ADMM regTrafo: RLS_TRAFO_*; gradient uses tv_shape/tv_dims */
+  float rho;                 /* ADMM penalty for this term                         */
+  int32_t _pad;
+} rls_reg_desc;
+
+/* Constructor keywords of FISTA.jl:57-67, POGM.jl:75-86, OptISTA.jl:62-71,
+ * CGNR.jl:48-53, ADMM.jl:80-94 after `rT(...)` conversion. */
+typedef struct {
+  int32_t kind;              /* RLS_FISTA ...                                      */
+  int32_t iterations;
+  int32_t restart;           /* 0 = :none, 1 = :gradient (FISTA, POGM)             */
+  int32_t proj_mask;         /* RLS_PROJ_* applied after prox (CGNR: at termination) */
+  float rho;                 /* step size (FISTA/POGM/OptISTA)                     */
+  float theta;
+  float sigma_fac;           /* POGM                                               */
+  float rel_tol;
+  float abs_tol;             /* ADMM                                               */
+  float tol_inner;           /* ADMM cg! reltol                                    */
+  int32_t iterations_cg;     /* ADMM                                               */
+  int32_t vary_rho;          /* ADMM RLS_VARY_RHO_*                                */
+  int32_t n_reg;             /* 1 (ADMM: 1..4)                                     */
+  int32_t _pad;
+  rls_reg_desc reg[4];
+} rls_solver_desc;
+
+/* Scalars of the solver state structs (FISTAState FISTA.jl:15-27, POGMState POGM.jl:15-36,
+ * OptISTAState OptISTA.jl:15-33, CGNRState CGNR.jl:13-24, ADMMState ADMM.jl:19-46) */
+typedef struct {
+  int32_t iteration;
+  int32_t done;              /* done(solver,state) evaluated for the NEXT iterate   */
+  float rho, theta, theta_old, theta_n, alpha, beta, gamma, gamma_old, sigma;
+  float norm_x0;             /* FISTA norm_x₀ / CGNR z0                             */
+  float rel_res_norm;        /* FISTA-family; CGNR: ‖r‖/z0                          */
+  float res_norm;            /* ‖res‖ (solverconvergence)                           */
+  float cg_alpha[2], cg_beta[2], cg_zeta[2];      /* CGNR αl, βl, ζl (Tc)           */
+  float admm_rk[4], admm_sk[4], admm_eps_pri[4], admm_eps_dua[4], admm_delta[4], admm_rho[4];
+  float admm_sigma_abs;
+  int32_t cg_iterations_last;                     /* ADMM: inner CG steps of the last outer iteration */
+  int32_t cg_iterations_total;
+  int32_t _pad;
+} rls_solver_scalars;
+
+/* createLinearSolver(S, A; AHA=op, kwargs...) RegularizedLeastSquares.jl:288-294.
+ * A may be NULL when only AHA is supplied (FISTA.jl:55); then b is A'b (FISTA.jl:112). */
+int32_t rls_solver_create(rls_mat_t A, rls_normal_t AHA, const rls_solver_desc* desc, rls_solver_t* out);
+int32_t rls_solver_destroy(rls_solver_t s);
+/* update λ / ρ after host-side normalisation in init! (FISTA.jl:128) without re-creating */
+int32_t rls_solver_set_reg(rls_solver_t s, int32_t idx, const rls_reg_desc* reg);
+/* init!(solver, state, b; x0): FISTA.jl:110-129, POGM.jl:138-164, OptISTA.jl:128-155,
+ * CGNR.jl:107-130, ADMM.jl:191-220.  b and x0 are device vectors (x0 may be NULL = 0). */
+int32_t rls_solver_init(rls_solver_t s, rls_vec_t b, rls_vec_t x0);
+/* iterate(solver, state): FISTA.jl:139-185, POGM.jl:173-237, OptISTA.jl:164-204,
+ * CGNR.jl:143-178, ADMM.jl:230-322.  *advanced = 0 when done() was already true
+ * (Julia `nothing`).  Synchronises to return the scalars. */
+int32_t rls_solver_iterate(rls_solver_t s, int32_t* advanced, rls_solver_scalars* scalars);
+/* the `for _ in enumerate(solver)` loop of solve! for an initialised solver: enqueue the
+ * remaining iterations with device-side done() gating, synchronise once. */
+int32_t rls_solver_run(rls_solver_t s, int32_t* iterations_done, rls_solver_scalars* scalars);
+/* callback-free solve!: enqueue up to `iterations` iterations with device-side
+ * done() gating (no host round trip per iteration), then synchronise once.
+ * RegularizedLeastSquares.jl:103-117 with the default no-op callback. */
+int32_t rls_solver_solve(rls_solver_t s, rls_vec_t b, rls_vec_t x0, int32_t* iterations_done,
+                         rls_solver_scalars* scalars);
+/* same, host buffers in and out (b: length m or n host elements, x: length n) */
+int32_t rls_solver_solve_host(rls_solver_t s, const void* b_host, int64_t b_len, void* x_host, int64_t x_len,
+                              int32_t* iterations_done, rls_solver_scalars* scalars);
+int32_t rls_solver_scalars_get(rls_solver_t s, rls_solver_scalars* scalars);
+/* state vectors by name: "x","x0","xold","res","y","z","zold","w","p","v","beta","beta_y","z0".."u0".. (borrowed handle) */
+int32_t rls_solver_vec(rls_solver_t s, const char* name, rls_vec_t* out);
+
+/* ---- multi right-hand-side solve (MultiThreading.jl:30-80) ---------------------- */
+/* K independent states sharing A; B is m×K column-major on the host, X n×K out.
+ * Per-column done() masks are kept on the device; iterations run until no column
+ * is active.  iterations_done[k] returns each column's count. */
+int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_host, int64_t ldb, int32_t K, void* X_host,
+                                    int64_t ldx, int32_t* iterations_done);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLS_B200_H */

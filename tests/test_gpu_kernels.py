@@ -1,0 +1,177 @@
+"""GPU parity of the building blocks against NumPy / the oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle.philox import philox_matrix, philox_vector, IH4, UNIFORM01
+from util import rel, rand_matrix, rand_vector
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float32, np.complex64]
+# (m, n): aligned, ragged rows (m % 4 != 0), single row / column, tall, wide
+SHAPES = [(256, 512), (1023, 771), (1, 17), (19, 1), (4100, 300), (130, 6000), (8192 + 8, 1536)]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_philox_bit_exact(rls, ctx, dtype):
+    A = rls.B200Matrix.philox(dtype, 300, 70, seed=99, scale=0.25, ctx=ctx).to_numpy()
+    assert np.array_equal(A, philox_matrix(dtype, 300, 70, 99, IH4, 0.25))
+    # a row shard regenerates exactly its rows of the global matrix
+    S = rls.B200Matrix.philox(dtype, 100, 70, seed=99, scale=0.25, row_offset=120, m_global=300, ctx=ctx).to_numpy()
+    assert np.array_equal(S, A[120:220])
+    v = rls.B200Vector(ctx, dtype, 1000).fill_philox(5, stream=3, dist=0, scale=2.0).to_numpy()
+    assert np.array_equal(v, philox_vector(dtype, 1000, 5, 3, UNIFORM01, 2.0))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", SHAPES)
+def test_gemv_n_c(rls, ctx, dtype, shape):
+    m, n = shape
+    A, _ = rand_matrix(dtype, m, n, 11)
+    x = rand_vector(dtype, n, 12)
+    y = rand_vector(dtype, m, 13)
+    Ad = rls.B200Matrix.from_numpy(A, ctx)
+    assert np.array_equal(Ad.to_numpy(), A)
+    yd = Ad.mul(rls.B200Vector.from_numpy(x, ctx)).to_numpy()
+    gd = Ad.adjoint_mul(rls.B200Vector.from_numpy(y, ctx)).to_numpy()
+    A64 = A.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
+    assert rel(yd, A64 @ x) < 2e-6
+    assert rel(gd, A64.conj().T @ y) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("form", ["twopass", "onepass", "gram"])
+@pytest.mark.parametrize("shape", [(256, 512), (1023, 772), (515, 2048), (64, 4096), (3000, 1000)])
+def test_normal_operator_forms(rls, ctx, dtype, form, shape):
+    m, n = shape
+    A, _ = rand_matrix(dtype, m, n, 21)
+    x = rand_vector(dtype, n, 22)
+    Ad = rls.B200Matrix.from_numpy(A, ctx)
+    op = rls.B200NormalOp(Ad, form=form)
+    assert op.form == form
+    xd = rls.B200Vector.from_numpy(x, ctx)
+    g1 = op.apply(xd).to_numpy()
+    g2 = op.apply(xd).to_numpy()           # second launch: tickets / flags / tags must have reset
+    A64 = A.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
+    ref = A64.conj().T @ (A64 @ x)
+    assert rel(g1, ref) < 3e-6
+    assert np.array_equal(g1, g2), "normal operator is not deterministic run to run"
+
+
+@pytest.mark.parametrize("lpc", [8, 16, 32])
+@pytest.mark.parametrize("lag", [1, 3])
+def test_onepass_variants(rls, ctx, lpc, lag, monkeypatch):
+    monkeypatch.setenv("RLS_ONEPASS_LPC", str(lpc))
+    monkeypatch.setenv("RLS_ONEPASS_LAG", str(lag))
+    for dtype in DTYPES:
+        m, n = 2052, 9000
+        A, _ = rand_matrix(dtype, m, n, 31)
+        x = rand_vector(dtype, n, 32)
+        op = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx), form="onepass")
+        g = op.apply(rls.B200Vector.from_numpy(x, ctx)).to_numpy()
+        A64 = A.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
+        assert rel(g, A64.conj().T @ (A64 @ x)) < 3e-6
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_reductions(rls, ctx, dtype):
+    a = rand_vector(dtype, 100003, 41)
+    b = rand_vector(dtype, 100003, 42)
+    ad, bd = rls.B200Vector.from_numpy(a, ctx), rls.B200Vector.from_numpy(b, ctx)
+    assert abs(ad.norm() - np.linalg.norm(a.astype(np.complex128))) < 1e-9 * 400
+    assert abs(ad.asum() - np.sum(np.abs(a.astype(np.complex128)))) < 1e-3
+    assert abs(ad.dot(bd) - np.vdot(a.astype(np.complex128), b.astype(np.complex128))) < 1e-6 * 400
+    e = rls.B200Vector(ctx, dtype, 0)
+    assert e.norm() == 0.0
+    A, _ = rand_matrix(dtype, 301, 77, 43)
+    assert abs(rls.B200Matrix.from_numpy(A, ctx).frob2() - np.sum(np.abs(A.astype(np.complex128)) ** 2)) < 1e-6 * 77
+
+
+# ---------------------------------------------------------------- proximal maps
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_prox_elementwise(rls, ctx, dtype):
+    x = rand_vector(dtype, 5000, 51)
+    x[::7] = 0
+    for lam in (np.float32(0.3), np.float32(0.0), 0.7):
+        a = x.copy(); b = x.copy()
+        rls.prox_(rls.L1Regularization(lam), a)
+        O.prox_(O.L1Regularization(lam), b)
+        assert rel(a, b) < 1e-6, "L1"
+        a = x.copy(); b = x.copy()
+        rls.prox_(rls.L2Regularization(lam), a)
+        O.prox_(O.L2Regularization(lam), b)
+        assert np.array_equal(a, b), "L2 is bit exact"
+    a = x.copy(); b = x.copy()
+    rls.prox_(rls.PositiveRegularization, a); O.prox_(O.PositiveRegularization(), b)
+    assert np.array_equal(a, b)
+    a = x.copy(); b = x.copy()
+    rls.prox_(rls.RealRegularization, a); O.prox_(O.RealRegularization(), b)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_prox_l1_bit_exact_vs_oracle(rls, ctx, dtype):
+    x = rand_vector(dtype, 4096, 52)
+    a = x.copy(); b = x.copy()
+    rls.prox_(rls.L1Regularization(np.float32(0.4)), a)
+    O.prox_(O.L1Regularization(np.float32(0.4)), b)
+    # every op individually rounded on both sides; complex modulus via double hypot
+    assert np.max(np.abs(a - b)) <= 2 * np.finfo(np.float32).eps * np.max(np.abs(b))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("slices", [1, 8, 5])
+def test_prox_l21(rls, ctx, dtype, slices):
+    x = rand_vector(dtype, 256 * slices, 53)
+    a = x.copy(); b = x.copy()
+    rls.prox_(rls.L21Regularization(np.float32(1.5), slices=slices), a)
+    O.prox_(O.L21Regularization(np.float32(1.5), slices=slices), b)
+    assert rel(a, b) < 1e-6
+    # all-zero group with λ = 0 -> 0/0 = NaN is preserved (reference quirk)
+    z = np.zeros(16, dtype)
+    rls.prox_(rls.L21Regularization(np.float32(0.0), slices=4), z)
+    assert np.all(np.isnan(z.real))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,dims", [((64, 48), None), ((64, 48), (1,)), ((64, 48), (2,)), ((300,), None),
+                                        ((12, 10, 9), None), ((12, 10, 9), (1, 3)), ((1, 40), None)])
+def test_gradient_op_and_tv(rls, ctx, dtype, shape, dims):
+    n = int(np.prod(shape))
+    x = rand_vector(dtype, n, 54)
+    dd = tuple(range(1, len(shape) + 1)) if dims is None else dims
+    G = rls.GradientOp(dtype, shape, dims)
+    Go = O.GradientOp(dtype, shape, dims)
+    assert G.rows == Go.rows
+    xd = rls.B200Vector.from_numpy(x, ctx)
+    gx = G.mul(xd)
+    assert np.array_equal(gx.to_numpy(), Go.mul(x))
+    g = rand_vector(dtype, G.rows, 55)
+    assert rel(G.tmul(rls.B200Vector.from_numpy(g, ctx)).to_numpy(), Go.tmul(g)) < 1e-6
+    for iters in (1, 10):
+        a = x.copy(); b = x.copy()
+        rls.prox_(rls.TVRegularization(np.float32(0.2), shape=shape, dims=dims, iterationsTV=iters), a)
+        O.prox_(O.TVRegularization(np.float32(0.2), shape=shape, dims=dd, iterationsTV=iters), b)
+        assert rel(a, b) < 2e-6, f"TV {shape} dims={dims} iters={iters}"
+
+
+def test_tv_denoises_piecewise_constant(rls, ctx):
+    """test/testProxMaps.jl:75-103 properties on the device path (Float32 edition)."""
+    rng = np.random.default_rng(1234)
+    N = 128
+    x = np.zeros((N, N), np.complex64, order="F")
+    for _ in range(5):
+        i, j = rng.integers(0, N, 2)
+        x[i:, j:] += np.float32(rng.standard_normal())
+    x = x.ravel(order="F")
+    sigma = np.float32(np.sum(np.abs(x)) / x.size * 0.05)
+    noisy = (x + sigma / np.sqrt(2.0) * (rng.standard_normal(N * N) + 1j * rng.standard_normal(N * N))).astype(np.complex64)
+    x_tv = noisy.copy()
+    rls.prox_(rls.TVRegularization(np.float32(2 * sigma), shape=(N, N)), x_tv)
+    x_l1 = noisy.copy()
+    rls.prox_(rls.L1Regularization(np.float32(2 * sigma)), x_l1)
+    assert np.linalg.norm(x - x_tv) <= np.linalg.norm(x - noisy)
+    assert np.linalg.norm(x - x_tv) <= np.linalg.norm(x - x_l1)
+    tv = lambda v: 2 * sigma * np.sum(np.abs(O.grad_op(v, (N, N), (1, 2))))
+    assert 0.5 * np.linalg.norm(noisy - x_tv) ** 2 + tv(x_tv) <= tv(noisy)

@@ -1,0 +1,260 @@
+"""Per-iterate parity of the CUDA solvers against the oracle (rel-L2 <= 1e-5, Float32 /
+ComplexF32 — the tolerance BASELINE.json's north_star states), identical iteration counts
+and stopping decisions, through the C ABI."""
+import numpy as np
+import pytest
+
+import oracle as O
+from util import rel, rand_matrix, rand_vector, sparse_truth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+DTYPES = [np.float32, np.complex64]
+
+
+def problem(dtype, m, n, seed=100, noise=1e-3):
+    A, _ = rand_matrix(dtype, m, n, seed)
+    xt = sparse_truth(dtype, n, seed + 1)
+    b = (A @ xt + noise * rand_vector(dtype, m, seed + 2)).astype(dtype)
+    return A, xt, b
+
+
+def rho_for(A):
+    return np.float32(0.95 / np.linalg.norm(A.astype(np.complex128), 2) ** 2)
+
+
+def stepwise(S, R, b, iters, what="x", tol=TOL):
+    """drive both through init!/iterate and compare after every iteration"""
+    S.init_(b); R.init(b)
+    worst = 0.0
+    for k in range(iters + 2):
+        a1, a2 = S.iterate(), R.iterate()
+        assert a1 == a2, f"stopping decision differs at iteration {k}: gpu={a1} oracle={a2}"
+        if not a1:
+            break
+        e = rel(getattr(S, what), getattr(R, what))
+        worst = max(worst, e)
+        assert e < tol, f"iterate {k + 1}: rel-L2 {e:.3e}"
+    assert S.iteration == R.iteration
+    return worst
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("solver", ["FISTA", "POGM", "OptISTA"])
+@pytest.mark.parametrize("restart", ["none", "gradient"])
+def test_proxgrad_l1_per_iterate(rls, ctx, dtype, solver, restart):
+    if solver == "OptISTA" and restart == "gradient":
+        pytest.skip("OptISTA has no restart keyword")
+    A, xt, b = problem(dtype, 384, 1024)
+    rho = rho_for(A)
+    lam = np.float32(2e-2)
+    kw = dict(iterations=40, rho=rho, relTol=0.0)
+    if solver != "OptISTA":
+        kw["restart"] = restart
+    S = rls.createLinearSolver(getattr(rls, solver), A, reg=rls.L1Regularization(lam), normal="twopass", **kw)
+    R = O.createLinearSolver(getattr(O, solver), A, reg=O.L1Regularization(lam), **kw)
+    stepwise(S, R, b, 40)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("form", ["twopass", "onepass", "gram"])
+def test_fista_forms_whole_solve(rls, ctx, dtype, form):
+    A, xt, b = problem(dtype, 1024, 4096)
+    rho = rho_for(A)
+    lam = np.float32(1e-2)
+    S = rls.FISTA(A, reg=rls.L1Regularization(lam), iterations=100, rho=rho, relTol=0.0, normal=form)
+    R = O.FISTA(A, reg=O.L1Regularization(lam), iterations=100, rho=rho, relTol=0.0)
+    x = rls.solve_(S, b)
+    xr = R.solve(b)
+    assert S.iteration == R.iteration == 100
+    assert rel(x, xr) < TOL
+    assert abs(S.state.rel_res_norm - R.rel_res_norm) <= 1e-4 * abs(R.rel_res_norm)
+    # whole-solve fast path == init!/iterate loop with a callback
+    trace = []
+    x2 = rls.solve_(S, b, callbacks=lambda s, it: trace.append(it))
+    assert trace == list(range(101))          # iterations+1 calls (test/testCallbacks.jl:13)
+    assert np.array_equal(x, x2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("lam", [np.float32(0), np.float32(1e-3), 1e-3])
+def test_cgnr_per_iterate(rls, ctx, dtype, lam):
+    A, xt, b = problem(dtype, 512, 256)
+    regs = lambda M: M.L2Regularization(lam)
+    S = rls.CGNR(A, reg=regs(rls), iterations=30, relTol=0.0, normal="twopass")
+    R = O.CGNR(A, reg=regs(O), iterations=30, relTol=0.0)
+    stepwise(S, R, b, 30, tol=5e-5)          # CG steering scalars amplify rounding (SURVEY 7 hard part 2)
+    assert rel(S.x, R.x) < 5e-5
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_cgnr_c1_shape_and_stop(rls, ctx, dtype):
+    """BASELINE configs[0]: CGNR + L2 on a wide system, U[0,1) entries (test/testSolvers.jl:25-27)."""
+    from oracle.philox import philox_matrix, philox_vector, UNIFORM01
+    m, n = 256, 1024
+    A = philox_matrix(dtype, m, n, 12345, UNIFORM01, 1.0)
+    xt = philox_vector(dtype, n, 12345, 5, UNIFORM01)
+    b = (A @ xt).astype(dtype)
+    lam = np.float32(1e-3)
+    for relTol, iters in ((0.0, 50), (1e-3, 50)):
+        S = rls.CGNR(A, reg=rls.L2Regularization(lam), iterations=iters, relTol=relTol)
+        R = O.CGNR(A, reg=O.L2Regularization(lam), iterations=iters, relTol=relTol)
+        x = rls.solve_(S, b); xr = R.solve(b)
+        assert S.iteration == R.iteration, "identical iteration counts / stopping decisions"
+        assert rel(x, xr) < 2e-4
+        assert rel(A @ x, b) < 5e-2
+    # iteration cap min(iterations, n) (CGNR.jl:185) and projections at termination only
+    S = rls.CGNR(A[:, :8].copy(), reg=[rls.L2Regularization(lam), rls.PositiveRegularization()], iterations=50, relTol=0.0)
+    R = O.CGNR(A[:, :8].copy(), reg=[O.L2Regularization(lam), O.PositiveRegularization()], iterations=50, relTol=0.0)
+    x = rls.solve_(S, b); xr = R.solve(b)
+    assert S.iteration == R.iteration == 8
+    if np.dtype(dtype).kind == "c":
+        assert np.all(x.imag == 0)
+    assert np.all(x.real >= 0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fista_reltol_stop_and_projection(rls, ctx, dtype):
+    A, xt, b = problem(dtype, 300, 200, noise=0.0)
+    rho = rho_for(A)
+    lam = np.float32(1e-4)
+    for proj in ("Positive", "Real"):
+        S = rls.FISTA(A, reg=[rls.L1Regularization(lam), getattr(rls, proj + "Regularization")()], iterations=300,
+                      rho=rho, relTol=1e-3)
+        R = O.FISTA(A, reg=[O.L1Regularization(lam), getattr(O, proj + "Regularization")()], iterations=300,
+                    rho=rho, relTol=1e-3)
+        x = rls.solve_(S, b); xr = R.solve(b)
+        assert 0 < R.iteration < 300, "the tolerance must trigger before the cap for this test to mean anything"
+        assert S.iteration == R.iteration
+        assert rel(x, xr) < TOL
+
+
+@pytest.mark.parametrize("solver", ["FISTA", "POGM", "OptISTA"])
+@pytest.mark.parametrize("regname", ["L2", "L21", "TV"])
+def test_proxgrad_other_regs(rls, ctx, solver, regname):
+    dtype = np.complex64
+    A, xt, b = problem(dtype, 256, 32 * 24)
+    rho = rho_for(A)
+    mk = {"L2": lambda M: M.L2Regularization(np.float32(5e-2)),
+          "L21": lambda M: M.L21Regularization(np.float32(5e-3), slices=8),
+          "TV": lambda M: M.TVRegularization(np.float32(5e-3), shape=(32, 24))}[regname]
+    S = getattr(rls, solver)(A, reg=mk(rls), iterations=25, rho=rho, relTol=0.0, normal="twopass")
+    R = getattr(O, solver)(A, reg=mk(O), iterations=25, rho=rho, relTol=0.0)
+    what = "x"
+    stepwise(S, R, b, 25, what=what, tol=2e-5)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("variant", ["l1", "l1_vary_balance", "l1_vary_pnp", "tv_identity", "l1_gradient", "two_terms"])
+def test_admm(rls, ctx, dtype, variant):
+    shape = (24, 20)
+    n = shape[0] * shape[1]
+    A, xt, b = problem(dtype, 320, n)
+    kw = dict(iterations=15, iterationsCG=10, rho=0.1, absTol=0.0, relTol=0.0)
+    def mk(M):
+        if variant == "l1":
+            return dict(reg=M.L1Regularization(np.float32(1e-2)))
+        if variant == "l1_vary_balance":
+            return dict(reg=M.L1Regularization(np.float32(1e-2)), vary_rho="balance")
+        if variant == "l1_vary_pnp":
+            return dict(reg=M.L1Regularization(np.float32(1e-2)), vary_rho="PnP")
+        if variant == "tv_identity":
+            return dict(reg=M.TVRegularization(np.float32(1e-2), shape=shape))
+        if variant == "l1_gradient":
+            return dict(reg=M.L1Regularization(np.float32(1e-2)), regTrafo=M.GradientOp(dtype, shape))
+        return dict(reg=[M.L1Regularization(np.float32(1e-2)), M.L1Regularization(1e-3)],
+                    regTrafo=[None, M.GradientOp(dtype, shape)], rho=[0.1, 0.2])
+    k1, k2 = dict(kw), dict(kw)
+    k1.update(mk(rls)); k2.update(mk(O))
+    S = rls.ADMM(A, normal="twopass", **k1)
+    R = O.ADMM(A, **k2)
+    S.init_(b); R.init(b)
+    for k in range(15):
+        a1, a2 = S.iterate(), R.iterate()
+        assert a1 == a2 == True
+        assert S._scalars.cg_iterations_last == R.cg_iters[-1], f"inner CG count differs at outer {k}"
+        assert rel(S.x, R.x) < 5e-5, f"outer {k}"
+    conv = S.convergence()
+    assert np.allclose(conv["primal"], R.rk, rtol=2e-3)
+    assert np.allclose(conv["dual"], R.sk, rtol=2e-3)
+    assert S.iterate() is False and R.iterate() is False
+
+
+def test_admm_docstring_kat_float32(rls, ctx):
+    """src/RegularizedLeastSquares.jl:44-61, Float32 edition of the one true KAT."""
+    A = np.array([[0.831658, 0.96717], [0.383056, 0.39043], [0.820692, 0.08118]])
+    x = np.array([0.5932234523399985, 0.2697534345340015])
+    b = A @ x
+    S = rls.ADMM(A.astype(np.float32), reg=rls.L1Regularization(0.0001))
+    xg = rls.solve_(S, b.astype(np.float32))
+    assert np.allclose(xg, [0.5932171509222105, 0.26971370566079866], rtol=2e-4)
+    R = O.ADMM(A.astype(np.float32), reg=O.L1Regularization(0.0001))
+    assert rel(xg, R.solve(b.astype(np.float32))) < 1e-5
+
+
+@pytest.mark.parametrize("solver", ["FISTA", "CGNR", "ADMM", "POGM", "OptISTA"])
+def test_multi_rhs(rls, ctx, solver):
+    """test/testMultiThreading.jl: batched == sequential, and a vector solve still works afterwards."""
+    dtype = np.complex64
+    A, _, _ = problem(dtype, 200, 96)
+    X = np.stack([sparse_truth(dtype, 96, 300 + k, every=7) for k in range(5)], axis=1)
+    B = (A @ X).astype(dtype)
+    kw = dict(iterations=30)
+    if solver in ("FISTA", "POGM", "OptISTA"):
+        kw.update(rho=rho_for(A), reg=rls.L1Regularization(np.float32(1e-4)))
+    S = rls.createLinearSolver(getattr(rls, solver), A, **kw)
+    Xb = rls.solve_(S, B)
+    Xs = np.stack([rls.solve_(S, B[:, k].copy()) for k in range(5)], axis=1)
+    assert np.array_equal(Xb, Xs)
+    xv = rls.solve_(S, B[:, 0].copy())
+    assert np.array_equal(xv, Xs[:, 0])
+
+
+def test_measurement_based_normalization(rls, ctx):
+    dtype = np.complex64
+    A, xt, b = problem(dtype, 256, 512)
+    rho = rho_for(A)
+    for name in ("FISTA", "CGNR", "ADMM"):
+        if name == "CGNR":
+            kw1 = dict(reg=rls.L2Regularization(np.float32(1e-2))); kw2 = dict(reg=O.L2Regularization(np.float32(1e-2)))
+        else:
+            kw1 = dict(reg=rls.L1Regularization(np.float32(1e-2))); kw2 = dict(reg=O.L1Regularization(np.float32(1e-2)))
+        if name == "FISTA":
+            kw1["rho"] = kw2["rho"] = rho
+        S = getattr(rls, name)(A, iterations=20, normalizeReg=rls.MeasurementBasedNormalization(), **kw1)
+        R = getattr(O, name)(A, iterations=20, normalizeReg=O.MeasurementBasedNormalization(), **kw2)
+        x = rls.solve_(S, b); xr = R.solve(b)
+        assert rel(x, xr) < 5e-5, name
+    S = rls.FISTA(A, iterations=20, rho=rho, reg=rls.L1Regularization(np.float32(1e-2)),
+                  normalizeReg=rls.SystemMatrixBasedNormalization())
+    R = O.FISTA(A, iterations=20, rho=rho, reg=O.L1Regularization(np.float32(1e-2)),
+                normalizeReg=O.SystemMatrixBasedNormalization())
+    assert rel(rls.solve_(S, b), R.solve(b)) < TOL
+
+
+def test_power_iterations_and_default_rho(rls, ctx):
+    dtype = np.complex64
+    A, xt, b = problem(dtype, 256, 512)
+    Ad = rls.B200Matrix.from_numpy(A, ctx)
+    op = rls.B200NormalOp(Ad, form="twopass")
+    b0 = rand_vector(dtype, 512, 77)
+    lam_gpu = op.power_iterations(rls.B200Vector.from_numpy(b0, ctx))
+    lam_ref = O.power_iterations(O.NormalOp(A), b0)
+    assert abs(lam_gpu - lam_ref) < 1e-4 * lam_ref
+    S = rls.FISTA(Ad, reg=rls.L1Regularization(np.float32(1e-3)), iterations=50)     # default rho
+    x = rls.solve_(S, b)
+    assert np.all(np.isfinite(x)) and rel(A @ x, b) < 0.5
+
+
+def test_errors_are_reference_errors(rls, ctx):
+    A = np.ones((8, 8), np.float32)
+    with pytest.raises(ValueError, match="does not allow for more additional regularization terms"):
+        rls.FISTA(A, reg=[rls.L1Regularization(1.0), rls.L2Regularization(1.0)], rho=0.1)
+    with pytest.raises(TypeError, match="Float32 / ComplexF32"):
+        rls.FISTA(np.ones((8, 8), np.float64), rho=0.1)
+    S = rls.FISTA(A, rho=0.1)
+    with pytest.raises(rls.RlsError):
+        rls.solve_(S, np.ones(5, np.float32))     # wrong length b: status code, no abort
+    with pytest.warns(UserWarning, match="filtered out"):
+        rls.createLinearSolver(rls.CGNR, A, iterations=3, rho=0.1)
