@@ -20,6 +20,13 @@
 // warps per SM.
 #include "rls_common.cuh"
 
+// TMA / shared-memory-resident implementation (rls_normal_tma.cu)
+struct TmaPlan;
+int32_t rls_tma_plan_create(rls_ctx_s* c, rls_mat_s* A, TmaPlan** out);
+int32_t rls_tma_apply(TmaPlan* p, const void* x, void* g, const int* gate);
+int32_t rls_tma_check_abort(TmaPlan* p);
+void rls_tma_plan_destroy(TmaPlan* p);
+
 namespace {
 
 constexpr int OP_CWARPS = 8;                       // compute warps per CTA
@@ -333,7 +340,8 @@ struct rls_normal_s {
   bool own_G = true; // false when the caller supplied AHA as a matrix (FISTA(; AHA=...), FISTA.jl:55)
   int64_t n_ = 0;
   int32_t dtype_ = 0;
-  // one-pass
+  // one-pass: TMA/shared-memory-resident kernel when supported, else the L2-lag kernel below
+  TmaPlan* tma = nullptr;
   OnepassWs ws{};
   void* ws_mem = nullptr;
   int op_grid = 0, op_lpc = 0, op_maxc = 0, op_cpw = 0, op_lag = 2, op_hint = 1;
@@ -456,17 +464,22 @@ extern "C" int32_t rls_normal_create(rls_mat_t A, int32_t form, rls_normal_t* ou
   const double bytes = (double)A->m * (double)A->n * (double)rls_elem_size(A->dtype);
   if (form == RLS_NORMAL_AUTO) {
     // the panel kernel pays off once A is far larger than L2; small systems stay two-pass
-    form = (bytes >= 4.0 * (double)(A->ctx->l2_bytes ? A->ctx->l2_bytes : ((size_t)64 << 20)) && plan_onepass(op))
-               ? RLS_NORMAL_ONEPASS : RLS_NORMAL_TWOPASS;
+    form = (bytes >= 4.0 * (double)(A->ctx->l2_bytes ? A->ctx->l2_bytes : ((size_t)64 << 20))) ? RLS_NORMAL_ONEPASS
+                                                                                               : RLS_NORMAL_TWOPASS;
   }
   if (form == RLS_NORMAL_ONEPASS) {
-    if (!plan_onepass(op)) {
-      delete op;
-      rls_set_error("one-pass normal operator does not support n=%lld on this device (too many columns per warp)", (long long)A->n);
-      return RLS_ERR_UNSUPPORTED;
+    const char* impl = getenv("RLS_ONEPASS_IMPL");
+    const bool want_l2 = impl && strcmp(impl, "l2") == 0;
+    if (!want_l2 && rls_tma_plan_create(A->ctx, A, &op->tma) != RLS_OK) op->tma = nullptr;
+    if (!op->tma) {
+      if (!plan_onepass(op)) {
+        delete op;
+        rls_set_error("one-pass normal operator does not support n=%lld on this device", (long long)A->n);
+        return RLS_ERR_UNSUPPORTED;
+      }
+      int32_t s = alloc_onepass_ws(op);
+      if (s != RLS_OK) { delete op; return s; }
     }
-    int32_t s = alloc_onepass_ws(op);
-    if (s != RLS_OK) { delete op; return s; }
   }
   op->form = form;
   if (form == RLS_NORMAL_GRAM) {
@@ -488,6 +501,7 @@ extern "C" int32_t rls_normal_destroy(rls_normal_t op) {
   if (op->gpart) rls_vec_destroy(op->gpart);
   if (op->G && op->own_G) rls_mat_destroy(op->G);
   if (op->ws_mem) cudaFree(op->ws_mem);
+  if (op->tma) rls_tma_plan_destroy(op->tma);
   delete op;
   return RLS_OK;
 }
@@ -575,7 +589,8 @@ int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const in
       break;
     case RLS_NORMAL_ONEPASS:
       if (op->A->m == 0) { RLS_CUDA(cudaMemsetAsync(out, 0, op->A->n * rls_elem_size(op->A->dtype), c->stream)); break; }
-      RLS_TRY(launch_onepass(op, x, out, gate));
+      if (op->tma) RLS_TRY(rls_tma_apply(op->tma, x, out, gate));
+      else RLS_TRY(launch_onepass(op, x, out, gate));
       break;
     default:
       rls_set_error("bad normal-operator form");
@@ -593,6 +608,7 @@ int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const in
 
 int32_t rls_normal_check_abort(rls_normal_t op) {
   if (op->form != RLS_NORMAL_ONEPASS) return RLS_OK;
+  if (op->tma) return rls_tma_check_abort(op->tma);
   int flag = 0;
   RLS_CUDA(cudaMemcpyAsync(&flag, op->ws.abort_flag, sizeof(int), cudaMemcpyDeviceToHost, op->ctx->stream));
   RLS_CUDA(cudaStreamSynchronize(op->ctx->stream));

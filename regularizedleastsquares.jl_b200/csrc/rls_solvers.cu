@@ -752,7 +752,7 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L) {
       if (k == 0) { copy_kernel<T><<<g, EB, 0, st>>>(beta, P<T>(L.v[V_BETAY]), n, gate); c->launches++; }
       copy_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_XOLD]), P<T>(L.v[V_X]), n, gate);                    // xᵒˡᵈ = x   :243
       // cg!(x, AHA + Σ ρ Φ'Φ, β)   :244
-      fill_gated_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_CGU]), Elem<T>::zero(), n, gate);
+      fill_gated_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_CGU]), T{}, n, gate);
       c->launches += 2;
       RLS_TRY(composite_apply<T>(s, L, P<T>(L.v[V_X]), P<T>(L.v[V_CGC]), gate, false));
       admm_cg_init_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_CGR]), beta, P<T>(L.v[V_CGC]), n, S, part, tick);

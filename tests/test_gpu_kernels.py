@@ -59,9 +59,30 @@ def test_normal_operator_forms(rls, ctx, dtype, form, shape):
     assert np.array_equal(g1, g2), "normal operator is not deterministic run to run"
 
 
+@pytest.mark.parametrize("lpc", [8, 16])
+@pytest.mark.parametrize("stage_kb,lag", [(28, 6), (8, 1), (56, 6), (4, 2)])
+def test_onepass_tma_variants(rls, ctx, lpc, stage_kb, lag, monkeypatch):
+    """the TMA / shared-memory-resident kernel under different segment widths, stage sizes and lags"""
+    monkeypatch.setenv("RLS_TMA_LPC", str(lpc))
+    monkeypatch.setenv("RLS_TMA_STAGE_KB", str(stage_kb))
+    monkeypatch.setenv("RLS_TMA_LAG", str(lag))
+    for dtype in DTYPES:
+        for (m, n) in [(2052, 9000), (70, 33), (1, 5000), (4099, 20000)]:
+            A, _ = rand_matrix(dtype, m, n, 31)
+            x = rand_vector(dtype, n, 32)
+            op = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx), form="onepass")
+            xd = rls.B200Vector.from_numpy(x, ctx)
+            g = op.apply(xd).to_numpy()
+            A64 = A.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
+            assert rel(g, A64.conj().T @ (A64 @ x)) < 3e-6, (dtype, m, n)
+            assert np.array_equal(g, op.apply(xd).to_numpy())
+
+
 @pytest.mark.parametrize("lpc", [8, 16, 32])
 @pytest.mark.parametrize("lag", [1, 3])
 def test_onepass_variants(rls, ctx, lpc, lag, monkeypatch):
+    """the L2-lag fallback kernel (used when the TMA kernel cannot describe the matrix)"""
+    monkeypatch.setenv("RLS_ONEPASS_IMPL", "l2")
     monkeypatch.setenv("RLS_ONEPASS_LPC", str(lpc))
     monkeypatch.setenv("RLS_ONEPASS_LAG", str(lag))
     for dtype in DTYPES:

@@ -1,0 +1,223 @@
+"""Pins the CPU oracle against every known answer / acceptance property the reference
+holds for the hot path: the solve! docstring KAT, the getting-started CGNR
+example, the 256-point DFT compressed-sensing problem of test/testSolvers.jl, the prox
+property tests of test/testProxMaps.jl and the multi-RHS test.  Runs on CPU."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle.philox import philox4x32_10
+
+
+def test_admm_docstring_kat():
+    """src/RegularizedLeastSquares.jl:44-61 — the one exact known answer upstream."""
+    A = np.array([[0.831658, 0.96717], [0.383056, 0.39043], [0.820692, 0.08118]])
+    x = np.array([0.5932234523399985, 0.2697534345340015])
+    b = A @ x
+    for mode in ("gram", "lazy"):
+        S = O.ADMM(A, reg=O.L1Regularization(0.0001), normal=mode)
+        xa = O.solve_(S, b)
+        assert np.allclose(xa, [0.5932171509222105, 0.26971370566079866], rtol=0, atol=1e-12)
+        assert S.iteration == 10
+
+
+def test_philox_known_answers():
+    """Random123 KAT vectors for philox4x32_10."""
+    z = np.zeros(1, np.uint32); f = np.full(1, 0xFFFFFFFF, np.uint32)
+    assert [int(v[0]) for v in philox4x32_10(z, z, z, z, 0, 0)] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert [int(v[0]) for v in philox4x32_10(f, f, f, f, 0xFFFFFFFF, 0xFFFFFFFF)] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+
+
+def test_cgnr_getting_started():
+    """docs/src/literate/examples/getting_started.jl:29-38,49-51: 32x16 Float64, 32 iterations, rtol 1e-3."""
+    rng = np.random.default_rng(0)
+    A = rng.random((32, 16)); x = rng.random(16); b = A @ x
+    xa = O.solve_(O.createLinearSolver(O.CGNR, A, iterations=32), b)
+    assert np.allclose(xa, x, rtol=1e-3)
+    xa = O.solve_(O.createLinearSolver(O.CGNR, A, iterations=32, reg=O.L2Regularization(0.0001)), b)
+    assert np.allclose(xa, x, rtol=1e-2)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
+def test_all_solvers_3x2(dtype):
+    """test/testSolvers.jl:3-43: 3x2 systems, rtol 0.1."""
+    rng = np.random.default_rng(12345)
+    A = rng.random((3, 2)).astype(dtype); x = rng.random(2).astype(dtype)
+    if np.dtype(dtype).kind == "c":
+        A = (A + 1j * rng.random((3, 2))).astype(dtype); x = (x + 1j * rng.random(2)).astype(dtype)
+    b = A @ x
+    for solver in (O.CGNR, O.FISTA, O.POGM, O.OptISTA, O.ADMM):
+        S = O.createLinearSolver(solver, A, iterations=200, normal="gram", bogus_keyword=1)
+        xa = O.solve_(S, b)
+        assert np.linalg.norm(xa - x) <= 0.1 * np.linalg.norm(x), solver.__name__
+        # AHA-only interface (test/testSolvers.jl:45-65)
+        S = O.createLinearSolver(solver, None, AHA=A.conj().T @ A, iterations=200)
+        assert np.linalg.norm(O.solve_(S, A.conj().T @ b) - x) <= 0.1 * np.linalg.norm(x)
+
+
+@pytest.mark.parametrize("elType", [np.float32, np.float64])
+def test_convex_dft_compressed_sensing(elType):
+    """test/testSolvers.jl:67-171.  (Julia's Random.seed!(12345) stream cannot be reproduced
+    here; the instance is drawn from NumPy's generator instead.)"""
+    rng = np.random.default_rng(1)
+    N = 256
+    F = (np.exp(-2j * np.pi * np.outer(np.arange(N), np.arange(N)) / N) / np.sqrt(N))
+    x = np.zeros(N)
+    for _ in range(3):
+        x[rng.integers(0, N)] = rng.random()
+    b = F @ x
+    idx = np.sort(np.unique(rng.integers(0, N, N // 2)))
+    ctype = np.complex128      # upstream F and b are ComplexF64 for every elType; elType only types λ
+    b = b[idx].astype(ctype); F = F[idx, :].astype(ctype)
+    for solver in (O.POGM, O.OptISTA, O.FISTA, O.ADMM):
+        reg = O.L1Regularization(elType(1e-3))
+        S = O.createLinearSolver(solver, F, reg=reg, iterations=200, normalizeReg=O.NoNormalization())
+        xa = O.solve_(S, b)
+        assert np.linalg.norm(x - xa) <= 0.1 * np.linalg.norm(x), solver.__name__
+        if solver in (O.POGM, O.FISTA):
+            S = O.createLinearSolver(solver, F, reg=reg, iterations=200, restart="gradient")
+            assert np.linalg.norm(x - O.solve_(S, b)) <= 0.1 * np.linalg.norm(x)
+        # invariance to the scale of F with MeasurementBasedNormalization (:108-124)
+        reg2 = O.L1Regularization(elType(reg.lam * len(b) / np.sum(np.abs(b))))
+        S = O.createLinearSolver(solver, (F * 1e3).astype(ctype), reg=reg2, iterations=200,
+                                 normalizeReg=O.MeasurementBasedNormalization())
+        xa = O.solve_(S, b) * 1e3
+        assert np.linalg.norm(x - xa) <= 0.1 * np.linalg.norm(x), solver.__name__ + " rescaled"
+    # :127-171 — rho = 1e6 and 1e-6 with :balance, rho = 1e-6 with :PnP (it only ever increases rho)
+    for rho, vary in ((1e6, "balance"), (1e-6, "balance"), (1e-6, "PnP")):
+        S = O.createLinearSolver(O.ADMM, F, reg=O.L1Regularization(elType(1e-3)), iterations=200, rho=rho, vary_rho=vary)
+        assert np.linalg.norm(x - O.solve_(S, b)) <= 0.1 * np.linalg.norm(x), (rho, vary)
+
+
+def test_prox_l2_l1():
+    """test/testProxMaps.jl:2-39."""
+    rng = np.random.default_rng(1234)
+    N = 256
+    x = np.zeros(N)
+    x[rng.integers(0, N, 5)] = rng.random(5)
+    lam = 0.01
+    x_l2 = O.prox_(O.L2Regularization(lam), x.copy())
+    assert np.linalg.norm(x_l2 - x / (1 + 2 * lam)) / np.linalg.norm(x / (1 + 2 * lam)) < 1e-3
+    assert 0.5 * np.linalg.norm(x - x_l2) ** 2 + O.reg_norm(O.L2Regularization(lam), x_l2) <= O.reg_norm(O.L2Regularization(lam), x)
+    sig = 0.03
+    x = np.zeros(N)
+    x[rng.integers(0, N, 5)] = (1 - 2 * sig) * rng.random(5) + 2 * sig
+    s = np.sum(np.abs(x)) / N * sig
+    noisy = x + s / np.sqrt(2.0) * (rng.standard_normal(N) + 1j * rng.standard_normal(N))
+    x_l1 = O.prox_(O.L1Regularization(2 * s), noisy.copy())
+    assert np.linalg.norm(x - x_l1) <= np.linalg.norm(x - noisy)
+    assert np.linalg.norm(x - x_l1) / np.linalg.norm(x) < 0.1
+    r = O.L1Regularization(2 * s)
+    assert 0.5 * np.linalg.norm(noisy - x_l1) ** 2 + O.reg_norm(r, x_l1) <= O.reg_norm(r, noisy)
+
+
+def test_prox_l21():
+    """test/testProxMaps.jl:44-72 (N=256, 8 slices, last 2 noisy)."""
+    rng = np.random.default_rng(1234)
+    N, S, noisyS, sig = 256, 8, 2, 0.05
+    X = np.zeros((N, S), np.complex128)
+    for _ in range(5):
+        X[rng.integers(0, N), :] = (1 - 2 * sig) * rng.random(S) + 2 * sig
+    x = X.ravel(order="F")
+    s = np.sum(np.abs(x)) / x.size * sig
+    noisy = x.copy()
+    noisy[(S - noisyS) * N:] += s / np.sqrt(2.0) * (rng.standard_normal(N * noisyS) + 1j * rng.standard_normal(N * noisyS))
+    x_l1 = O.prox_(O.L1Regularization(2 * s), noisy.copy())
+    r = O.L21Regularization(2 * s, slices=S)
+    x_l21 = O.prox_(r, noisy.copy())
+    assert np.linalg.norm(x - x_l21) <= np.linalg.norm(x - noisy)
+    assert np.linalg.norm(x - x_l21) <= np.linalg.norm(x - x_l1)
+    assert np.linalg.norm(x - x_l21) / np.linalg.norm(x) < 0.05
+    obj = lambda v: 0.5 * np.linalg.norm(noisy - v) ** 2 + O.reg_norm(r, v)
+    assert obj(x_l21) <= O.reg_norm(r, noisy)
+    assert obj(x_l21) <= obj(x_l1)
+
+
+def test_prox_tv_2d_and_directional():
+    """test/testProxMaps.jl:75-136."""
+    rng = np.random.default_rng(1234)
+    N, sig = 64, 0.05
+    X = np.zeros((N, N), np.complex128)
+    for _ in range(5):
+        i, j = rng.integers(0, N, 2)
+        X[i:, j:] += rng.standard_normal()
+    x = X.ravel(order="F")
+    s = np.sum(np.abs(x)) / x.size * sig
+    noisy = x + s / np.sqrt(2.0) * (rng.standard_normal(N * N) + 1j * rng.standard_normal(N * N))
+    x_l1 = O.prox_(O.L1Regularization(2 * s), noisy.copy())
+    r = O.TVRegularization(2 * s, shape=(N, N))
+    x_tv = O.prox_(r, noisy.copy())
+    assert np.linalg.norm(x - x_tv) <= np.linalg.norm(x - noisy)
+    assert np.linalg.norm(x - x_tv) <= np.linalg.norm(x - x_l1)
+    obj = lambda v: 0.5 * np.linalg.norm(noisy - v) ** 2 + O.reg_norm(r, v)
+    assert obj(x_tv) <= O.reg_norm(r, noisy)
+    assert obj(x_tv) <= obj(x_l1)
+    # directional TV == column-wise 1-D TV (FGP both ways) to 1e-8
+    a = O.prox_(O.TVRegularization(2 * s, shape=(N, N), dims=1), noisy.copy()).reshape(N, N, order="F")
+    cols = noisy.reshape(N, N, order="F").copy()
+    for j in range(N):
+        cols[:, j] = O.prox_(O.TVRegularization(2 * s, shape=(N,), dims=1), cols[:, j].copy())
+    assert np.linalg.norm(a - cols) / np.linalg.norm(x) < 1e-8
+
+
+def test_prox_positive_real():
+    """test/testProxMaps.jl:139-151."""
+    rng = np.random.default_rng(1234)
+    x = rng.standard_normal(256) + 1j * rng.standard_normal(256)
+    xp = O.prox_(O.PositiveRegularization(), x.copy())
+    assert np.array_equal(xp, np.maximum(x.real, 0) + 0j)
+    xr = O.prox_(O.RealRegularization(), x.copy())
+    assert np.array_equal(xr, x.real + 0j)
+    xf = rng.standard_normal(16).astype(np.float32)
+    assert np.array_equal(O.prox_(O.PositiveRegularization(), xf.copy()), np.maximum(xf, 0))
+
+
+def test_multi_rhs_sequential_equals_columns():
+    """test/testMultiThreading.jl:1-20."""
+    rng = np.random.default_rng(3)
+    A = (rng.random((3, 2)) + 1j * rng.random((3, 2))).astype(np.complex64)
+    X = (rng.random((2, 4)) + 1j * rng.random((2, 4))).astype(np.complex64)
+    B = A @ X
+    for solver in (O.CGNR, O.FISTA, O.POGM, O.OptISTA, O.ADMM):
+        S = O.createLinearSolver(solver, A, iterations=100, normal="gram")
+        Xb = O.solve_(S, B)
+        assert np.linalg.norm(Xb - X) <= 0.1 * np.linalg.norm(X)
+        xv = O.solve_(S, B[:, 0].copy())
+        assert np.allclose(xv, Xb[:, 0])
+
+
+def test_callbacks_fire_iterations_plus_one():
+    """test/testCallbacks.jl:1-57 idiom: relTol = 0, iterations+1 invocations, last == solution."""
+    rng = np.random.default_rng(5)
+    A = rng.random((16, 8)).astype(np.float32); b = A @ rng.random(8).astype(np.float32)
+    S = O.FISTA(A, iterations=12, relTol=0.0, rho=np.float32(0.05))
+    seen = []
+    x = S.solve(b, callbacks=lambda s, it: seen.append((it, s.x.copy())))
+    assert [k for k, _ in seen] == list(range(13))
+    assert np.array_equal(seen[-1][1], x)
+
+
+def test_gram_and_lazy_forms_agree():
+    rng = np.random.default_rng(7)
+    A = (rng.standard_normal((40, 24)) + 1j * rng.standard_normal((40, 24))).astype(np.complex64)
+    b = (A @ rng.standard_normal(24)).astype(np.complex64)
+    for solver in (O.FISTA, O.CGNR):
+        kw = dict(iterations=15)
+        if solver is O.FISTA:
+            kw.update(rho=np.float32(0.005), reg=O.L1Regularization(np.float32(1e-3)), relTol=0.0)
+        a = solver(A, normal="gram", **kw).solve(b)
+        c = solver(A, normal="lazy", **kw).solve(b)
+        assert np.linalg.norm(a - c) <= 2e-4 * np.linalg.norm(c)
+
+
+def test_float32_scalar_recurrences_stay_float32():
+    A = np.eye(4, dtype=np.float32)
+    S = O.FISTA(A, iterations=5, rho=0.5, relTol=0.0)
+    S.solve(np.ones(4, np.float32))
+    assert type(S.theta) is np.float32 and type(S.rel_res_norm) is np.float32
+    S = O.OptISTA(A, iterations=5, rho=0.5, relTol=0.0)
+    S.solve(np.ones(4, np.float32))
+    assert type(S.gamma) is np.float32 and type(S.thetan) is np.float32
+    S = O.CGNR(A.astype(np.complex64), iterations=3)
+    S.solve(np.ones(4, np.complex64))
+    assert type(S.alpha) is np.complex64
