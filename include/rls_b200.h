@@ -154,6 +154,8 @@ int32_t rls_normal_create(rls_mat_t A, int32_t form, rls_normal_t* out);
 int32_t rls_normal_from_gram(rls_mat_t G, rls_normal_t* out);
 int32_t rls_normal_destroy(rls_normal_t op);
 int32_t rls_normal_form(rls_normal_t op, int32_t* form);
+/* kernel plan behind the operator, for diagnostics (e.g. "onepass/tma: grid=148 ...") */
+int32_t rls_normal_describe(rls_normal_t op, char* buf, int32_t len);
 /* mul!(res, AHA, x): FISTA.jl:152, POGM.jl:181, OptISTA.jl:182, CGNR.jl:151, cg! in ADMM.jl:244 */
 int32_t rls_normal_apply(rls_normal_t op, rls_vec_t x, rls_vec_t res);
 /* power_iterations(AHA, b; rtol, maxiter) Utils.jl:262-287; b0 replaces the randn start vector */

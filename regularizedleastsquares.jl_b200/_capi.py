@@ -108,6 +108,7 @@ SIGNATURES = {
     "rls_normal_from_gram": [_P, _PP],
     "rls_normal_destroy": [_P],
     "rls_normal_form": [_P, _PI32],
+    "rls_normal_describe": [_P, C.c_char_p, _I32],
     "rls_normal_apply": [_P, _P, _P],
     "rls_power_iterations": [_P, _P, _F64, _I32, _PF64],
     "rls_prox_l1": [_P, _F32],

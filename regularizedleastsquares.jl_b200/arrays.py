@@ -252,6 +252,11 @@ class B200NormalOp:
         capi.call("rls_normal_form", self.handle, C.byref(f))
         return _FORM_NAMES[f.value]
 
+    def describe(self):
+        buf = C.create_string_buffer(256)
+        capi.call("rls_normal_describe", self.handle, buf, 256)
+        return buf.value.decode()
+
     def apply(self, x, out=None):
         """mul!(res, AHA, x)"""
         out = B200Vector(self.ctx, self.dtype, self.n) if out is None else out

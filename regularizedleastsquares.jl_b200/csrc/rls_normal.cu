@@ -26,6 +26,7 @@ int32_t rls_tma_plan_create(rls_ctx_s* c, rls_mat_s* A, TmaPlan** out);
 int32_t rls_tma_apply(TmaPlan* p, const void* x, void* g, const int* gate);
 int32_t rls_tma_check_abort(TmaPlan* p);
 void rls_tma_plan_destroy(TmaPlan* p);
+void rls_tma_describe(TmaPlan* p, char* buf, int len);
 
 namespace {
 
@@ -463,14 +464,21 @@ extern "C" int32_t rls_normal_create(rls_mat_t A, int32_t form, rls_normal_t* ou
   op->dtype_ = A->dtype;
   const double bytes = (double)A->m * (double)A->n * (double)rls_elem_size(A->dtype);
   if (form == RLS_NORMAL_AUTO) {
-    // the panel kernel pays off once A is far larger than L2; small systems stay two-pass
-    form = (bytes >= 4.0 * (double)(A->ctx->l2_bytes ? A->ctx->l2_bytes : ((size_t)64 << 20))) ? RLS_NORMAL_ONEPASS
-                                                                                               : RLS_NORMAL_TWOPASS;
+    // Measured on B200 (profiles/): the two-sweep form runs at the HBM read roofline (7.3 TB/s), the
+    // one-pass panel kernels currently reach the same wall time with half the DRAM traffic.  AUTO
+    // therefore keeps the two-sweep form unless RLS_AUTO_ONEPASS=1 asks for the panel kernel on
+    // matrices far larger than L2.
+    const char* want = getenv("RLS_AUTO_ONEPASS");
+    const bool big = bytes >= 4.0 * (double)(A->ctx->l2_bytes ? A->ctx->l2_bytes : ((size_t)64 << 20));
+    form = (want && atoi(want) != 0 && big) ? RLS_NORMAL_ONEPASS : RLS_NORMAL_TWOPASS;
   }
   if (form == RLS_NORMAL_ONEPASS) {
     const char* impl = getenv("RLS_ONEPASS_IMPL");
     const bool want_l2 = impl && strcmp(impl, "l2") == 0;
-    if (!want_l2 && rls_tma_plan_create(A->ctx, A, &op->tma) != RLS_OK) op->tma = nullptr;
+    if (!want_l2 && rls_tma_plan_create(A->ctx, A, &op->tma) != RLS_OK) {
+      op->tma = nullptr;
+      if (getenv("RLS_VERBOSE")) fprintf(stderr, "[rls] TMA one-pass unavailable, using the L2-lag kernel: %s\n", rls_last_error());
+    }
     if (!op->tma) {
       if (!plan_onepass(op)) {
         delete op;
@@ -503,6 +511,18 @@ extern "C" int32_t rls_normal_destroy(rls_normal_t op) {
   if (op->ws_mem) cudaFree(op->ws_mem);
   if (op->tma) rls_tma_plan_destroy(op->tma);
   delete op;
+  return RLS_OK;
+}
+
+// human-readable description of the kernel plan behind this operator (diagnostics / bench config)
+extern "C" int32_t rls_normal_describe(rls_normal_t op, char* buf, int32_t len) {
+  RLS_CHECK_ARG(op && buf && len > 0, "NULL argument");
+  if (op->form == RLS_NORMAL_ONEPASS && op->tma) rls_tma_describe(op->tma, buf, len);
+  else if (op->form == RLS_NORMAL_ONEPASS)
+    snprintf(buf, len, "onepass/l2: grid=%d lanes/column=%d cols/lane<=%d cols/warp=%d lag=%d hint=%d", op->op_grid, op->op_lpc,
+             op->op_maxc, op->op_cpw, op->op_lag, op->op_hint);
+  else if (op->form == RLS_NORMAL_GRAM) snprintf(buf, len, "gram: dense %lldx%lld", (long long)op->n_, (long long)op->n_);
+  else snprintf(buf, len, "twopass: gemv_n + gemv_c");
   return RLS_OK;
 }
 

@@ -60,14 +60,15 @@ def test_normal_operator_forms(rls, ctx, dtype, form, shape):
 
 
 @pytest.mark.parametrize("lpc", [8, 16])
-@pytest.mark.parametrize("stage_kb,lag", [(28, 6), (8, 1), (56, 6), (4, 2)])
-def test_onepass_tma_variants(rls, ctx, lpc, stage_kb, lag, monkeypatch):
-    """the TMA / shared-memory-resident kernel under different segment widths, stage sizes and lags"""
+@pytest.mark.parametrize("stage_kb,lag,hint", [(32, 2, 1), (8, 1, 0), (64, 6, 1), (16, 3, 0)])
+def test_onepass_tma_variants(rls, ctx, lpc, stage_kb, lag, hint, monkeypatch):
+    """the TMA two-phase streaming kernel under different segment widths, stage sizes, lags and L2 hints"""
     monkeypatch.setenv("RLS_TMA_LPC", str(lpc))
     monkeypatch.setenv("RLS_TMA_STAGE_KB", str(stage_kb))
     monkeypatch.setenv("RLS_TMA_LAG", str(lag))
+    monkeypatch.setenv("RLS_TMA_HINT", str(hint))
     for dtype in DTYPES:
-        for (m, n) in [(2052, 9000), (70, 33), (1, 5000), (4099, 20000)]:
+        for (m, n) in [(2052, 9000), (70, 33), (1, 5000), (4099, 20000), (300, 70000)]:
             A, _ = rand_matrix(dtype, m, n, 31)
             x = rand_vector(dtype, n, 32)
             op = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx), form="onepass")

@@ -27,5 +27,4 @@ for _ in range(reps):
     op.apply(x, g)
 ms = ctx.timer_stop() / reps
 by = m * n * dtype.itemsize
-print(f"{form} {dtype} {m}x{n} env(LPC={os.environ.get('RLS_ONEPASS_LPC')},LAG={os.environ.get('RLS_ONEPASS_LAG')},"
-      f"HINT={os.environ.get('RLS_ONEPASS_HINT')}): {ms:.4f} ms/apply  {by / ms / 1e6:.1f} GB/s algorithmic", flush=True)
+print(f"[{op.describe()}] {form} {dtype} {m}x{n} : {ms:.4f} ms/apply  {by / ms / 1e6:.1f} GB/s algorithmic", flush=True)
