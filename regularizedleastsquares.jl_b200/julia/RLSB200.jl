@@ -1,0 +1,200 @@
+# RLSB200.jl — the reference-side binding of librls_b200.so.
+#
+# A package extension of RegularizedLeastSquares.jl that adds *methods*, not new API
+# (the extension point documented in docs/src/solvers.md:85-98 and used by
+# ext/RegularizedLeastSquaresGPUArraysExt): device array types `B200Matrix` / `B200Vector`,
+# `similar` so that `init!` re-allocates solver state on the device (src/FISTA.jl:94-103),
+# and `init!` / `iterate` / `solve!` / `prox!` methods that `ccall` the C ABI of
+# include/rls_b200.h.  NOT EXECUTED in this repository's CI: Julia is not installed in the
+# build image; the Python mirror (regularizedleastsquares.jl_b200/*.py) makes exactly the
+# same call sequence and is what the tests drive.
+module RLSB200
+
+using RegularizedLeastSquares
+using LinearAlgebra
+import RegularizedLeastSquares: init!, iterate, solve!, prox!, solversolution, solverconvergence,
+       L1Regularization, L2Regularization, L21Regularization, TVRegularization, PositiveRegularization,
+       RealRegularization, FISTA, POGM, OptISTA, CGNR, ADMM, λ, sink
+
+const LIB = get(ENV, "RLS_B200_LIB", "librls_b200.so")
+
+# ---- status handling: never let a C error pass silently --------------------------------------
+struct RlsError <: Exception
+  status::Int32
+  msg::String
+end
+function check(status::Int32)
+  status == 0 && return nothing
+  throw(RlsError(status, unsafe_string(ccall((:rls_last_error, LIB), Cstring, ()))))
+end
+
+# ---- enums of include/rls_b200.h ----------------------------------------------------------------
+const RLS_F32, RLS_C32 = Int32(0), Int32(1)
+const RLS_FISTA, RLS_POGM, RLS_OPTISTA, RLS_CGNR, RLS_ADMM = Int32.(0:4)
+const RLS_REG_NONE, RLS_REG_L1, RLS_REG_L2, RLS_REG_L21, RLS_REG_TV = Int32.(0:4)
+const RLS_PROJ_REAL, RLS_PROJ_POSITIVE = Int32(1), Int32(2)
+const RLS_NORMAL_AUTO = Int32(3)
+dtypecode(::Type{Float32}) = RLS_F32
+dtypecode(::Type{ComplexF32}) = RLS_C32
+dtypecode(T) = error("librls_b200 accelerates Float32 / ComplexF32 only, got $T (no CPU fallback)")
+
+# ---- POD structs (layout checked against the header by tests/test_abi.py) ----------------------
+struct RegDesc
+  kind::Int32; lambda_is_f64::Int32; lambda::Float64; slices::Int64
+  tv_ndims::Int32; tv_ndirs::Int32; tv_shape::NTuple{4,Int64}; tv_dims::NTuple{4,Int32}
+  tv_iterations::Int32; trafo::Int32; rho::Float32; _pad::Int32
+end
+struct SolverDesc
+  kind::Int32; iterations::Int32; restart::Int32; proj_mask::Int32
+  rho::Float32; theta::Float32; sigma_fac::Float32; rel_tol::Float32; abs_tol::Float32; tol_inner::Float32
+  iterations_cg::Int32; vary_rho::Int32; n_reg::Int32; _pad::Int32
+  reg::NTuple{4,RegDesc}
+end
+struct SolverScalars
+  iteration::Int32; done::Int32
+  rho::Float32; theta::Float32; theta_old::Float32; theta_n::Float32; alpha::Float32; beta::Float32
+  gamma::Float32; gamma_old::Float32; sigma::Float32; norm_x0::Float32; rel_res_norm::Float32; res_norm::Float32
+  cg_alpha::NTuple{2,Float32}; cg_beta::NTuple{2,Float32}; cg_zeta::NTuple{2,Float32}
+  admm_rk::NTuple{4,Float32}; admm_sk::NTuple{4,Float32}; admm_eps_pri::NTuple{4,Float32}
+  admm_eps_dua::NTuple{4,Float32}; admm_delta::NTuple{4,Float32}; admm_rho::NTuple{4,Float32}
+  admm_sigma_abs::Float32; cg_iterations_last::Int32; cg_iterations_total::Int32; _pad::Int32
+end
+
+# ---- context (one per device) -------------------------------------------------------------------
+mutable struct Context
+  handle::Ptr{Cvoid}
+  function Context(device::Integer = 0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rls_ctx_create, LIB), Int32, (Int32, Ref{Ptr{Cvoid}}), device, h))
+    finalizer(c -> ccall((:rls_ctx_destroy, LIB), Int32, (Ptr{Cvoid},), c.handle), new(h[]))
+  end
+end
+const DEFAULT_CTX = Ref{Union{Nothing,Context}}(nothing)
+ctx() = something(DEFAULT_CTX[], (DEFAULT_CTX[] = Context(0)))
+
+# ---- device arrays -------------------------------------------------------------------------------
+mutable struct B200Vector{T} <: AbstractVector{T}
+  handle::Ptr{Cvoid}; len::Int; owned::Bool
+end
+function B200Vector{T}(::UndefInitializer, n::Integer) where T
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:rls_vec_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Ref{Ptr{Cvoid}}), ctx().handle, dtypecode(T), n, h))
+  finalizer(v -> v.owned && ccall((:rls_vec_destroy, LIB), Int32, (Ptr{Cvoid},), v.handle), B200Vector{T}(h[], n, true))
+end
+Base.size(v::B200Vector) = (v.len,)
+Base.similar(v::B200Vector{T}, n::Integer...) where T = B200Vector{T}(undef, prod(n))   # FISTA.jl:95-98
+Base.similar(v::B200Vector, ::Type{T}, dims::Dims) where T = B200Vector{T}(undef, prod(dims))
+function B200Vector(x::Vector{T}) where T
+  v = B200Vector{T}(undef, length(x))
+  GC.@preserve x check(ccall((:rls_vec_upload, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), v.handle, pointer(x), length(x)))
+  v
+end
+function Base.Array(v::B200Vector{T}) where T
+  x = Vector{T}(undef, v.len)
+  GC.@preserve x check(ccall((:rls_vec_download, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), v.handle, pointer(x), v.len))
+  x
+end
+Base.getindex(v::B200Vector, i::Int) = error("scalar indexing of a B200Vector is disabled; use Array(v)")
+function LinearAlgebra.norm(v::B200Vector)
+  r = Ref{Float64}(0); check(ccall((:rls_vec_nrm2, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}), v.handle, r)); real(eltype(v))(r[])
+end
+
+mutable struct B200Matrix{T} <: AbstractMatrix{T}
+  handle::Ptr{Cvoid}; m::Int; n::Int
+end
+function B200Matrix(A::Matrix{T}) where T        # column-major, exactly as Julia stores it
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve A check(ccall((:rls_mat_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}),
+                             ctx().handle, dtypecode(T), size(A, 1), size(A, 2), pointer(A), stride(A, 2), h))
+  finalizer(M -> ccall((:rls_mat_destroy, LIB), Int32, (Ptr{Cvoid},), M.handle), B200Matrix{T}(h[], size(A)...))
+end
+Base.size(A::B200Matrix) = (A.m, A.n)
+
+"AHA for a device matrix: `normalOperator(A)` / `A'*A` both resolve to the library's normal operator"
+mutable struct B200NormalOp{T}
+  handle::Ptr{Cvoid}; A::B200Matrix{T}
+end
+function B200NormalOp(A::B200Matrix{T}; form = RLS_NORMAL_AUTO) where T
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:rls_normal_create, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), A.handle, form, h))
+  finalizer(o -> ccall((:rls_normal_destroy, LIB), Int32, (Ptr{Cvoid},), o.handle), B200NormalOp{T}(h[], A))
+end
+Base.:*(At::Adjoint{T,B200Matrix{T}}, A::B200Matrix{T}) where T = B200NormalOp(parent(At))   # FISTA.jl:58 `AHA = A'*A`
+Base.eltype(::B200NormalOp{T}) where T = T
+Base.size(op::B200NormalOp, d...) = size(op.A, 2)
+function LinearAlgebra.mul!(res::B200Vector, op::B200NormalOp, x::B200Vector)                # FISTA.jl:152
+  check(ccall((:rls_normal_apply, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), op.handle, x.handle, res.handle)); res
+end
+function LinearAlgebra.mul!(g::B200Vector, At::Adjoint{T,B200Matrix{T}}, y::B200Vector) where T  # FISTA.jl:114
+  check(ccall((:rls_gemv_c, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), parent(At).handle, y.handle, g.handle)); g
+end
+
+# ---- prox! on device vectors (mirrors ext/RegularizedLeastSquaresGPUArraysExt) --------------------
+prox!(::L1Regularization, x::B200Vector, λ::Float32) = (check(ccall((:rls_prox_l1, LIB), Int32, (Ptr{Cvoid}, Float32), x.handle, λ)); x)
+prox!(::L2Regularization, x::B200Vector, λ::Float32) = (check(ccall((:rls_prox_l2, LIB), Int32, (Ptr{Cvoid}, Float32), x.handle, λ)); x)
+prox!(r::L21Regularization, x::B200Vector, λ::Float32) = (check(ccall((:rls_prox_l21, LIB), Int32, (Ptr{Cvoid}, Float32, Int64), x.handle, λ, r.slices)); x)
+function prox!(r::TVRegularization, x::B200Vector, λ::Float32)
+  shape = collect(Int64, r.shape); dims = collect(Int32, r.dims)
+  check(ccall((:rls_prox_tv, LIB), Int32, (Ptr{Cvoid}, Float32, Int32, Ptr{Int64}, Int32, Ptr{Int32}, Int32),
+              x.handle, λ, length(shape), shape, length(dims), dims, r.iterationsTV)); x
+end
+prox!(::PositiveRegularization, x::B200Vector) = (check(ccall((:rls_prox_positive, LIB), Int32, (Ptr{Cvoid},), x.handle)); x)
+prox!(::RealRegularization, x::B200Vector) = (check(ccall((:rls_prox_real, LIB), Int32, (Ptr{Cvoid},), x.handle)); x)
+
+# ---- solvers: one library-side solver object per Julia solver, keyed by objectid ---------------------
+regkind(::L1Regularization) = RLS_REG_L1; regkind(::L2Regularization) = RLS_REG_L2
+regkind(::L21Regularization) = RLS_REG_L21; regkind(::TVRegularization) = RLS_REG_TV
+function regdesc(reg; rho = 0f0)
+  s = sink(reg); l = λ(reg)
+  shape = s isa TVRegularization ? ntuple(i -> i <= length(s.shape) ? Int64(s.shape[i]) : Int64(0), 4) : ntuple(_ -> Int64(0), 4)
+  dims = s isa TVRegularization ? ntuple(i -> i <= length(s.dims) ? Int32(collect(s.dims)[i]) : Int32(0), 4) : ntuple(_ -> Int32(0), 4)
+  RegDesc(regkind(s), l isa Float64 ? 1 : 0, Float64(l), s isa L21Regularization ? s.slices : 1,
+          s isa TVRegularization ? length(s.shape) : 0, s isa TVRegularization ? length(s.dims) : 0, shape, dims,
+          s isa TVRegularization ? s.iterationsTV : 0, 0, Float32(rho), 0)
+end
+projmask(proj) = reduce(|, (p isa PositiveRegularization ? RLS_PROJ_POSITIVE : RLS_PROJ_REAL for p in proj); init = Int32(0))
+const EMPTYREG = RegDesc(0, 0, 0.0, 1, 0, 0, ntuple(_ -> Int64(0), 4), ntuple(_ -> Int32(0), 4), 0, 0, 0f0, 0)
+
+const HANDLES = IdDict{Any,Ptr{Cvoid}}()
+function handle!(solver::FISTA, state)        # POGM / OptISTA / CGNR / ADMM are built the same way
+  get!(HANDLES, solver) do
+    d = SolverDesc(RLS_FISTA, solver.iterations, solver.restart == :gradient ? 1 : 0, projmask(solver.proj),
+                   state.ρ, state.theta, 1f0, state.relTol, 0f0, 0f0, 0, 0, 1, 0,
+                   (regdesc(solver.reg), EMPTYREG, EMPTYREG, EMPTYREG))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rls_solver_create, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{SolverDesc}, Ref{Ptr{Cvoid}}),
+                solver.A.handle, solver.AHA.handle, Ref(d), h))
+    h[]
+  end
+end
+
+# state-type dispatch: FISTAState{rT, <:B200Vector} is what `init!` builds once `b isa B200Vector`
+function init!(solver::FISTA, state::RegularizedLeastSquares.FISTAState{rT,<:B200Vector}, b::B200Vector; x0 = 0, theta = 1) where rT
+  check(ccall((:rls_solver_init, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), handle!(solver, state), b.handle, C_NULL))
+  sync_scalars!(solver, state)
+end
+function iterate(solver::FISTA, state::RegularizedLeastSquares.FISTAState{rT,<:B200Vector}) where rT
+  adv = Ref{Int32}(0); sc = Ref{SolverScalars}()
+  check(ccall((:rls_solver_iterate, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}, Ref{SolverScalars}), handle!(solver, state), adv, sc))
+  adv[] == 0 && return nothing
+  state.theta = sc[].theta; state.thetaᵒˡᵈ = sc[].theta_old; state.rel_res_norm = sc[].rel_res_norm; state.iteration = sc[].iteration
+  return state.x, state
+end
+# callback-free solve!: one C call for the whole loop, host buffers in and out
+function solve!(solver::FISTA, b::Vector{T}; callbacks = nothing, kwargs...) where T <: Union{Float32,ComplexF32}
+  callbacks === nothing || return invoke(solve!, Tuple{RegularizedLeastSquares.AbstractLinearSolver,Any}, solver, B200Vector(b); callbacks, kwargs...)
+  x = Vector{T}(undef, size(solver.AHA, 2)); it = Ref{Int32}(0); sc = Ref{SolverScalars}()
+  GC.@preserve b x check(ccall((:rls_solver_solve_host, LIB), Int32,
+      (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ref{Int32}, Ref{SolverScalars}),
+      handle!(solver, solver.state), pointer(b), length(b), pointer(x), length(x), it, sc))
+  x
+end
+
+function sync_scalars!(solver, state)
+  sc = Ref{SolverScalars}()
+  check(ccall((:rls_solver_scalars_get, LIB), Int32, (Ptr{Cvoid}, Ref{SolverScalars}), HANDLES[solver], sc))
+  state.norm_x₀ = sc[].norm_x0; state.iteration = sc[].iteration
+  state
+end
+
+end # module

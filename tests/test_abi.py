@@ -1,0 +1,82 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads, and exports every
+symbol include/rls_b200.h declares; POD structs agree between C and ctypes; no host code
+path calls a __device__-only function (nvcc compiles that to exit(1)).  No compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rls_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rls_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(rls):
+    lib = C.CDLL(rls._capi.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 60
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, f"declared in include/rls_b200.h but not exported: {missing}"
+    # and the Python binding covers them all
+    bound = set(rls._capi.SIGNATURES) | set(rls._capi._SPECIAL)
+    assert not [s for s in syms if s not in bound], [s for s in syms if s not in bound]
+
+
+def test_abi_version_and_error_string(rls):
+    assert rls.ABI_VERSION == 1
+    assert isinstance(rls._capi.last_error(), str)
+
+
+def test_struct_layouts_match_c(rls, tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rls_b200.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(rls_reg_desc), sizeof(rls_solver_desc), '
+                   'sizeof(rls_solver_scalars), offsetof(rls_solver_desc, reg), offsetof(rls_reg_desc, tv_shape), '
+                   'offsetof(rls_solver_scalars, admm_rk));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    c = rls._capi
+    assert [int(v) for v in out] == [C.sizeof(c.RegDesc), C.sizeof(c.SolverDesc), C.sizeof(c.SolverScalars),
+                                     c.SolverDesc.reg.offset, c.RegDesc.tv_shape.offset, c.SolverScalars.admm_rk.offset]
+
+
+def test_no_device_function_called_from_host(rls):
+    dis = subprocess.run(["objdump", "-d", "--no-show-raw-insn", rls._capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "<exit@plt>" not in dis, "host code calls a __device__-only function (nvcc turns that into exit(1))"
+
+
+def test_library_is_sm100a_and_uses_tma(rls):
+    out = subprocess.run(["cuobjdump", "-lelf", rls._capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", rls._capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTMALDG" in sass, "the one-pass kernel must stage A with TMA"
+    assert "HMMA" not in sass
+
+
+def test_no_gpu_means_loud_failure_not_fallback(rls):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(rls.RlsError):
+        rls.B200Context(0)
+    import numpy as np
+    with pytest.raises(rls.RlsError):
+        rls.prox_(rls.L1Regularization(0.1), np.ones(4, np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "regularizedleastsquares.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".jl")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f"{f} reaches into oracle/"

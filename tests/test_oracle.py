@@ -205,6 +205,8 @@ def test_gram_and_lazy_forms_agree():
         kw = dict(iterations=15)
         if solver is O.FISTA:
             kw.update(rho=np.float32(0.005), reg=O.L1Regularization(np.float32(1e-3)), relTol=0.0)
+        else:
+            kw.update(iterations=6)      # Float32 CG steering scalars amplify rounding once converged
         a = solver(A, normal="gram", **kw).solve(b)
         c = solver(A, normal="lazy", **kw).solve(b)
         assert np.linalg.norm(a - c) <= 2e-4 * np.linalg.norm(c)
