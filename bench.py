@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
-def cpu_sample(iters=20, m_sub=4096, threads=None):
+def cpu_sample(iters=100, m_sub=8192, threads=None):
     """The oracle's FISTA loop (NumPy -> threaded OpenBLAS sgemv) on a row subsample of the
     workload; iterations/s are scaled linearly in m to the full 16384 rows."""
     import oracle as O
@@ -101,7 +101,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count()
-    m_sub, iters = 4096, 20
+    m_sub, iters = 8192, 100
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_sample(iters=3, m_sub=m_sub)
     t0 = time.perf_counter()
@@ -226,10 +226,11 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, k, dt = cpu_sample(iters=20, m_sub=4096)
+        v, k, dt = cpu_sample()
+        m_sub = 8192
         cpu = {"value": v, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"{k} FISTA-L1 iterations of the oracle loop (NumPy/OpenBLAS) on a 4096-row subsample in {dt:.1f} s, "
-                         f"scaled by 4096/{M} to the full system; restated reference, Julia is not installed"}
+               "sample": f"{k} FISTA-L1 iterations of the oracle loop (NumPy/OpenBLAS) on a {m_sub}-row subsample in {dt:.1f} s, "
+                         f"scaled by {m_sub}/{M} to the full system; restated reference, Julia is not installed"}
     if rank == 0:
         line = {
             "metric": "FISTA-L1 iterations/s on dense A (Float32 16384x65536 per GPU)",

@@ -1,0 +1,63 @@
+"""Row-sharded solve under torchrun: every rank holds a row block of the same Philox system,
+rank 0 also solves the full system on its own GPU; the sharded FISTA / CGNR / ADMM results must
+match it (rel-L2 <= 1e-5; the only difference is the summation order of the n-vector allreduce).
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/multi_gpu_check.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rls_b200 as rls
+
+rank, world, local = rls.dist.env_rank()
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ctx = rls.B200Context.default(local)
+rls.dist.init_comm(ctx, rank, world)
+
+ok = True
+for dtype, m, n in ((np.float32, 4096, 8192), (np.complex64, 3001, 2048)):
+    lo, hi = rls.dist.row_range(m, rank, world, align=4)
+    scale = 1.0 / np.sqrt(m)
+    A_i = rls.B200Matrix.philox(dtype, hi - lo, n, seed=77, scale=scale, row_offset=lo, m_global=m, ctx=ctx)
+    b_full = rls.B200Vector(ctx, dtype, m).fill_philox(78, stream=2, dist=1).to_numpy()
+    b_i = b_full[lo:hi].copy()
+    results = {}
+    for name, mk in (("FISTA", lambda A: rls.FISTA(A, reg=rls.L1Regularization(np.float32(1e-2)), iterations=30, rho=np.float32(0.2), relTol=0.0, normal="twopass")),
+                     ("FISTA-onepass", lambda A: rls.FISTA(A, reg=rls.L1Regularization(np.float32(1e-2)), iterations=30, rho=np.float32(0.2), relTol=0.0, normal="onepass")),
+                     ("CGNR", lambda A: rls.CGNR(A, reg=rls.L2Regularization(np.float32(1e-2)), iterations=10, relTol=0.0, normal="twopass")),
+                     ("ADMM", lambda A: rls.ADMM(A, reg=rls.L1Regularization(np.float32(1e-2)), iterations=5, iterationsCG=5, normal="twopass"))):
+        S = mk(A_i)
+        results[name] = rls.solve_(S, b_i)
+    # replicas must be bit-identical across ranks
+    for name, x in results.items():
+        t = torch.from_numpy(np.ascontiguousarray(x).view(np.float32).copy()).cuda()
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        same = bool(torch.equal(t, ref))
+        flag = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0 and not int(flag[0]):
+            print(f"FAIL {name} {np.dtype(dtype).name}: replicas differ across ranks"); ok = False
+    dist.barrier()
+    if rank == 0:
+        # single-GPU reference on a separate, communicator-free context
+        ctx1 = rls.B200Context(local)
+        A = rls.B200Matrix.philox(dtype, m, n, seed=77, scale=scale, ctx=ctx1)
+        for name, mk in (("FISTA", lambda A: rls.FISTA(A, reg=rls.L1Regularization(np.float32(1e-2)), iterations=30, rho=np.float32(0.2), relTol=0.0, normal="twopass", ctx=ctx1)),
+                         ("CGNR", lambda A: rls.CGNR(A, reg=rls.L2Regularization(np.float32(1e-2)), iterations=10, relTol=0.0, normal="twopass", ctx=ctx1)),
+                         ("ADMM", lambda A: rls.ADMM(A, reg=rls.L1Regularization(np.float32(1e-2)), iterations=5, iterationsCG=5, normal="twopass", ctx=ctx1))):
+            x1 = rls.solve_(mk(A), b_full)
+            for key in ([name, name + "-onepass"] if name == "FISTA" else [name]):
+                e = np.linalg.norm(results[key] - x1) / np.linalg.norm(x1)
+                good = e < (1e-5 if name == "FISTA" else 5e-5)
+                ok &= good
+                print(f"{'ok  ' if good else 'FAIL'} {key:14s} {np.dtype(dtype).name:9s} {m}x{n} over {world} GPUs: rel-L2 vs 1 GPU = {e:.2e}")
+    dist.barrier()
+if rank == 0:
+    print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
