@@ -1,23 +1,24 @@
-// rls_normal_tma.cu — one-HBM-pass normal operator  g = A'(A x)  as a TMA-fed two-phase
-// streaming kernel (the roofline-defining kernel of the package).
+// rls_normal_tma.cu — single-HBM-pass normal operator  g = A'(A x)  with TMA-staged,
+// shared-memory-resident row panels and a flag-in-data all-reduce of y (the roofline-defining
+// kernel of the package).
 //
-// Persistent cooperative kernel, one CTA per SM; every CTA owns a fixed range of columns
-// (multiples of 32).  A row panel (PR rows x all columns) is used twice:
-//   phase 1  y_p = A_p x   : the CTA's [PR x cols] tile streams from HBM through a shared-memory
-//                            ring (TMA cp.async.bulk.tensor + mbarrier complete_tx) and is
-//                            reduced against x; the PR-vector of partial sums is exchanged
-//                            between CTAs through per-CTA slots in L2 (all-gather with a fixed
-//                            summation order => deterministic, bit-identical on every CTA);
-//   phase 2  g += A_p' y_p : D panels later the same tile streams through the ring again — now
-//                            an L2 hit (phase-1 loads carry an evict_last policy, phase-2 loads
-//                            evict_first) — and is reduced against y_p.
-// HBM therefore sees A once; the lag D hides the latency of the y exchange completely, and
-// because nothing has to stay resident in shared memory the panels can be tall enough
-// (256-byte column segments) for full HBM efficiency.  g lives in registers for the whole
-// launch and is written once.  Warp roles: 16 compute warps, 1 TMA producer, 1 sender
-// (CTA-level y reduction + slot publish), 4 gatherers.  Every wait is bounded: a time-out
-// raises an abort flag instead of hanging the GPU.  Out-of-range rows / columns are
-// zero-filled by TMA, so there is no tail masking.  Float32 and interleaved ComplexF32.
+// Persistent cooperative kernel, one CTA per SM.  Every CTA owns a fixed range of columns
+// (multiples of 32).  A row panel (32 floats of every column = 128-byte segments) is used twice:
+//   phase 1  y_p = A_p x   : the CTA's [32 x cols] tile is brought into a shared-memory ring by a
+//                            TMA producer thread (cp.async.bulk.tensor + mbarrier complete_tx) and
+//                            reduced against x by 14 compute warps;
+//   exchange               : the CTA's 32 partial sums are published to its slot in L2 as
+//                            {value, tag} 8-byte units (one 16-byte store per lane, no fence, no
+//                            counter); every CTA gathers all slots (5-6 loads per lane, retried
+//                            until the tags match) and sums them in a fixed order => deterministic
+//                            and bit-identical on every CTA.  Measured 1.4 us per all-reduce against
+//                            5.1 us for the slot/fence/atomic-counter protocol (tools/xchg_lat.cu);
+//   phase 2  g += A_p' y_p : one panel later the SAME shared-memory tile is read again and then
+//                            released to the producer.
+// A is therefore delivered from HBM to the SMs exactly once (no L2 re-read); g lives in registers
+// for the whole launch and is written once.  Every wait is bounded: a time-out raises an abort flag
+// instead of hanging the GPU.  Out-of-range rows / columns are zero-filled by TMA (no tail masking).
+// Float32 and interleaved ComplexF32.
 #include <cuda.h>
 
 #include <type_traits>
@@ -26,24 +27,21 @@
 
 namespace {
 
-constexpr int T_NCW = 16;              // compute warps
-constexpr int T_NGW = 2;               // gatherer warps (cooperate on every panel; the lag hides their latency)
-constexpr int T_CT = T_NCW * 32;
-constexpr int T_THREADS = (T_NCW + 2 + T_NGW) * 32;
+constexpr int T_NCW = 14;              // compute warps (+1 producer = 13 -> register allocation rounds to 16 warps: 128 regs/thread)
+constexpr int T_CT = T_NCW * 32;       // compute threads
+constexpr int T_THREADS = T_CT + 32;   // + the TMA producer warp
 constexpr int T_BOXC = 32;             // columns per TMA box
-constexpr int T_NY = 8;                // y ring in shared memory (lag <= T_NY - 1)
-constexpr int T_NB = 16;               // slot / counter ring in global memory (lag <= (T_NB - 2) / 2)
-constexpr int T_MAXLAG = 6;
+constexpr int T_LPC = 8;               // float4 per column segment: 128-byte segments, 32 floats per panel column
+constexpr int T_PRF = T_LPC * 4;       // floats of y per panel
+constexpr int T_NB = 16;               // slot ring in global memory (lag 2 needs >= 6)
 constexpr int T_MAXI = 4;              // max float4 sweeps of the compute warps over a stage
-constexpr int T_GLD = 10;              // slot loads in flight per gatherer lane
+constexpr int T_GLD = 6;               // slot loads in flight per lane (grid <= 2*T_NCW*T_GLD per batch)
 constexpr unsigned T_SPIN_LIMIT = 4000000u;
 
 struct TmaWs {
-  float4* slots;        // [T_NB][grid][16]
-  unsigned* counter;    // [T_NB] arrival counters, 128 bytes apart (zeroed before every launch)
+  uint4* slots;         // [T_NB][grid][16] : {y[2e], tag, y[2e+1], tag}
   int* abort_flag;
 };
-constexpr int T_CSTRIDE = 32;          // uints between counters (one L2 line each)
 
 struct TmaArgs {
   const void* x;
@@ -54,12 +52,8 @@ struct TmaArgs {
   int nblk;             // total 32-column blocks
   int sb;               // boxes per stage
   int nstages;          // ring depth S
-  int lag;              // D: phase 2 of panel p runs during step p + D
   int stage_bytes;
-  int use_hint;
-  int p2_ldg;           // 1: phase 2 re-reads the panel with plain 128-bit loads from L2 (TMA carries A only once)
-  const void* A;
-  long long ld;
+  unsigned tag_base;    // tags of this launch: tag_base + panel + 1
   const int* gate;
 };
 
@@ -99,42 +93,21 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
-                                                 unsigned long long policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
+// L2-coherent 16-byte accesses for the flag-in-data exchange (each 8-byte {value, tag} unit is single-copy atomic)
+__device__ __forceinline__ uint4 ld_cg_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
 }
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void st_cg_u4(uint4* p, uint4 v) {
+  asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(T_CT) : "memory"); }
+
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4shfl_xor(float4 a, int o) {
   return make_float4(__shfl_xor_sync(0xffffffffu, a.x, o), __shfl_xor_sync(0xffffffffu, a.y, o),
                      __shfl_xor_sync(0xffffffffu, a.z, o), __shfl_xor_sync(0xffffffffu, a.w, o));
-}
-
-__device__ __forceinline__ float4 ldg_l2(const float4* p, unsigned long long pol) {
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-               : "l"(p), "l"(pol));
-  return r;
-}
-template <typename T>
-__device__ __forceinline__ float4 mask_rows4(float4 v, long long row0, long long m) {
-  constexpr int VEC = Elem<T>::vec;
-  if (row0 + VEC <= m) return v;
-  float t[4] = {v.x, v.y, v.z, v.w};
-  constexpr int FPE = 4 / VEC;
-#pragma unroll
-  for (int e = 0; e < VEC; ++e)
-    if (row0 + e >= m)
-      for (int f = 0; f < FPE; ++f) t[e * FPE + f] = 0.f;
-  return make_float4(t[0], t[1], t[2], t[3]);
 }
 
 template <typename T> __device__ __forceinline__ void fma_y(float4& acc, float4 a, T x);
@@ -156,58 +129,48 @@ template <> __device__ __forceinline__ void fma_g<float2>(float2& acc, float4 a,
   acc.x = fmaf(a.z, y.z, acc.x); acc.x = fmaf(a.w, y.w, acc.x); acc.y = fmaf(a.z, y.w, acc.y); acc.y = fmaf(-a.w, y.z, acc.y);
 }
 
-// shared-memory carve-up (dynamic): [stages][x][ypart][ysm][gsm][barriers]
-template <typename T, int LPC>
+// shared-memory carve-up (dynamic): [stages][x][ypart][gsm][barriers]
+template <typename T>
 struct SmemLayout {
   int stage_bytes, nstages, xcols;
   __host__ __device__ size_t off_x() const { return (size_t)stage_bytes * nstages; }
   __host__ __device__ size_t off_ypart() const { return off_x() + (((size_t)xcols * sizeof(T) + 127) & ~(size_t)127); }
-  __host__ __device__ size_t off_ysm() const { return off_ypart() + sizeof(float4) * 2 * T_NCW * LPC; }
-  __host__ __device__ size_t off_gsm() const { return off_ysm() + sizeof(float4) * T_NY * LPC; }
-  __host__ __device__ size_t off_bars() const { return off_gsm() + sizeof(float4) * 2 * T_NGW * LPC; }
-  __host__ __device__ size_t total() const { return off_bars() + sizeof(uint64_t) * (2 * 16 + 4 + T_NY + 4) + 64; }
+  __host__ __device__ size_t off_gsm() const { return off_ypart() + sizeof(float4) * T_NCW * T_LPC; }
+  __host__ __device__ size_t off_bars() const { return off_gsm() + sizeof(float4) * T_NCW * T_LPC; }
+  __host__ __device__ size_t total() const { return off_bars() + sizeof(uint64_t) * (2 * 16) + 64; }
 };
 
-// LPC = float4 per column segment (8: 128-byte, 16: 256-byte segments); NJ = max column chunks per panel
-template <typename T, int LPC, int NJ>
+// NJ = max column chunks (stages) per panel for this instantiation
+template <typename T, int NJ>
 __global__ void __launch_bounds__(T_THREADS, 1) normal_tma_kernel(const __grid_constant__ CUtensorMap tmap, TmaArgs a) {
   if (a.gate && *a.gate) return;
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int LPC = T_LPC;
   constexpr int NGRP = 32 / LPC;          // columns covered by one warp-wide float4 read
   constexpr int BOX_BYTES = T_BOXC * LPC * 16;
-  constexpr int PRF = LPC * 4;            // floats of y per panel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grid = gridDim.x, cta = blockIdx.x;
-  const int S = a.nstages, D = a.lag, P = a.panels;
+  const int S = a.nstages, P = a.panels;
 
   // this CTA's column blocks
   const int blk0 = (int)(((long long)cta * a.nblk) / grid);
   const int blk1 = (int)(((long long)(cta + 1) * a.nblk) / grid);
   const int nb = blk1 - blk0;
-  const int nch = (nb + a.sb - 1) / a.sb;               // stages (column chunks) per panel and phase
+  const int nch = (nb + a.sb - 1) / a.sb;               // stages (column chunks) per panel
   const long long col0 = (long long)blk0 * T_BOXC;
 
-  SmemLayout<T, LPC> L{a.stage_bytes, S, ((a.nblk + grid - 1) / grid + 1) * T_BOXC};
+  SmemLayout<T> L{a.stage_bytes, S, ((a.nblk + grid - 1) / grid + 1) * T_BOXC};
   uint8_t* stage_base = smem;
   T* xs = reinterpret_cast<T*>(smem + L.off_x());
-  float4* ypart = reinterpret_cast<float4*>(smem + L.off_ypart());   // [2][NCW][LPC]
-  float4* ysm = reinterpret_cast<float4*>(smem + L.off_ysm());       // [T_NY][LPC]
-  float4* gsm = reinterpret_cast<float4*>(smem + L.off_gsm());       // [2][T_NGW][LPC]
+  float4* ypart = reinterpret_cast<float4*>(smem + L.off_ypart());   // [NCW][LPC]  per-warp partial y of the current panel
+  float4* gsm = reinterpret_cast<float4*>(smem + L.off_gsm());       // [NCW][LPC]  per-warp partial of the gathered y
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars());
   uint64_t* full = bars;              // [16]
   uint64_t* empty = bars + 16;        // [16]
-  uint64_t* yp_full = bars + 32;      // [2]
-  uint64_t* yp_free = bars + 34;      // [2]
-  uint64_t* yready = bars + 36;       // [T_NY]
-  uint64_t* gdone = bars + 36 + T_NY; // [2] gatherer partials written
-  uint64_t* gfree = gdone + 2;        // [2] gatherer partials consumed
   int* abort_flag = a.ws.abort_flag;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], T_NCW); }
-    for (int k = 0; k < 2; ++k) { mbar_init(&yp_full[k], T_NCW); mbar_init(&yp_free[k], 1); }
-    for (int k = 0; k < T_NY; ++k) mbar_init(&yready[k], 1);
-    for (int k = 0; k < 2; ++k) { mbar_init(&gdone[k], T_NGW); mbar_init(&gfree[k], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
@@ -221,121 +184,36 @@ __global__ void __launch_bounds__(T_THREADS, 1) normal_tma_kernel(const __grid_c
 
   if (warp == T_NCW) {
     // ================================ TMA producer ====================================
-    // issue order == consumption order: [phase-1 chunks of panel t][phase-2 chunks of panel t-D]
     if (lane == 0 && nb > 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-      unsigned long long pol_keep = 0, pol_drop = 0;
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
       long long k = 0;
-      for (int t = 0; t < P + D; ++t) {
-        for (int ph = 0; ph < 2; ++ph) {
-          const int pnl = ph == 0 ? t : t - D;
-          if (pnl < 0 || pnl >= P) continue;
-          if (ph == 1 && a.p2_ldg) continue;
-          for (int j = 0; j < nch; ++j, ++k) {
-            const int s = (int)(k % S);
-            const unsigned use = (unsigned)(k / S);
-            if (use > 0 && !mbar_wait(&empty[s], (use - 1) & 1, abort_flag)) return;
-            const int bx0 = j * a.sb;
-            const int nbx = min(a.sb, nb - bx0);
-            mbar_expect_tx(&full[s], (unsigned)(nbx * BOX_BYTES));
-            uint8_t* dst = stage_base + (size_t)s * a.stage_bytes;
-            for (int bx = 0; bx < nbx; ++bx) {
-              if (a.use_hint)
-                tma_load_2d_hint(dst + (size_t)bx * BOX_BYTES, &tmap, pnl * PRF, (blk0 + bx0 + bx) * T_BOXC, &full[s],
-                                 ph == 0 ? pol_keep : pol_drop);
-              else
-                tma_load_2d(dst + (size_t)bx * BOX_BYTES, &tmap, pnl * PRF, (blk0 + bx0 + bx) * T_BOXC, &full[s]);
-            }
-          }
+      for (int t = 0; t < P; ++t) {
+        for (int j = 0; j < nch; ++j, ++k) {
+          const int s = (int)(k % S);
+          const unsigned use = (unsigned)(k / S);
+          if (use > 0 && !mbar_wait(&empty[s], (use - 1) & 1, abort_flag)) return;
+          const int bx0 = j * a.sb;
+          const int nbx = min(a.sb, nb - bx0);
+          mbar_expect_tx(&full[s], (unsigned)(nbx * BOX_BYTES));
+          uint8_t* dst = stage_base + (size_t)s * a.stage_bytes;
+          for (int bx = 0; bx < nbx; ++bx)
+            tma_load_2d(dst + (size_t)bx * BOX_BYTES, &tmap, t * T_PRF, (blk0 + bx0 + bx) * T_BOXC, &full[s]);
         }
-      }
-    }
-    return;
-  }
-  if (warp == T_NCW + 1) {
-    // ================================ sender ==========================================
-    for (int t = 0; t < P; ++t) {
-      const int pb = t & 1;
-      if (!mbar_wait(&yp_full[pb], (unsigned)(t >> 1) & 1, abort_flag)) return;
-      const int b = t % T_NB;
-      if (lane < LPC) {
-        float4 s = ypart[(pb * T_NCW + 0) * LPC + lane];
-#pragma unroll
-        for (int w = 1; w < T_NCW; ++w) s = f4add(s, ypart[(pb * T_NCW + w) * LPC + lane]);
-        a.ws.slots[((size_t)b * grid + cta) * 16 + lane] = s;
-      }
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) {
-        atomicAdd(&a.ws.counter[b * T_CSTRIDE], 1u);
-        mbar_arrive(&yp_free[pb]);
-      }
-    }
-    return;
-  }
-  if (warp >= T_NCW + 2) {
-    // ================================ gatherers =======================================
-    // All T_NGW warps work on every panel: the grid's slots are dealt to T_NGW*NGRP lane groups,
-    // every lane issues its loads in one batch, partial sums are combined in a fixed order
-    // (lane order, shuffle tree, warp order) => deterministic and bit-identical on every CTA.
-    const int gw = warp - (T_NCW + 2);
-    const int gl = lane / LPC, r4 = lane % LPC;
-    constexpr int NG = T_NGW * NGRP;
-    const int g0 = gw * NGRP + gl;
-    for (int t = 0; t < P; ++t) {
-      const int b = t % T_NB;
-      const unsigned target = (unsigned)grid * (unsigned)(t / T_NB + 1);   // counters are zeroed before every launch
-      unsigned ok = 1;
-      if (lane == 0) {
-        unsigned spins = 0;
-        while ((int)(ld_acquire_u32(&a.ws.counter[b * T_CSTRIDE]) - target) < 0) {
-          if (++spins > T_SPIN_LIMIT || *((volatile int*)abort_flag)) { ok = 0; break; }
-          __nanosleep(100);
-        }
-        if (!ok) *abort_flag = 1;
-      }
-      ok = __shfl_sync(0xffffffffu, ok, 0);
-      __syncwarp();
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok) {
-        const float4* __restrict__ sl = a.ws.slots + (size_t)b * grid * 16 + r4;
-        for (int base = g0; base < grid; base += NG * T_GLD) {
-          float4 v[T_GLD];
-#pragma unroll
-          for (int u = 0; u < T_GLD; ++u) {
-            const int c = base + u * NG;
-            v[u] = (c < grid) ? __ldcg(sl + (size_t)c * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < T_GLD; ++u) acc = f4add(acc, v[u]);
-        }
-#pragma unroll
-        for (int o = LPC; o < 32; o <<= 1) acc = f4add(acc, f4shfl_xor(acc, o));
-      }
-      const int pb = t & 1;
-      if (t >= 2 && !mbar_wait(&gfree[pb], (unsigned)((t >> 1) - 1) & 1, abort_flag)) return;
-      if (lane < LPC) gsm[(pb * T_NGW + gw) * LPC + lane] = acc;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&gdone[pb]);
-      if (gw == 0) {
-        if (!mbar_wait(&gdone[pb], (unsigned)(t >> 1) & 1, abort_flag)) return;
-        if (lane < LPC) {
-          float4 s = gsm[(pb * T_NGW + 0) * LPC + lane];
-#pragma unroll
-          for (int w = 1; w < T_NGW; ++w) s = f4add(s, gsm[(pb * T_NGW + w) * LPC + lane]);
-          ysm[(t % T_NY) * LPC + lane] = s;
-        }
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&gfree[pb]); mbar_arrive(&yready[t % T_NY]); }
       }
     }
     return;
   }
 
   // ================================== compute warps =====================================
+  // step t:  (1) issue the gather loads for panel q = t-1 (they fly during phase 1)
+  //          (2) phase 1 of panel t from the ring (tiles stay resident)
+  //          (3) CTA reduction, publish {value, tag} pairs of panel t to this CTA's slot
+  //          (4) validate / sum the gathered slots of panel q in a fixed order
+  //          (5) phase 2 of panel q from the same tiles, release them to the producer
   const int r4 = lane % LPC, cg = lane / LPC;
+  const int ep = lane & 15;                       // element pair (2 floats of y) this lane gathers
+  const int grp = warp * 2 + (lane >> 4);         // CTA residue class (mod NG) this lane gathers
+  constexpr int NG = 2 * T_NCW;
   T gacc[NJ][T_MAXI];
 #pragma unroll
   for (int j = 0; j < NJ; ++j)
@@ -343,91 +221,29 @@ __global__ void __launch_bounds__(T_THREADS, 1) normal_tma_kernel(const __grid_c
     for (int i = 0; i < T_MAXI; ++i) gacc[j][i] = T{};
 
   bool dead = false;
-  long long k = 0;                       // running stage index, same order as the producer
-  if (a.p2_ldg) {
-    // ---- hybrid: phase 1 from the TMA ring (HBM), phase 2 with 128-bit loads that hit L2 ----
-    constexpr int VEC = Elem<T>::vec;
-    const float4* __restrict__ Av = reinterpret_cast<const float4*>(a.A);
-    const long long ldv = a.ld / VEC;
-    unsigned long long pol = 0;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    for (int t = 0; t < P + D; ++t) {
-      const int q = t - D;
-      const bool do1 = t < P, do2 = q >= 0;
-      float4 yacc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      const long long row0 = ((long long)q * LPC + r4) * VEC;           // first row of this lane's slice of panel q
-      const bool rvalid = do2 && row0 < a.m;
-      bool have_y = false;
+  for (int t = 0; t <= P; ++t) {
+    const int q = t - 1;
+    const bool do1 = t < P, do2 = q >= 0;
+    // ---- (1) gather loads for panel q ----
+    uint4 gl[T_GLD];
+    const unsigned want = a.tag_base + (unsigned)q + 1u;
+    const uint4* __restrict__ sl = a.ws.slots + ((size_t)(q & (T_NB - 1)) * grid) * 16 + ep;
+    if (do2) {
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        if (j < nch) {
-          const int nbx = min(a.sb, nb - j * a.sb);
-          const int nelem = nbx * T_BOXC * LPC;
-          // (a) issue the phase-2 loads of chunk j (panel q) — they fly while phase 1 of chunk j runs
-          float4 v2[T_MAXI];
-#pragma unroll
-          for (int i = 0; i < T_MAXI; ++i) {
-            const int e = (i * T_NCW + warp) * 32 + lane;
-            const long long col = col0 + (long long)j * a.sb * T_BOXC + (i * T_NCW + warp) * NGRP + cg;
-            v2[i] = (rvalid && e < nelem && col < a.n) ? ldg_l2(Av + col * ldv + ((long long)q * LPC + r4), pol)
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          // (b) phase 1 of chunk j (panel t) from the ring
-          if (do1) {
-            const int s = (int)(k % S);
-            if (!dead && !mbar_wait(&full[s], (unsigned)(k / S) & 1, abort_flag)) dead = true;
-            ++k;
-            const float4* __restrict__ tile = reinterpret_cast<const float4*>(stage_base + (size_t)s * a.stage_bytes);
-#pragma unroll
-            for (int i = 0; i < T_MAXI; ++i) {
-              const int e = (i * T_NCW + warp) * 32 + lane;
-              if (e < nelem) {
-                const int c = j * a.sb * T_BOXC + (i * T_NCW + warp) * NGRP + cg;
-                fma_y<T>(yacc, tile[e], xs[c]);
-              }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-          }
-          // (c) consume the phase-2 loads
-          if (do2) {
-            if (!have_y) {
-              if (!dead && !mbar_wait(&yready[q % T_NY], (unsigned)(q / T_NY) & 1, abort_flag)) dead = true;
-              y4 = ysm[(q % T_NY) * LPC + r4];
-              have_y = true;
-            }
-            const bool partial = rvalid && row0 + VEC > a.m;
-#pragma unroll
-            for (int i = 0; i < T_MAXI; ++i) {
-              float4 v = v2[i];
-              if (partial) v = mask_rows4<T>(v, row0, a.m);
-              fma_g<T>(gacc[j][i], v, y4);
-            }
-          }
-        }
-      }
-      if (do1) {
-#pragma unroll
-        for (int o = LPC; o < 32; o <<= 1) yacc = f4add(yacc, f4shfl_xor(yacc, o));
-        const int pb = t & 1;
-        if (t >= 2 && !dead && !mbar_wait(&yp_free[pb], (unsigned)((t >> 1) - 1) & 1, abort_flag)) dead = true;
-        if (lane < LPC) ypart[(pb * T_NCW + warp) * LPC + lane] = yacc;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&yp_full[pb]);
+      for (int u = 0; u < T_GLD; ++u) {
+        const int c = grp + NG * u;
+        gl[u] = (c < grid) ? ld_cg_u4(sl + (size_t)c * 16) : make_uint4(0u, want, 0u, want);
       }
     }
-  } else {
-  for (int t = 0; t < P + D; ++t) {
-    if (t < P) {
-      // ---- phase 1: y_t partial over this warp's share of the CTA's columns (HBM stream) ----
+    // ---- (2) phase 1 of panel t ----
+    if (do1) {
       float4 yacc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         if (j < nch) {
+          const long long k = (long long)t * nch + j;
           const int s = (int)(k % S);
           if (!dead && !mbar_wait(&full[s], (unsigned)(k / S) & 1, abort_flag)) dead = true;
-          ++k;
           const int nbx = min(a.sb, nb - j * a.sb);
           const int nelem = nbx * T_BOXC * LPC;                 // float4 elements in this stage
           const float4* __restrict__ tile = reinterpret_cast<const float4*>(stage_base + (size_t)s * a.stage_bytes);
@@ -439,29 +255,65 @@ __global__ void __launch_bounds__(T_THREADS, 1) normal_tma_kernel(const __grid_c
               fma_y<T>(yacc, tile[e], xs[c]);
             }
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[s]);
         }
       }
 #pragma unroll
       for (int o = LPC; o < 32; o <<= 1) yacc = f4add(yacc, f4shfl_xor(yacc, o));
-      const int pb = t & 1;
-      if (t >= 2 && !dead && !mbar_wait(&yp_free[pb], (unsigned)((t >> 1) - 1) & 1, abort_flag)) dead = true;
-      if (lane < LPC) ypart[(pb * T_NCW + warp) * LPC + lane] = yacc;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&yp_full[pb]);
+      if (lane < LPC) ypart[warp * LPC + lane] = yacc;
     }
-    if (t >= D) {
-      // ---- phase 2: g += A_q' y_q, the tile comes back through the ring from L2 ----
-      const int q = t - D;
-      if (!dead && !mbar_wait(&yready[q % T_NY], (unsigned)(q / T_NY) & 1, abort_flag)) dead = true;
-      const float4 y4 = ysm[(q % T_NY) * LPC + r4];
+    bar_compute();                                               // ypart(t) complete
+    // ---- (3) CTA reduction in warp order, publish: one 16-byte store per lane, no fence ----
+    if (do1 && warp == 0 && lane < 16) {
+      const float2* yp2 = reinterpret_cast<const float2*>(ypart);
+      float2 s2 = yp2[lane];
+#pragma unroll
+      for (int w = 1; w < T_NCW; ++w) { float2 v = yp2[w * (LPC * 2) + lane]; s2.x += v.x; s2.y += v.y; }
+      const unsigned tag = a.tag_base + (unsigned)t + 1u;
+      st_cg_u4(a.ws.slots + ((size_t)(t & (T_NB - 1)) * grid + cta) * 16 + lane,
+               make_uint4(__float_as_uint(s2.x), tag, __float_as_uint(s2.y), tag));
+    }
+    if (do2) {
+      // ---- (4) validate the gathered slots (retry until every unit carries panel q's tag), fixed-order sum ----
+      float2 acc = make_float2(0.f, 0.f);
+      unsigned spins = 0;
+#pragma unroll
+      for (int u = 0; u < T_GLD; ++u) {
+        const int c = grp + NG * u;
+        while (!dead && (gl[u].y != want || gl[u].w != want)) {
+          if (++spins > T_SPIN_LIMIT || *((volatile int*)abort_flag)) { *abort_flag = 1; dead = true; break; }
+          gl[u] = ld_cg_u4(sl + (size_t)c * 16);
+        }
+        acc.x += __uint_as_float(gl[u].x);
+        acc.y += __uint_as_float(gl[u].z);
+      }
+      for (int base = NG * T_GLD; base < grid; base += NG * T_GLD) {   // grids wider than NG*T_GLD CTAs
+        for (int u = 0; u < T_GLD; ++u) {
+          const int c = base + grp + NG * u;
+          if (c >= grid) break;
+          uint4 v = ld_cg_u4(sl + (size_t)c * 16);
+          while (!dead && (v.y != want || v.w != want)) {
+            if (++spins > T_SPIN_LIMIT) { *abort_flag = 1; dead = true; break; }
+            v = ld_cg_u4(sl + (size_t)c * 16);
+          }
+          acc.x += __uint_as_float(v.x);
+          acc.y += __uint_as_float(v.z);
+        }
+      }
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+      if (lane < 16) reinterpret_cast<float2*>(gsm)[warp * 16 + lane] = acc;
+    }
+    bar_compute();                                               // gsm(q) complete; ypart may be rewritten
+    if (do2) {
+      // ---- (5) y_q = sum over warps (fixed order), phase 2: g += A_q' y_q, release the tiles ----
+      float4 y4 = gsm[r4];
+#pragma unroll
+      for (int w = 1; w < T_NCW; ++w) y4 = f4add(y4, gsm[w * LPC + r4]);
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         if (j < nch) {
+          const long long k = (long long)q * nch + j;
           const int s = (int)(k % S);
-          if (!dead && !mbar_wait(&full[s], (unsigned)(k / S) & 1, abort_flag)) dead = true;
-          ++k;
           const int nbx = min(a.sb, nb - j * a.sb);
           const int nelem = nbx * T_BOXC * LPC;
           const float4* __restrict__ tile = reinterpret_cast<const float4*>(stage_base + (size_t)s * a.stage_bytes);
@@ -475,7 +327,6 @@ __global__ void __launch_bounds__(T_THREADS, 1) normal_tma_kernel(const __grid_c
         }
       }
     }
-  }
   }
   // ---- write g: reduce each column's partial over its LPC lanes ----
   T* __restrict__ g = reinterpret_cast<T*>(a.g);
@@ -529,11 +380,13 @@ struct TmaPlan {
   rls_ctx_s* ctx = nullptr;
   rls_mat_s* A = nullptr;
   CUtensorMap tmap;
-  int lpc = 0, nj = 0, grid = 0, sb = 0, nstages = 0, lag = 0, stage_bytes = 0, panels = 0, nblk = 0, use_hint = 1, p2_ldg = 0;
+  int nj = 0, grid = 0, sb = 0, nstages = 0, stage_bytes = 0, panels = 0, nblk = 0;
   const void* kernel = nullptr;
   size_t smem_bytes = 0;
   TmaWs ws{};
   void* ws_mem = nullptr;
+  size_t ws_bytes = 0;
+  unsigned tag_next = 1;
 };
 
 void rls_tma_plan_destroy(TmaPlan* p) {
@@ -542,58 +395,50 @@ void rls_tma_plan_destroy(TmaPlan* p) {
   delete p;
 }
 
-template <typename T, int LPC>
+template <typename T>
 static const void* pick_tma_kernel(int nj) {
-  if (nj <= 1) return (const void*)normal_tma_kernel<T, LPC, 1>;
-  if (nj <= 2) return (const void*)normal_tma_kernel<T, LPC, 2>;
-  return (const void*)normal_tma_kernel<T, LPC, 4>;
+  if (nj <= 1) return (const void*)normal_tma_kernel<T, 1>;
+  if (nj <= 2) return (const void*)normal_tma_kernel<T, 2>;
+  return (const void*)normal_tma_kernel<T, 4>;
 }
 
-template <typename T, int LPC>
+template <typename T>
 static int32_t tma_configure(TmaPlan* p) {
   rls_ctx_s* c = p->ctx;
   rls_mat_s* A = p->A;
-  constexpr int BOX_BYTES = T_BOXC * LPC * 16;
+  constexpr int BOX_BYTES = T_BOXC * T_LPC * 16;
   const int grid = c->sm_count;
   const int nblk = (int)((A->n + T_BOXC - 1) / T_BOXC);
   const int nbmax = (nblk + grid - 1) / grid;                 // boxes of the widest CTA
   int dev_smem = 0;
   RLS_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  int sb = env_int("RLS_TMA_STAGE_KB", 32) * 1024 / BOX_BYTES;   // ~32 KB stages
+  int sb = env_int("RLS_TMA_STAGE_KB", 28) * 1024 / BOX_BYTES;   // ~28 KB stages
   if (sb < 1) sb = 1;
   if (sb > nbmax) sb = nbmax;
-  while ((sb * T_BOXC * LPC + T_CT - 1) / T_CT > T_MAXI) --sb;   // at most T_MAXI sweeps per stage
   int nch = (nbmax + sb - 1) / sb;
-  if (nch > 4) {
-    rls_set_error("one-pass(TMA): %lld columns over %d SMs need more than 4 stages per panel", (long long)A->n, grid);
+  if (nch > 4) { nch = 4; sb = (nbmax + nch - 1) / nch; }
+  if ((sb * T_BOXC * T_LPC + T_CT - 1) / T_CT > T_MAXI) {
+    rls_set_error("one-pass(TMA): %lld columns over %d SMs exceed the per-CTA tile budget", (long long)A->n, grid);
     return RLS_ERR_UNSUPPORTED;
   }
   const int stage_bytes = sb * BOX_BYTES;
-  SmemLayout<T, LPC> L{stage_bytes, 0, (nbmax + 1) * T_BOXC};
+  SmemLayout<T> L{stage_bytes, 0, (nbmax + 1) * T_BOXC};
   int S = 16;
   for (; S >= 2; --S) {
     L.nstages = S;
     if (L.total() <= (size_t)dev_smem) break;
   }
-  if (S < 2) {
-    rls_set_error("one-pass(TMA): shared memory cannot hold two stages of %d bytes", stage_bytes);
+  // two resident panels (phase 2 runs one panel behind phase 1) and at least one prefetch stage
+  if (S < 2 * nch + 1) {
+    rls_set_error("one-pass(TMA): shared memory cannot hold the panel pipeline for %lld columns per SM", (long long)A->n / grid);
     return RLS_ERR_UNSUPPORTED;
   }
   L.nstages = S;
-  const int PR = LPC * Elem<T>::vec;
-  p->panels = (int)((A->m + PR - 1) / PR);
-  // lag: keep (lag + 1) panels inside ~40 % of L2, and give the y exchange at least ~8 us
-  const double panel_bytes = (double)PR * (double)A->n * sizeof(T);
-  const double l2 = (double)(c->l2_bytes ? c->l2_bytes : ((size_t)96 << 20));
-  int lag = (int)(0.40 * l2 / panel_bytes) - 1;
-  if (lag > T_MAXLAG) lag = T_MAXLAG;
-  if (lag < 1) lag = 1;
-  lag = std::max(1, std::min(T_MAXLAG, env_int("RLS_TMA_LAG", lag)));
-  p->grid = grid; p->sb = sb; p->nstages = S; p->stage_bytes = stage_bytes; p->nblk = nblk; p->nj = nch; p->lag = lag;
-  p->use_hint = env_int("RLS_TMA_HINT", 1);
-  p->p2_ldg = env_int("RLS_TMA_P2LDG", 0);   // experimental hybrid (phase 2 by plain loads); off: measured slower
+  p->grid = grid; p->sb = sb; p->nstages = S; p->stage_bytes = stage_bytes; p->nblk = nblk; p->nj = nch;
   p->smem_bytes = L.total();
-  p->kernel = pick_tma_kernel<T, LPC>(nch);
+  const int PR = T_LPC * Elem<T>::vec;
+  p->panels = (int)((A->m + PR - 1) / PR);
+  p->kernel = pick_tma_kernel<T>(nch);
   RLS_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
   int per_sm = 0;
   RLS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->kernel, T_THREADS, p->smem_bytes));
@@ -607,11 +452,10 @@ static int32_t tma_configure(TmaPlan* p) {
   const int fpe = Elem<T>::is_complex ? 2 : 1;
   cuuint64_t gdim[2] = {(cuuint64_t)A->m * fpe, (cuuint64_t)A->n};
   cuuint64_t gstr[1] = {(cuuint64_t)A->ld * sizeof(T)};
-  cuuint32_t box[2] = {(cuuint32_t)(LPC * 4), (cuuint32_t)T_BOXC};
+  cuuint32_t box[2] = {(cuuint32_t)T_PRF, (cuuint32_t)T_BOXC};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&p->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, A->d, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, LPC >= 16 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { rls_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return RLS_ERR_UNSUPPORTED; }
   return RLS_OK;
 }
@@ -626,23 +470,17 @@ int32_t rls_tma_plan_create(rls_ctx_s* c, rls_mat_s* A, TmaPlan** out) {
   TmaPlan* p = new TmaPlan();
   p->ctx = c;
   p->A = A;
-  // 256-byte column segments reach full HBM read bandwidth, 128-byte ones ~83 % (tools/seg_bw.cu)
-  p->lpc = env_int("RLS_TMA_LPC", 16);
-  if (p->lpc != 8 && p->lpc != 16) p->lpc = 16;
-  int32_t s;
-  if (A->dtype == RLS_C32) s = p->lpc == 16 ? tma_configure<float2, 16>(p) : tma_configure<float2, 8>(p);
-  else s = p->lpc == 16 ? tma_configure<float, 16>(p) : tma_configure<float, 8>(p);
+  int32_t s = (A->dtype == RLS_C32) ? tma_configure<float2>(p) : tma_configure<float>(p);
   if (s != RLS_OK) { delete p; return s; }
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  size_t o_slots = take(sizeof(float4) * T_NB * p->grid * 16);
-  size_t o_cnt = take(sizeof(unsigned) * T_NB * T_CSTRIDE);
+  size_t o_slots = take(sizeof(uint4) * T_NB * p->grid * 16);
   size_t o_ab = take(sizeof(int));
   if (cudaMalloc(&p->ws_mem, off) != cudaSuccess) { delete p; rls_set_error("cudaMalloc failed for the one-pass workspace"); return RLS_ERR_NOMEM; }
-  cudaMemsetAsync(p->ws_mem, 0, off, c->stream);
+  p->ws_bytes = off;
+  cudaMemsetAsync(p->ws_mem, 0, off, c->stream);   // tag 0 is never used by a launch
   char* b = (char*)p->ws_mem;
-  p->ws.slots = (float4*)(b + o_slots);
-  p->ws.counter = (unsigned*)(b + o_cnt);
+  p->ws.slots = (uint4*)(b + o_slots);
   p->ws.abort_flag = (int*)(b + o_ab);
   *out = p;
   return RLS_OK;
@@ -650,18 +488,17 @@ int32_t rls_tma_plan_create(rls_ctx_s* c, rls_mat_s* A, TmaPlan** out) {
 
 int32_t rls_tma_apply(TmaPlan* p, const void* x, void* g, const int* gate) {
   rls_ctx_s* c = p->ctx;
-  // the arrival counters are zeroed by a stream-ordered memset before every launch, so a launch that is
-  // gated off on the device (done() already true) leaves nothing behind for the next one
-  RLS_CUDA(cudaMemsetAsync(p->ws.counter, 0, sizeof(unsigned) * T_NB * T_CSTRIDE, c->stream));
+  if (p->tag_next > 0xffffffffu - (unsigned)(p->panels + 2)) {   // tag wrap: restart from a clean slate
+    RLS_CUDA(cudaMemsetAsync(p->ws.slots, 0, sizeof(uint4) * T_NB * p->grid * 16, c->stream));
+    p->tag_next = 1;
+  }
   TmaArgs a;
   a.x = x; a.g = g; a.ws = p->ws;
   a.m = p->A->m; a.n = p->A->n;
-  a.panels = p->panels; a.nblk = p->nblk; a.sb = p->sb; a.nstages = p->nstages; a.lag = p->lag; a.stage_bytes = p->stage_bytes;
-  a.use_hint = p->use_hint;
-  a.p2_ldg = p->p2_ldg;
-  a.A = p->A->d;
-  a.ld = p->A->ld;
+  a.panels = p->panels; a.nblk = p->nblk; a.sb = p->sb; a.nstages = p->nstages; a.stage_bytes = p->stage_bytes;
+  a.tag_base = p->tag_next;   // unique per launch, so a launch that is gated off on the device leaves nothing behind
   a.gate = gate;
+  p->tag_next += (unsigned)p->panels + 1u;
   void* args[] = {(void*)&p->tmap, (void*)&a};
   RLS_CUDA(cudaLaunchCooperativeKernel(p->kernel, dim3(p->grid), dim3(T_THREADS), args, p->smem_bytes, c->stream));
   c->launches++;
@@ -680,7 +517,6 @@ int32_t rls_tma_check_abort(TmaPlan* p) {
 }
 
 void rls_tma_describe(TmaPlan* p, char* buf, int len) {
-  snprintf(buf, len, "onepass/tma: grid=%d segment=%dB panels=%d lag=%d chunks/panel<=%d boxes/stage=%d stage=%dB stages=%d smem=%zuB hint=%d phase2=%s",
-           p->grid, p->lpc * 16, p->panels, p->lag, p->nj, p->sb, p->stage_bytes, p->nstages, p->smem_bytes, p->use_hint,
-           p->p2_ldg ? "ldg(L2)" : "tma(L2)");
+  snprintf(buf, len, "onepass/tma: smem-resident panels, flag-in-data exchange; grid=%d segment=128B panels=%d chunks/panel<=%d boxes/stage=%d stage=%dB stages=%d smem=%zuB",
+           p->grid, p->panels, p->nj, p->sb, p->stage_bytes, p->nstages, p->smem_bytes);
 }
