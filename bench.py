@@ -250,8 +250,10 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": f"normal operator A'(A x) [{AHA.describe()}]",
                          "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                         "note": "one launch = one normal-operator apply; the two-sweep form is two kernels (gemv_n + gemv_c), "
-                                 "each streaming A once at ~7.2 TB/s, and is scored against a single read of A"},
+                         "matrix_layout": A.layout,
+                         "note": "one launch = one normal-operator apply, scored against a single read of A (m*n*4 B); "
+                                 "onepass/rowmajor = cluster kernel that sweeps A once (+ a tiny partial-sum kernel); "
+                                 "twopass = gemv_n + gemv_c, two sweeps"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if cpu is not None:

@@ -62,6 +62,14 @@ enum {
   RLS_NORMAL_AUTO = 3
 };
 
+/* ---- device storage layout of a system matrix ---------------------------------
+ * The HOST side is always column-major (Julia `Matrix`).  On the device the library may
+ * keep the rows contiguous instead: the normal operator A'(A x) = sum_i conj(a_i)(a_i.x)
+ * then needs ONE sweep over HBM (csrc/rls_rowpass.cu).  Upload / download / Philox fills
+ * translate; results do not depend on the layout. */
+enum { RLS_LAYOUT_COLMAJOR = 0, RLS_LAYOUT_ROWMAJOR = 1,
+       RLS_LAYOUT_AUTO = 2 /* row-major whenever the one-pass cluster kernel supports the shape */ };
+
 /* ---- ADMM regTrafo (ADMM.jl:63,74) -------------------------------------------- */
 enum { RLS_TRAFO_IDENTITY = 0, RLS_TRAFO_GRADIENT = 1 };
 enum { RLS_VARY_RHO_NONE = 0, RLS_VARY_RHO_BALANCE = 1, RLS_VARY_RHO_PNP = 2 };
@@ -125,10 +133,15 @@ int32_t rls_vec_asum(rls_vec_t v, double* out);                           /* nor
 int32_t rls_vec_dot(rls_vec_t a, rls_vec_t b, double out_re_im[2]);
 
 /* ============================ matrices ======================================== */
-/* Dense column-major system matrix (or row shard of it).  host==NULL allocates
- * uninitialised device storage (fill with rls_mat_fill_philox or rls_mat_upload). */
+/* Dense system matrix (or row shard of it); the host array is column-major.  host==NULL allocates
+ * uninitialised device storage (fill with rls_mat_fill_philox or rls_mat_upload).  The device
+ * layout is the library's choice (RLS_LAYOUT_AUTO); use rls_mat_create_layout to force one. */
 int32_t rls_mat_create(rls_ctx_t ctx, int32_t dtype, int64_t m, int64_t n, const void* host, int64_t ld,
                        rls_mat_t* out);
+/* same, choosing the device layout (RLS_LAYOUT_*); host data stays column-major with leading dimension ld */
+int32_t rls_mat_create_layout(rls_ctx_t ctx, int32_t dtype, int64_t m, int64_t n, const void* host, int64_t ld,
+                              int32_t layout, rls_mat_t* out);
+int32_t rls_mat_layout(rls_mat_t A, int32_t* layout);
 /* adopt an existing device allocation (CuArray) without copying; not freed by destroy */
 int32_t rls_mat_wrap_device(rls_ctx_t ctx, int32_t dtype, int64_t m, int64_t n, void* dev, int64_t ld,
                             rls_mat_t* out);

@@ -21,6 +21,7 @@ RLS_NORMAL_TWOPASS, RLS_NORMAL_ONEPASS, RLS_NORMAL_GRAM, RLS_NORMAL_AUTO = 0, 1,
 RLS_TRAFO_IDENTITY, RLS_TRAFO_GRADIENT = 0, 1
 RLS_VARY_RHO_NONE, RLS_VARY_RHO_BALANCE, RLS_VARY_RHO_PNP = 0, 1, 2
 RLS_DIST_UNIFORM01, RLS_DIST_IH4 = 0, 1
+RLS_LAYOUT_COLMAJOR, RLS_LAYOUT_ROWMAJOR, RLS_LAYOUT_AUTO = 0, 1, 2
 RLS_MAX_TV_DIMS = 4
 
 
@@ -95,6 +96,8 @@ SIGNATURES = {
     "rls_vec_asum": [_P, _PF64],
     "rls_vec_dot": [_P, _P, _PF64],
     "rls_mat_create": [_P, _I32, _I64, _I64, _P, _I64, _PP],
+    "rls_mat_create_layout": [_P, _I32, _I64, _I64, _P, _I64, _I32, _PP],
+    "rls_mat_layout": [_P, _PI32],
     "rls_mat_wrap_device": [_P, _I32, _I64, _I64, _P, _I64, _PP],
     "rls_mat_destroy": [_P],
     "rls_mat_shape": [_P, _PI64, _PI64, _PI32],

@@ -170,9 +170,18 @@ class B200Vector:
         return p.value
 
 
+_LAYOUTS = {"col": capi.RLS_LAYOUT_COLMAJOR, "row": capi.RLS_LAYOUT_ROWMAJOR, "auto": capi.RLS_LAYOUT_AUTO}
+_LAYOUT_NAMES = {capi.RLS_LAYOUT_COLMAJOR: "col", capi.RLS_LAYOUT_ROWMAJOR: "row"}
+
+
 class B200Matrix:
-    """Dense column-major system matrix (or this rank's row shard of it) in HBM."""
-    def __init__(self, ctx, dtype, m, n, host=None):
+    """Dense system matrix (or this rank's row shard of it) in HBM.
+
+    The host side is always column-major (Julia `Matrix`).  `layout="row"` keeps the ROWS contiguous on
+    the device, which lets the normal operator A'(A x) sweep HBM once (csrc/rls_rowpass.cu); `layout="col"`
+    mirrors the host storage (what `rls_mat_wrap_device` adopts from a CuArray); `"auto"` (default) lets
+    the library choose (row-major whenever the one-pass kernel supports the shape)."""
+    def __init__(self, ctx, dtype, m, n, host=None, layout="auto"):
         self.ctx = _ctx(ctx)
         self.dtype = np.dtype(dtype)
         self.m, self.n = int(m), int(n)
@@ -182,23 +191,28 @@ class B200Matrix:
             host = np.asfortranarray(host, dtype=self.dtype)
             assert host.shape == (self.m, self.n)
             ptr = host.ctypes.data_as(C.c_void_p)
-        capi.call("rls_mat_create", self.ctx.handle, dtype_code(dtype), self.m, self.n, ptr, ld, C.byref(h))
+        capi.call("rls_mat_create_layout", self.ctx.handle, dtype_code(dtype), self.m, self.n, ptr, ld, _LAYOUTS[layout],
+                  C.byref(h))
         self.handle = h
         self._fin = weakref.finalize(self, capi.load().rls_mat_destroy, h)
+        lay = C.c_int32()
+        capi.call("rls_mat_layout", h, C.byref(lay))
+        self.layout = _LAYOUT_NAMES[lay.value]
 
     @property
     def shape(self):
         return (self.m, self.n)
 
     @classmethod
-    def from_numpy(cls, A, ctx=None):
+    def from_numpy(cls, A, ctx=None, layout="auto"):
         A = np.asarray(A)
-        return cls(ctx, A.dtype, A.shape[0], A.shape[1], host=A)
+        return cls(ctx, A.dtype, A.shape[0], A.shape[1], host=A, layout=layout)
 
     @classmethod
-    def philox(cls, dtype, m, n, seed, dist=capi.RLS_DIST_IH4, scale=1.0, row_offset=0, m_global=None, ctx=None):
+    def philox(cls, dtype, m, n, seed, dist=capi.RLS_DIST_IH4, scale=1.0, row_offset=0, m_global=None, ctx=None,
+               layout="auto"):
         """Generate A (or rows [row_offset, row_offset+m) of a global m_global x n matrix) on the device."""
-        A = cls(ctx, dtype, m, n)
+        A = cls(ctx, dtype, m, n, layout=layout)
         capi.call("rls_mat_fill_philox", A.handle, int(seed), int(dist), float(scale), int(row_offset),
                   int(m if m_global is None else m_global))
         return A

@@ -81,9 +81,11 @@ struct rls_vec_s {
 struct rls_mat_s {
   rls_ctx_s* ctx;
   int32_t dtype;
-  int64_t m, n, ld;
+  int64_t m, n, ld;   // ld: element stride between columns (col-major) or between rows (row-major)
   void* d;
   bool owned;
+  int32_t layout = RLS_LAYOUT_COLMAJOR;
+  struct RowPlan* rowplan = nullptr;  // row-major matrices: kernel plan shared by gemv / normal operator
 };
 
 static inline size_t rls_elem_size(int32_t dtype) { return dtype == RLS_C32 ? 8 : 4; }
@@ -115,6 +117,16 @@ int32_t rls_normal_shape(rls_normal_t op, int64_t* n, int32_t* dtype);
 rls_ctx_s* rls_normal_ctx(rls_normal_t op);
 rls_mat_s* rls_normal_matrix(rls_normal_t op);
 int32_t rls_normal_check_abort(rls_normal_t op);
+// row-major one-pass kernels (rls_rowpass.cu)
+struct RowPlan;
+int32_t rls_rowpass_plan_create(rls_ctx_s* c, rls_mat_s* A, RowPlan** out);
+void rls_rowpass_plan_destroy(RowPlan* p);
+int32_t rls_rowpass_normal(RowPlan* p, const void* x, void* res, const int* gate);
+int32_t rls_rowpass_gemv_n(RowPlan* p, const void* x, void* y, const int* gate);
+int32_t rls_rowpass_gemv_c(RowPlan* p, const void* y, void* g, const int* gate);
+int32_t rls_rowpass_check_abort(RowPlan* p);
+void rls_rowpass_describe(RowPlan* p, char* buf, int len);
+RowPlan* rls_mat_rowplan(rls_mat_s* A);  // lazily created, owned by the matrix
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------

@@ -401,6 +401,23 @@ __global__ void mat_philox_kernel(float* A, int64_t m, int64_t n, int64_t ld, ui
   }
 }
 
+// row-major storage: same counters (the VALUE of A[i,j] does not depend on the layout), threads run along a row
+template <bool CPLX>
+__global__ void mat_philox_rowmajor_kernel(float* A, int64_t m, int64_t n, int64_t ld, uint64_t seed, int dist, float scale,
+                                           int64_t row_offset, int64_t m_global) {
+  for (int64_t i = blockIdx.y; i < m; i += gridDim.y) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+      uint64_t idx = (uint64_t)(row_offset + i) + (uint64_t)j * (uint64_t)m_global;
+      if (CPLX) {
+        float2 v = make_float2(philox_value(seed, idx, 0ull, 0u, dist, scale), philox_value(seed, idx, 0ull, 1u, dist, scale));
+        ((float2*)A)[i * ld + j] = v;
+      } else {
+        A[i * ld + j] = philox_value(seed, idx, 0ull, 0u, dist, scale);
+      }
+    }
+  }
+}
+
 extern "C" int32_t rls_mat_fill_philox(rls_mat_t A, uint64_t seed, int32_t dist, float scale, int64_t row_offset,
                                        int64_t m_global) {
   RLS_CHECK_ARG(A, "mat is NULL");
@@ -409,6 +426,16 @@ extern "C" int32_t rls_mat_fill_philox(rls_mat_t A, uint64_t seed, int32_t dist,
                 (long long)row_offset, (long long)(row_offset + A->m), (long long)m_global);
   if (A->m == 0 || A->n == 0) return RLS_OK;
   RlsDeviceGuard g(A->ctx->device);
+  if (A->layout == RLS_LAYOUT_ROWMAJOR) {
+    dim3 rgrid((unsigned)std::min<int64_t>((A->n + 255) / 256, 64), (unsigned)std::min<int64_t>(A->m, 16384));
+    if (A->dtype == RLS_C32)
+      mat_philox_rowmajor_kernel<true><<<rgrid, 256, 0, A->ctx->stream>>>((float*)A->d, A->m, A->n, A->ld, seed, dist, scale, row_offset, m_global);
+    else
+      mat_philox_rowmajor_kernel<false><<<rgrid, 256, 0, A->ctx->stream>>>((float*)A->d, A->m, A->n, A->ld, seed, dist, scale, row_offset, m_global);
+    A->ctx->launches++;
+    RLS_CUDA(cudaGetLastError());
+    return RLS_OK;
+  }
   dim3 grid((unsigned)std::min<int64_t>((A->m + 255) / 256, 64), (unsigned)std::min<int64_t>(A->n, 16384));
   if (A->dtype == RLS_C32)
     mat_philox_kernel<true><<<grid, 256, 0, A->ctx->stream>>>((float*)A->d, A->m, A->n, A->ld, seed, dist, scale, row_offset, m_global);
@@ -488,26 +515,38 @@ extern "C" int32_t rls_vec_dot(rls_vec_t a, rls_vec_t b, double out[2]) {
 // ------------------------------------------------------------------------------------
 // matrices
 // ------------------------------------------------------------------------------------
-extern "C" int32_t rls_mat_create(rls_ctx_t ctx, int32_t dtype, int64_t m, int64_t n, const void* host, int64_t ld,
-                                  rls_mat_t* out) {
+extern "C" int32_t rls_mat_create_layout(rls_ctx_t ctx, int32_t dtype, int64_t m, int64_t n, const void* host, int64_t ld,
+                                         int32_t layout, rls_mat_t* out) {
   RLS_CHECK_ARG(ctx && out, "NULL argument");
   RLS_CHECK_ARG(dtype == RLS_F32 || dtype == RLS_C32, "unsupported dtype %d (Float32 / ComplexF32 only)", dtype);
   RLS_CHECK_ARG(m >= 0 && n >= 0, "negative shape");
   RLS_CHECK_ARG(!host || ld >= m, "ld < m");
+  RLS_CHECK_ARG(layout >= RLS_LAYOUT_COLMAJOR && layout <= RLS_LAYOUT_AUTO, "unknown layout %d", layout);
+  if (layout == RLS_LAYOUT_AUTO) {
+    // rows of at most 16 x 8192 floats fit the cluster decomposition of rls_rowpass.cu
+    const int64_t nf = n * (dtype == RLS_C32 ? 2 : 1);
+    const char* force = getenv("RLS_LAYOUT");
+    if (force && force[0] == 'c') layout = RLS_LAYOUT_COLMAJOR;
+    else layout = (nf + 3) / 4 * 4 <= 16 * 8192 ? RLS_LAYOUT_ROWMAJOR : RLS_LAYOUT_COLMAJOR;
+  }
   RlsDeviceGuard g(ctx->device);
-  // device leading dimension padded to a 16-byte multiple so every column supports 128-bit loads
+  // device leading dimension padded to a 16-byte multiple so every column (row) supports 128-bit
+  // loads and bulk copies; the padding is zeroed once and never written again
+  const bool rowmajor = layout == RLS_LAYOUT_ROWMAJOR;
   int64_t vec = dtype == RLS_C32 ? 2 : 4;
-  int64_t dld = ((m + vec - 1) / vec) * vec;
+  int64_t fast = rowmajor ? n : m, slow = rowmajor ? m : n;
+  int64_t dld = ((fast + vec - 1) / vec) * vec;
   if (dld == 0) dld = vec;
   rls_mat_s* A = new rls_mat_s{ctx, dtype, m, n, dld, nullptr, true};
-  size_t bytes = (size_t)dld * (size_t)(n > 0 ? n : 1) * rls_elem_size(dtype);
+  A->layout = layout;
+  size_t bytes = (size_t)dld * (size_t)(slow > 0 ? slow : 1) * rls_elem_size(dtype);
   cudaError_t e = cudaMalloc(&A->d, bytes);
   if (e != cudaSuccess) {
     delete A;
     rls_set_error("cudaMalloc(%zu) for %lldx%lld matrix failed: %s", bytes, (long long)m, (long long)n, cudaGetErrorString(e));
     return RLS_ERR_NOMEM;
   }
-  if (dld != m) cudaMemsetAsync(A->d, 0, bytes, ctx->stream);
+  if (dld != fast) cudaMemsetAsync(A->d, 0, bytes, ctx->stream);
   *out = A;
   if (host) {
     int32_t s = rls_mat_upload(A, host, ld);
@@ -518,6 +557,23 @@ extern "C" int32_t rls_mat_create(rls_ctx_t ctx, int32_t dtype, int64_t m, int64
     }
   }
   return RLS_OK;
+}
+
+extern "C" int32_t rls_mat_create(rls_ctx_t ctx, int32_t dtype, int64_t m, int64_t n, const void* host, int64_t ld,
+                                  rls_mat_t* out) {
+  return rls_mat_create_layout(ctx, dtype, m, n, host, ld, RLS_LAYOUT_AUTO, out);
+}
+
+extern "C" int32_t rls_mat_layout(rls_mat_t A, int32_t* layout) {
+  RLS_CHECK_ARG(A && layout, "NULL argument");
+  *layout = A->layout;
+  return RLS_OK;
+}
+
+RowPlan* rls_mat_rowplan(rls_mat_s* A) {
+  if (A->layout != RLS_LAYOUT_ROWMAJOR) return nullptr;
+  if (!A->rowplan && rls_rowpass_plan_create(A->ctx, A, &A->rowplan) != RLS_OK) A->rowplan = nullptr;
+  return A->rowplan;
 }
 
 extern "C" int32_t rls_mat_wrap_device(rls_ctx_t ctx, int32_t dtype, int64_t m, int64_t n, void* dev, int64_t ld,
@@ -532,10 +588,9 @@ extern "C" int32_t rls_mat_wrap_device(rls_ctx_t ctx, int32_t dtype, int64_t m, 
 extern "C" int32_t rls_mat_destroy(rls_mat_t A) {
   if (!A) return RLS_OK;
   RlsDeviceGuard g(A->ctx->device);
-  if (A->owned && A->d) {
-    cudaStreamSynchronize(A->ctx->stream);
-    cudaFree(A->d);
-  }
+  cudaStreamSynchronize(A->ctx->stream);
+  if (A->rowplan) rls_rowpass_plan_destroy(A->rowplan);
+  if (A->owned && A->d) cudaFree(A->d);
   delete A;
   return RLS_OK;
 }
@@ -548,11 +603,75 @@ extern "C" int32_t rls_mat_shape(rls_mat_t A, int64_t* m, int64_t* n, int32_t* d
   return RLS_OK;
 }
 
+// out(r,c) at c*ldo + r  <-  in(r,c) at r*ldi + c   (32x32 tiles through shared memory)
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_tiles_kernel(const T* __restrict__ in, int64_t ldi, T* __restrict__ out, int64_t ldo,
+                                                             int64_t R, int64_t C) {
+  __shared__ T tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int64_t tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
+  for (int64_t t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int64_t r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+    for (int k = ty; k < 32; k += 8)
+      if (r0 + k < R && c0 + tx < C) tile[k][tx] = in[(r0 + k) * ldi + c0 + tx];
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8)
+      if (c0 + k < C && r0 + tx < R) out[(c0 + k) * ldo + r0 + tx] = tile[tx][k];
+    __syncthreads();
+  }
+}
+
+template <typename T>
+static void launch_transpose(rls_ctx_s* c, const void* in, int64_t ldi, void* out, int64_t ldo, int64_t R, int64_t C) {
+  int64_t tiles = ((R + 31) / 32) * ((C + 31) / 32);
+  int grid = (int)std::min<int64_t>(tiles, (int64_t)c->sm_count * 16);
+  transpose_tiles_kernel<T><<<grid, 256, 0, c->stream>>>((const T*)in, ldi, (T*)out, ldo, R, C);
+  c->launches++;
+}
+
+// host (column-major) <-> device row-major: column blocks are staged column-major on the device and
+// transposed there, so the host side stays a plain strided copy
+static int32_t rowmajor_transfer(rls_mat_s* A, void* host, int64_t ld, bool upload) {
+  rls_ctx_s* c = A->ctx;
+  const size_t es = rls_elem_size(A->dtype);
+  int64_t chunk = std::max<int64_t>(32, ((int64_t)64 << 20) / std::max<int64_t>(1, (int64_t)(A->m * es)));
+  chunk = std::min<int64_t>((chunk + 31) / 32 * 32, std::max<int64_t>(A->n, 1));
+  void* stage = nullptr;
+  cudaError_t e = cudaMalloc(&stage, (size_t)A->m * (size_t)chunk * es);
+  if (e != cudaSuccess) { rls_set_error("cudaMalloc for the transpose staging buffer failed: %s", cudaGetErrorString(e)); return RLS_ERR_NOMEM; }
+  int32_t status = RLS_OK;
+  for (int64_t j0 = 0; j0 < A->n && status == RLS_OK; j0 += chunk) {
+    const int64_t nc = std::min<int64_t>(chunk, A->n - j0);
+    char* hp = (char*)host + (size_t)j0 * (size_t)ld * es;
+    char* dp = (char*)A->d + (size_t)j0 * es;
+    if (upload) {
+      e = cudaMemcpy2DAsync(stage, (size_t)A->m * es, hp, (size_t)ld * es, (size_t)A->m * es, (size_t)nc, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) {
+        // staged block: (r = column j, c = row i) at r*m + c  ->  A[i*ld + j]
+        if (A->dtype == RLS_C32) launch_transpose<float2>(c, stage, A->m, dp, A->ld, nc, A->m);
+        else launch_transpose<float>(c, stage, A->m, dp, A->ld, nc, A->m);
+        e = cudaGetLastError();
+      }
+    } else {
+      if (A->dtype == RLS_C32) launch_transpose<float2>(c, dp, A->ld, stage, A->m, A->m, nc);
+      else launch_transpose<float>(c, dp, A->ld, stage, A->m, A->m, nc);
+      e = cudaGetLastError();
+      if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(hp, (size_t)ld * es, stage, (size_t)A->m * es, (size_t)A->m * es, (size_t)nc, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { rls_set_error("CUDA error in row-major transfer: %s", cudaGetErrorString(e)); status = RLS_ERR_CUDA; }
+  }
+  cudaFree(stage);
+  return status;
+}
+
 extern "C" int32_t rls_mat_upload(rls_mat_t A, const void* host, int64_t ld) {
   RLS_CHECK_ARG(A && host, "NULL argument");
   RLS_CHECK_ARG(ld >= A->m, "ld < m");
   if (A->m == 0 || A->n == 0) return RLS_OK;
   RlsDeviceGuard g(A->ctx->device);
+  if (A->layout == RLS_LAYOUT_ROWMAJOR) return rowmajor_transfer(A, const_cast<void*>(host), ld, true);
   size_t es = rls_elem_size(A->dtype);
   RLS_CUDA(cudaMemcpy2DAsync(A->d, (size_t)A->ld * es, host, (size_t)ld * es, (size_t)A->m * es, (size_t)A->n,
                              cudaMemcpyHostToDevice, A->ctx->stream));
@@ -565,6 +684,7 @@ extern "C" int32_t rls_mat_download(rls_mat_t A, void* host, int64_t ld) {
   RLS_CHECK_ARG(ld >= A->m, "ld < m");
   if (A->m == 0 || A->n == 0) return RLS_OK;
   RlsDeviceGuard g(A->ctx->device);
+  if (A->layout == RLS_LAYOUT_ROWMAJOR) return rowmajor_transfer(A, host, ld, false);
   size_t es = rls_elem_size(A->dtype);
   RLS_CUDA(cudaMemcpy2DAsync(host, (size_t)ld * es, A->d, (size_t)A->ld * es, (size_t)A->m * es, (size_t)A->n,
                              cudaMemcpyDeviceToHost, A->ctx->stream));
@@ -591,10 +711,11 @@ extern "C" int32_t rls_mat_frob2(rls_mat_t A, double* out) {
   RlsDeviceGuard g(c->device);
   if (A->m == 0 || A->n == 0) { *out = 0.0; return RLS_OK; }
   int grid = c->sm_count * 8;
+  const int64_t fast = A->layout == RLS_LAYOUT_ROWMAJOR ? A->n : A->m, slow = A->layout == RLS_LAYOUT_ROWMAJOR ? A->m : A->n;
   if (A->dtype == RLS_C32)
-    frob2_kernel<float2><<<grid, RED_BLOCK, 0, c->stream>>>((const float2*)A->d, A->m, A->n, A->ld, c->red_partials, c->red_ticket, c->red_out);
+    frob2_kernel<float2><<<grid, RED_BLOCK, 0, c->stream>>>((const float2*)A->d, fast, slow, A->ld, c->red_partials, c->red_ticket, c->red_out);
   else
-    frob2_kernel<float><<<grid, RED_BLOCK, 0, c->stream>>>((const float*)A->d, A->m, A->n, A->ld, c->red_partials, c->red_ticket, c->red_out);
+    frob2_kernel<float><<<grid, RED_BLOCK, 0, c->stream>>>((const float*)A->d, fast, slow, A->ld, c->red_partials, c->red_ticket, c->red_out);
   c->launches++;
   RLS_CUDA(cudaGetLastError());
   RLS_CUDA(cudaMemcpyAsync(c->red_out_host, c->red_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));

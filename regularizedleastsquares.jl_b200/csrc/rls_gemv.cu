@@ -241,6 +241,12 @@ static bool aligned_for_vec(const rls_mat_s* A) {
 int32_t rls_gemv_n_raw(rls_mat_s* A, const void* x, void* y, const int* gate) {
   rls_ctx_s* c = A->ctx;
   if (A->m == 0) return RLS_OK;
+  if (A->layout == RLS_LAYOUT_ROWMAJOR) {
+    RowPlan* rp = rls_mat_rowplan(A);
+    if (!rp) return RLS_ERR_UNSUPPORTED;
+    if (A->n == 0) { RLS_CUDA(cudaMemsetAsync(y, 0, A->m * rls_elem_size(A->dtype), c->stream)); return RLS_OK; }
+    return rls_rowpass_gemv_n(rp, x, y, gate);
+  }
   RLS_CHECK_ARG(aligned_for_vec(A), "matrix storage must be 16-byte aligned with ld a multiple of %d elements",
                 A->dtype == RLS_C32 ? 2 : 4);
   const int64_t vec = A->dtype == RLS_C32 ? 2 : 4;
@@ -291,6 +297,12 @@ static void launch_gemv_c(rls_mat_s* A, const void* y, void* g, const int* gate)
 int32_t rls_gemv_c_raw(rls_mat_s* A, const void* y, void* g, const int* gate) {
   rls_ctx_s* c = A->ctx;
   if (A->n == 0) return RLS_OK;
+  if (A->layout == RLS_LAYOUT_ROWMAJOR) {
+    RowPlan* rp = rls_mat_rowplan(A);
+    if (!rp) return RLS_ERR_UNSUPPORTED;
+    if (A->m == 0) { RLS_CUDA(cudaMemsetAsync(g, 0, A->n * rls_elem_size(A->dtype), c->stream)); return RLS_OK; }
+    return rls_rowpass_gemv_c(rp, y, g, gate);
+  }
   RLS_CHECK_ARG(aligned_for_vec(A), "matrix storage must be 16-byte aligned with ld a multiple of %d elements",
                 A->dtype == RLS_C32 ? 2 : 4);
   if (A->dtype == RLS_C32) launch_gemv_c<float2>(A, y, g, gate);

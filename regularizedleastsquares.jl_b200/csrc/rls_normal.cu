@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(OP_THREADS, 2) normal_onepass_kernel(OnepassAr
 // tcgen05 split-precision GEMM is scheduled work)
 constexpr int GT = 32;
 template <typename T>
-__global__ void __launch_bounds__(GT* GT) gram_kernel(const T* __restrict__ A, int64_t ld, int64_t m, int64_t n, T* __restrict__ G) {
+__global__ void __launch_bounds__(GT* GT) gram_kernel(const T* __restrict__ A, int64_t rs, int64_t cs, int64_t m, int64_t n, T* __restrict__ G) {
   __shared__ T sa[GT][GT + 1];
   __shared__ T sb[GT][GT + 1];
   const int tx = threadIdx.x % GT, ty = threadIdx.x / GT;
@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(GT* GT) gram_kernel(const T* __restrict__ A, i
   for (int64_t k0 = 0; k0 < m; k0 += GT) {
     // coalesced along rows (k): thread (tx = k offset, ty = column offset)
     int64_t k = k0 + tx;
-    sa[ty][tx] = (k < m && i0 + ty < n) ? A[k + (i0 + ty) * ld] : Elem<T>::zero();
-    sb[ty][tx] = (k < m && j0 + ty < n) ? A[k + (j0 + ty) * ld] : Elem<T>::zero();
+    sa[ty][tx] = (k < m && i0 + ty < n) ? A[k * rs + (i0 + ty) * cs] : Elem<T>::zero();
+    sb[ty][tx] = (k < m && j0 + ty < n) ? A[k * rs + (j0 + ty) * cs] : Elem<T>::zero();
     __syncthreads();
 #pragma unroll 8
     for (int kk = 0; kk < GT; ++kk) Elem<T>::dotc(sa[ty][kk], sb[tx][kk], accr, acci);
@@ -343,6 +343,7 @@ struct rls_normal_s {
   int32_t dtype_ = 0;
   // one-pass: TMA/shared-memory-resident kernel when supported, else the L2-lag kernel below
   TmaPlan* tma = nullptr;
+  RowPlan* row = nullptr;   // row-major A: cluster kernel plan (owned by the matrix)
   OnepassWs ws{};
   void* ws_mem = nullptr;
   int op_grid = 0, op_lpc = 0, op_maxc = 0, op_cpw = 0, op_lag = 2, op_hint = 1;
@@ -437,14 +438,15 @@ static int32_t alloc_onepass_ws(rls_normal_s* op) {
 static int32_t build_gram(rls_normal_s* op) {
   rls_mat_s* A = op->A;
   rls_ctx_s* c = op->ctx;
-  RLS_TRY(rls_mat_create(c, A->dtype, A->n, A->n, nullptr, A->n, &op->G));
+  RLS_TRY(rls_mat_create_layout(c, A->dtype, A->n, A->n, nullptr, A->n, RLS_LAYOUT_COLMAJOR, &op->G));
   // dense n x n with ld == n (padded ld would break the symmetric indexing in gram_kernel)
   RLS_CHECK_ARG(op->G->ld == A->n, "Gram form needs n to be a multiple of %d", A->dtype == RLS_C32 ? 2 : 4);
   dim3 grid((unsigned)((A->n + GT - 1) / GT), (unsigned)((A->n + GT - 1) / GT));
+  const int64_t rs = A->layout == RLS_LAYOUT_ROWMAJOR ? A->ld : 1, cs = A->layout == RLS_LAYOUT_ROWMAJOR ? 1 : A->ld;
   if (A->dtype == RLS_C32)
-    gram_kernel<float2><<<grid, GT * GT, 0, c->stream>>>((const float2*)A->d, A->ld, A->m, A->n, (float2*)op->G->d);
+    gram_kernel<float2><<<grid, GT * GT, 0, c->stream>>>((const float2*)A->d, rs, cs, A->m, A->n, (float2*)op->G->d);
   else
-    gram_kernel<float><<<grid, GT * GT, 0, c->stream>>>((const float*)A->d, A->ld, A->m, A->n, (float*)op->G->d);
+    gram_kernel<float><<<grid, GT * GT, 0, c->stream>>>((const float*)A->d, rs, cs, A->m, A->n, (float*)op->G->d);
   c->launches++;
   RLS_CUDA(cudaGetLastError());
   if (c->nranks > 1) RLS_TRY(rls_allreduce_raw(c, op->G->d, A->n * A->n * (A->dtype == RLS_C32 ? 2 : 1)));
@@ -463,6 +465,13 @@ extern "C" int32_t rls_normal_create(rls_mat_t A, int32_t form, rls_normal_t* ou
   op->n_ = A->n;
   op->dtype_ = A->dtype;
   const double bytes = (double)A->m * (double)A->n * (double)rls_elem_size(A->dtype);
+  if (A->layout == RLS_LAYOUT_ROWMAJOR && form != RLS_NORMAL_GRAM) {
+    // rows contiguous: the cluster kernel of rls_rowpass.cu sweeps A once (ONEPASS, also what AUTO
+    // resolves to) or runs as two sweeps y = A x, g = A' y (TWOPASS, kept for comparison)
+    op->row = rls_mat_rowplan(A);
+    if (!op->row) { delete op; return RLS_ERR_UNSUPPORTED; }
+    if (form == RLS_NORMAL_AUTO) form = RLS_NORMAL_ONEPASS;
+  }
   if (form == RLS_NORMAL_AUTO) {
     // Measured on B200 (profiles/): the two-sweep form runs at the HBM read roofline (7.3 TB/s), the
     // one-pass panel kernels currently reach the same wall time with half the DRAM traffic.  AUTO
@@ -472,7 +481,7 @@ extern "C" int32_t rls_normal_create(rls_mat_t A, int32_t form, rls_normal_t* ou
     const bool big = bytes >= 4.0 * (double)(A->ctx->l2_bytes ? A->ctx->l2_bytes : ((size_t)64 << 20));
     form = (want && atoi(want) != 0 && big) ? RLS_NORMAL_ONEPASS : RLS_NORMAL_TWOPASS;
   }
-  if (form == RLS_NORMAL_ONEPASS) {
+  if (form == RLS_NORMAL_ONEPASS && !op->row) {
     const char* impl = getenv("RLS_ONEPASS_IMPL");
     const bool want_l2 = impl && strcmp(impl, "l2") == 0;
     if (!want_l2 && rls_tma_plan_create(A->ctx, A, &op->tma) != RLS_OK) {
@@ -517,7 +526,9 @@ extern "C" int32_t rls_normal_destroy(rls_normal_t op) {
 // human-readable description of the kernel plan behind this operator (diagnostics / bench config)
 extern "C" int32_t rls_normal_describe(rls_normal_t op, char* buf, int32_t len) {
   RLS_CHECK_ARG(op && buf && len > 0, "NULL argument");
-  if (op->form == RLS_NORMAL_ONEPASS && op->tma) rls_tma_describe(op->tma, buf, len);
+  if (op->form == RLS_NORMAL_ONEPASS && op->row) rls_rowpass_describe(op->row, buf, len);
+  else if (op->row) snprintf(buf, len, "twopass/rowmajor: gemv_n + gemv_c (cluster kernels)");
+  else if (op->form == RLS_NORMAL_ONEPASS && op->tma) rls_tma_describe(op->tma, buf, len);
   else if (op->form == RLS_NORMAL_ONEPASS)
     snprintf(buf, len, "onepass/l2: grid=%d lanes/column=%d cols/lane<=%d cols/warp=%d lag=%d hint=%d", op->op_grid, op->op_lpc,
              op->op_maxc, op->op_cpw, op->op_lag, op->op_hint);
@@ -609,7 +620,8 @@ int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const in
       break;
     case RLS_NORMAL_ONEPASS:
       if (op->A->m == 0) { RLS_CUDA(cudaMemsetAsync(out, 0, op->A->n * rls_elem_size(op->A->dtype), c->stream)); break; }
-      if (op->tma) RLS_TRY(rls_tma_apply(op->tma, x, out, gate));
+      if (op->row) RLS_TRY(rls_rowpass_normal(op->row, x, out, gate));
+      else if (op->tma) RLS_TRY(rls_tma_apply(op->tma, x, out, gate));
       else RLS_TRY(launch_onepass(op, x, out, gate));
       break;
     default:
@@ -627,6 +639,7 @@ int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const in
 }
 
 int32_t rls_normal_check_abort(rls_normal_t op) {
+  if (op->row) return rls_rowpass_check_abort(op->row);
   if (op->form != RLS_NORMAL_ONEPASS) return RLS_OK;
   if (op->tma) return rls_tma_check_abort(op->tma);
   int flag = 0;

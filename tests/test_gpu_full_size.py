@@ -23,6 +23,12 @@ def test_c2_operator_properties(rls, ctx):
     two = rls.B200NormalOp(A, form="twopass").apply(x).to_numpy()
     one = rls.B200NormalOp(A, form="onepass").apply(x).to_numpy()
     assert rel(one, two) < 2e-6
+    # the column-major storage (what rls_mat_wrap_device adopts) holds the same matrix and gives the same result
+    assert A.layout == "row"
+    Ac = rls.B200Matrix.philox(np.float32, m, n, seed=12345, scale=1.0 / np.sqrt(m), ctx=ctx, layout="col")
+    assert rel(rls.B200NormalOp(Ac, form="twopass").apply(x).to_numpy(), one) < 2e-6
+    assert rel(rls.B200NormalOp(Ac, form="onepass").apply(x).to_numpy(), one) < 2e-6
+    del Ac
     # x' (A'A x) == ||A x||^2
     assert abs(float(np.dot(x.to_numpy().astype(np.float64), two.astype(np.float64))) - Ax.norm() ** 2) < 1e-5 * Ax.norm() ** 2
     # row subsample against NumPy on the same Philox entries

@@ -13,25 +13,34 @@ DTYPES = [np.float32, np.complex64]
 SHAPES = [(256, 512), (1023, 771), (1, 17), (19, 1), (4100, 300), (130, 6000), (8192 + 8, 1536)]
 
 
+LAYOUTS = ["row", "col"]
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_philox_bit_exact(rls, ctx, dtype):
-    A = rls.B200Matrix.philox(dtype, 300, 70, seed=99, scale=0.25, ctx=ctx).to_numpy()
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_philox_bit_exact(rls, ctx, dtype, layout):
+    A = rls.B200Matrix.philox(dtype, 300, 70, seed=99, scale=0.25, ctx=ctx, layout=layout).to_numpy()
     assert np.array_equal(A, philox_matrix(dtype, 300, 70, 99, IH4, 0.25))
     # a row shard regenerates exactly its rows of the global matrix
-    S = rls.B200Matrix.philox(dtype, 100, 70, seed=99, scale=0.25, row_offset=120, m_global=300, ctx=ctx).to_numpy()
+    S = rls.B200Matrix.philox(dtype, 100, 70, seed=99, scale=0.25, row_offset=120, m_global=300, ctx=ctx,
+                              layout=layout).to_numpy()
     assert np.array_equal(S, A[120:220])
     v = rls.B200Vector(ctx, dtype, 1000).fill_philox(5, stream=3, dist=0, scale=2.0).to_numpy()
     assert np.array_equal(v, philox_vector(dtype, 1000, 5, 3, UNIFORM01, 2.0))
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", SHAPES)
-def test_gemv_n_c(rls, ctx, dtype, shape):
+@pytest.mark.parametrize("shape", SHAPES + [(37, 20000), (9, 70001)])
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_gemv_n_c(rls, ctx, dtype, shape, layout):
     m, n = shape
+    if layout == "row" and n * (2 if np.dtype(dtype).kind == "c" else 1) > 131072:
+        pytest.skip("row-major layout supports rows of at most 131072 floats")
     A, _ = rand_matrix(dtype, m, n, 11)
     x = rand_vector(dtype, n, 12)
     y = rand_vector(dtype, m, 13)
-    Ad = rls.B200Matrix.from_numpy(A, ctx)
+    Ad = rls.B200Matrix.from_numpy(A, ctx, layout=layout)
+    assert Ad.layout == layout
     assert np.array_equal(Ad.to_numpy(), A)
     yd = Ad.mul(rls.B200Vector.from_numpy(x, ctx)).to_numpy()
     gd = Ad.adjoint_mul(rls.B200Vector.from_numpy(y, ctx)).to_numpy()
@@ -42,12 +51,15 @@ def test_gemv_n_c(rls, ctx, dtype, shape):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("form", ["twopass", "onepass", "gram"])
-@pytest.mark.parametrize("shape", [(256, 512), (1023, 772), (515, 2048), (64, 4096), (3000, 1000)])
-def test_normal_operator_forms(rls, ctx, dtype, form, shape):
+@pytest.mark.parametrize("shape", [(256, 512), (1023, 772), (515, 2048), (64, 4096), (3000, 1000), (50, 20000), (23, 40000)])
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_normal_operator_forms(rls, ctx, dtype, form, shape, layout):
     m, n = shape
+    if form == "gram" and n > 4096:
+        pytest.skip("Gram matrix of a wide system is not interesting here")
     A, _ = rand_matrix(dtype, m, n, 21)
     x = rand_vector(dtype, n, 22)
-    Ad = rls.B200Matrix.from_numpy(A, ctx)
+    Ad = rls.B200Matrix.from_numpy(A, ctx, layout=layout)
     op = rls.B200NormalOp(Ad, form=form)
     assert op.form == form
     xd = rls.B200Vector.from_numpy(x, ctx)
@@ -71,7 +83,7 @@ def test_onepass_tma_variants(rls, ctx, lpc, stage_kb, lag, hint, monkeypatch):
         for (m, n) in [(2052, 9000), (70, 33), (1, 5000), (4099, 20000), (300, 70000)]:
             A, _ = rand_matrix(dtype, m, n, 31)
             x = rand_vector(dtype, n, 32)
-            op = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx), form="onepass")
+            op = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx, layout="col"), form="onepass")
             xd = rls.B200Vector.from_numpy(x, ctx)
             g = op.apply(xd).to_numpy()
             A64 = A.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
@@ -90,7 +102,7 @@ def test_onepass_variants(rls, ctx, lpc, lag, monkeypatch):
         m, n = 2052, 9000
         A, _ = rand_matrix(dtype, m, n, 31)
         x = rand_vector(dtype, n, 32)
-        op = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx), form="onepass")
+        op = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx, layout="col"), form="onepass")
         g = op.apply(rls.B200Vector.from_numpy(x, ctx)).to_numpy()
         A64 = A.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
         assert rel(g, A64.conj().T @ (A64 @ x)) < 3e-6
