@@ -219,7 +219,8 @@ def run_b200(args):
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get(AHA.form)
+                tr = json.load(f)
+                traffic = tr.get(f"{AHA.form}/{A.layout}", tr.get(AHA.form) if A.layout == "col" else None)
         except Exception:
             traffic = None
     clocks = sampler.summary()

@@ -171,6 +171,10 @@ int32_t rls_normal_form(rls_normal_t op, int32_t* form);
 int32_t rls_normal_describe(rls_normal_t op, char* buf, int32_t len);
 /* mul!(res, AHA, x): FISTA.jl:152, POGM.jl:181, OptISTA.jl:182, CGNR.jl:151, cg! in ADMM.jl:244 */
 int32_t rls_normal_apply(rls_normal_t op, rls_vec_t x, rls_vec_t res);
+/* res_k = AHA x_k for K right-hand sides sharing one operator (MultiThreading.jl:45-78 applies it K times).
+ * Lazy forms on a row-major A run as two tensor-core GEMMs (Y = A X, G = A' Y; FP32-accurate split-precision
+ * tcgen05) that read A once each; other cases fall back to K single applies. */
+int32_t rls_normal_apply_batch(rls_normal_t op, int32_t K, const rls_vec_t* xs, const rls_vec_t* outs);
 /* power_iterations(AHA, b; rtol, maxiter) Utils.jl:262-287; b0 replaces the randn start vector */
 int32_t rls_power_iterations(rls_normal_t op, rls_vec_t b0, double rtol, int32_t maxiter, double* lambda_max);
 

@@ -277,6 +277,15 @@ class B200NormalOp:
         capi.call("rls_normal_apply", self.handle, x.handle, out.handle)
         return out
 
+    def apply_batch(self, xs, outs=None):
+        """res_k = AHA x_k for a list of vectors (tensor-core GEMM path when A is row-major)"""
+        K = len(xs)
+        outs = [B200Vector(self.ctx, self.dtype, self.n) for _ in range(K)] if outs is None else outs
+        xa = (C.c_void_p * K)(*[x.handle for x in xs])
+        oa = (C.c_void_p * K)(*[o.handle for o in outs])
+        capi.call("rls_normal_apply_batch", self.handle, K, xa, oa)
+        return outs
+
     def power_iterations(self, b0, rtol=1e-3, maxiter=30):
         lam = C.c_double()
         capi.call("rls_power_iterations", self.handle, b0.handle, float(rtol), int(maxiter), C.byref(lam))

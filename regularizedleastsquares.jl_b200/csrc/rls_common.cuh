@@ -127,6 +127,15 @@ int32_t rls_rowpass_gemv_c(RowPlan* p, const void* y, void* g, const int* gate);
 int32_t rls_rowpass_check_abort(RowPlan* p);
 void rls_rowpass_describe(RowPlan* p, char* buf, int len);
 RowPlan* rls_mat_rowplan(rls_mat_s* A);  // lazily created, owned by the matrix
+// tensor-core paths (rls_tc.cu): batched normal operator for K right-hand sides, Gram build
+struct TcBatchPlan;
+bool rls_tc_batch_supported(const rls_mat_s* A, int K);
+int32_t rls_tc_batch_create(rls_mat_s* A, int K, TcBatchPlan** out);
+void rls_tc_batch_destroy(TcBatchPlan* p);
+int32_t rls_tc_batch_apply(TcBatchPlan* p, const void* const* xs, void* const* outs, const int* const* gates);
+int32_t rls_tc_batch_check_abort(TcBatchPlan* p);
+int32_t rls_tc_gram(rls_mat_s* A, rls_mat_s* G);
+int32_t rls_normal_apply_batch_raw(rls_normal_t op, int K, const void* const* xs, void* const* outs, const int* const* gates);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------

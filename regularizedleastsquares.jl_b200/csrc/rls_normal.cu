@@ -344,6 +344,9 @@ struct rls_normal_s {
   // one-pass: TMA/shared-memory-resident kernel when supported, else the L2-lag kernel below
   TmaPlan* tma = nullptr;
   RowPlan* row = nullptr;   // row-major A: cluster kernel plan (owned by the matrix)
+  bool gram_on_tensor_cores = false;
+  TcBatchPlan* tc = nullptr;  // tensor-core plan of the multi-RHS apply (created on first use for a given K)
+  int tc_K = 0;
   OnepassWs ws{};
   void* ws_mem = nullptr;
   int op_grid = 0, op_lpc = 0, op_maxc = 0, op_cpw = 0, op_lag = 2, op_hint = 1;
@@ -441,6 +444,18 @@ static int32_t build_gram(rls_normal_s* op) {
   RLS_TRY(rls_mat_create_layout(c, A->dtype, A->n, A->n, nullptr, A->n, RLS_LAYOUT_COLMAJOR, &op->G));
   // dense n x n with ld == n (padded ld would break the symmetric indexing in gram_kernel)
   RLS_CHECK_ARG(op->G->ld == A->n, "Gram form needs n to be a multiple of %d", A->dtype == RLS_C32 ? 2 : 4);
+  // tensor cores (FP32-accurate split-precision tcgen05 GEMM) when A is row-major; RLS_GRAM_CUDA_CORES=1 keeps the
+  // tiled CUDA-core kernel (the comparison baseline)
+  const char* cc = getenv("RLS_GRAM_CUDA_CORES");
+  if (A->layout == RLS_LAYOUT_ROWMAJOR && !(cc && atoi(cc) != 0)) {
+    int32_t st = rls_tc_gram(A, op->G);
+    if (st == RLS_OK) {
+      op->gram_on_tensor_cores = true;
+      if (c->nranks > 1) RLS_TRY(rls_allreduce_raw(c, op->G->d, A->n * A->n * (A->dtype == RLS_C32 ? 2 : 1)));
+      return RLS_OK;
+    }
+    if (st != RLS_ERR_UNSUPPORTED && st != RLS_ERR_NOMEM) return st;
+  }
   dim3 grid((unsigned)((A->n + GT - 1) / GT), (unsigned)((A->n + GT - 1) / GT));
   const int64_t rs = A->layout == RLS_LAYOUT_ROWMAJOR ? A->ld : 1, cs = A->layout == RLS_LAYOUT_ROWMAJOR ? 1 : A->ld;
   if (A->dtype == RLS_C32)
@@ -519,6 +534,7 @@ extern "C" int32_t rls_normal_destroy(rls_normal_t op) {
   if (op->G && op->own_G) rls_mat_destroy(op->G);
   if (op->ws_mem) cudaFree(op->ws_mem);
   if (op->tma) rls_tma_plan_destroy(op->tma);
+  if (op->tc) rls_tc_batch_destroy(op->tc);
   delete op;
   return RLS_OK;
 }
@@ -532,7 +548,9 @@ extern "C" int32_t rls_normal_describe(rls_normal_t op, char* buf, int32_t len) 
   else if (op->form == RLS_NORMAL_ONEPASS)
     snprintf(buf, len, "onepass/l2: grid=%d lanes/column=%d cols/lane<=%d cols/warp=%d lag=%d hint=%d", op->op_grid, op->op_lpc,
              op->op_maxc, op->op_cpw, op->op_lag, op->op_hint);
-  else if (op->form == RLS_NORMAL_GRAM) snprintf(buf, len, "gram: dense %lldx%lld", (long long)op->n_, (long long)op->n_);
+  else if (op->form == RLS_NORMAL_GRAM)
+    snprintf(buf, len, "gram: dense %lldx%lld%s", (long long)op->n_, (long long)op->n_,
+             op->gram_on_tensor_cores ? " (built on tensor cores: tcgen05 kind::tf32 x3 split)" : "");
   else snprintf(buf, len, "twopass: gemv_n + gemv_c");
   return RLS_OK;
 }
@@ -635,6 +653,41 @@ int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const in
     c->launches++;
     RLS_CUDA(cudaGetLastError());
   }
+  return RLS_OK;
+}
+
+// res_k = AHA x_k for K right-hand sides.  Lazy forms on a row-major A: two tensor-core GEMMs that read A once
+// each (rls_tc.cu); otherwise K single applies.
+int32_t rls_normal_apply_batch_raw(rls_normal_t op, int K, const void* const* xs, void* const* outs, const int* const* gates) {
+  const char* off = getenv("RLS_BATCH_TENSOR_CORES");
+  const bool want = !(off && atoi(off) == 0);
+  if (want && op->form != RLS_NORMAL_GRAM && op->A && rls_tc_batch_supported(op->A, K)) {
+    if (op->tc && op->tc_K != K) { rls_tc_batch_destroy(op->tc); op->tc = nullptr; }
+    if (!op->tc) {
+      int32_t st = rls_tc_batch_create(op->A, K, &op->tc);
+      if (st != RLS_OK) op->tc = nullptr;
+      op->tc_K = K;
+    }
+    if (op->tc) return rls_tc_batch_apply(op->tc, xs, outs, gates);
+  }
+  for (int k = 0; k < K; ++k) RLS_TRY(rls_normal_apply_raw(op, xs[k], outs[k], gates ? gates[k] : nullptr));
+  return RLS_OK;
+}
+
+extern "C" int32_t rls_normal_apply_batch(rls_normal_t op, int32_t K, const rls_vec_t* xs, const rls_vec_t* outs) {
+  RLS_CHECK_ARG(op && xs && outs && K >= 1, "bad argument");
+  std::vector<const void*> xp(K);
+  std::vector<void*> op_(K);
+  for (int k = 0; k < K; ++k) {
+    RLS_CHECK_ARG(xs[k] && outs[k], "NULL vector");
+    RLS_CHECK_ARG(xs[k]->len == op->n_ && outs[k]->len == op->n_ && xs[k]->dtype == op->dtype_ && outs[k]->dtype == op->dtype_,
+                  "normal_apply_batch: shape / dtype mismatch in column %d", k);
+    RLS_CHECK_ARG(xs[k]->d != outs[k]->d, "normal_apply_batch: x and res must not alias");
+    xp[k] = xs[k]->d; op_[k] = outs[k]->d;
+  }
+  RlsDeviceGuard g(op->ctx->device);
+  RLS_TRY(rls_normal_apply_batch_raw(op, K, xp.data(), op_.data(), nullptr));
+  if (op->tc) return rls_tc_batch_check_abort(op->tc);
   return RLS_OK;
 }
 

@@ -30,7 +30,7 @@ namespace {
 
 constexpr int RP_CW = 16;              // compute warps
 constexpr int RP_CT = RP_CW * 32;      // compute threads
-constexpr int RP_THREADS = RP_CT + 32; // + producer warp
+constexpr int RP_THREADS = RP_CT;      // no producer warp: 16 warps -> 128 registers per thread
 constexpr int RP_MAXG = 16;            // largest cluster
 constexpr int RP_MAXR = 4;             // rows per round (template parameter R <= RP_MAXR)
 enum { RP_NORMAL = 0, RP_GEMV_N = 1, RP_GEMV_C = 2 };
@@ -99,7 +99,6 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(RP_CT) : "memory"); }
 // Deposit one float in CTA `peer`'s copy of a shared slot and signal its mbarrier in the SAME message
 // (st.async + complete_tx): no release fence on the sender (a release.cluster arrive compiles to
 // MEMBAR.ALL.GPU), no L1 invalidate on the receiver.
@@ -129,7 +128,7 @@ template <> __device__ __forceinline__ void axpy_conj<2>(float4& g, float4 a, fl
   g.z = fmaf(a.z, yr, g.z); g.z = fmaf(a.w, yi, g.z); g.w = fmaf(a.z, yi, g.w); g.w = fmaf(-a.w, yr, g.w);
 }
 
-template <int FPE, int V, int R, int MODE>
+template <int FPE, int V, int R, int MODE, bool FULL>
 __global__ void __launch_bounds__(RP_THREADS, 1) rowpass_kernel(RowpassArgs p) {
   if (p.gate && *p.gate) return;  // device-side done() gate: uniform over the grid
   constexpr int RF = R * FPE;     // floats exchanged per round
@@ -140,235 +139,53 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowpass_kernel(RowpassArgs p) {
 
   float* ring = reinterpret_cast<float*>(smem);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NS * W * 4);
-  uint64_t* empty = full + NS;
-  uint64_t* ybar = empty + NS;                                   // [2]
+  uint64_t* ybar = full + NS;                                    // [2]
   float* wpart = reinterpret_cast<float*>(ybar + 2);             // [RP_CW][RF]
   float* ybuf = wpart + RP_CW * RF;                              // [2][RP_MAXG][RF]
   float* ysm = ybuf + 2 * RP_MAXG * RF;                          // [RF]
   volatile int* s_abort = reinterpret_cast<volatile int*>(ysm + RF);
 
-  if (tid == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], RP_CW); }
-    mbar_init(&ybar[0], 1);  // one local arrive.expect_tx per round; the peers' st.async complete the bytes
-    mbar_init(&ybar[1], 1);
-    *s_abort = 0;
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  cluster_sync_all();  // peers' barriers are initialised before anyone posts to them
-
   const int nf_pad = (p.nf + 3) & ~3;
   const int col0 = (int)rank * W;
   const int slice = max(0, min(W, nf_pad - col0));  // floats of this CTA's slice (multiple of 4)
   const int64_t nrounds = (p.m + R - 1) / R;
-
-  if (warp == RP_CW) {
-    // ------------------------------ producer ------------------------------------------
-    if (lane == 0) {
-      unsigned long long pol;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-      int s = 0;
-      unsigned phase = 0;
-      for (int64_t rr = cid; rr < nrounds; rr += ncl) {
-        const int rv = (int)min((int64_t)R, p.m - rr * R);
-        for (int r = 0; r < rv; ++r) {
-          mbar_wait<false>(&empty[s], phase ^ 1u, s_abort, p.abort_flag);
-          if (slice > 0) {
-            mbar_expect_tx(&full[s], (unsigned)slice * 4u);
-            bulk_load(ring + (size_t)s * W, p.A + (rr * R + r) * p.ldf + col0, (unsigned)slice * 4u, &full[s], pol);
-          } else {
-            mbar_arrive(&full[s]);
-          }
-          if (++s == NS) { s = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else {
-    // ------------------------------ compute -------------------------------------------
-    bool valid[V];
-    float4 xr[V], g[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int q4 = 4 * (tid + v * RP_CT);
-      valid[v] = q4 < slice;
-      g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      xr[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (MODE != RP_GEMV_C && valid[v]) {
-        const int c = col0 + q4;
-        if (c + 3 < p.nf) xr[v] = *reinterpret_cast<const float4*>(p.x + c);
-        else {
-          xr[v].x = c < p.nf ? p.x[c] : 0.f;
-          xr[v].y = c + 1 < p.nf ? p.x[c + 1] : 0.f;
-          xr[v].z = c + 2 < p.nf ? p.x[c + 2] : 0.f;
-        }
-      }
-    }
-    int s = 0;
-    unsigned phase = 0, par = 0, ypar = 0;
-    for (int64_t rr = cid; rr < nrounds; rr += ncl) {
-      const int rv = (int)min((int64_t)R, p.m - rr * R);
-      float4 a[R][V];
-      float acc[R][FPE];
-      float y[RF];
-      if (MODE == RP_GEMV_C) {
-#pragma unroll
-        for (int k = 0; k < RF; ++k) y[k] = (k / FPE) < rv ? __ldg(p.yin + (rr * R) * FPE + k) : 0.f;
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-#pragma unroll
-        for (int e = 0; e < FPE; ++e) acc[r][e] = 0.f;
-        if (r < rv) {
-          mbar_wait<false>(&full[s], phase, s_abort, p.abort_flag);
-          const float4* st = reinterpret_cast<const float4*>(ring + (size_t)s * W);
-#pragma unroll
-          for (int v = 0; v < V; ++v) a[r][v] = valid[v] ? st[tid + v * RP_CT] : make_float4(0.f, 0.f, 0.f, 0.f);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[s]);
-          if (++s == NS) { s = 0; phase ^= 1u; }
-          if (MODE != RP_GEMV_C) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) dot_acc<FPE>(acc[r], a[r][v], xr[v]);
-          }
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; ++v) a[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      if (MODE != RP_GEMV_C) {
-        // warp -> CTA -> cluster reduction of the RF partial dot products, fixed order throughout
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int e = 0; e < FPE; ++e) {
-            const float w = warp_sum(acc[r][e]);
-            if (lane == 0) wpart[warp * RF + r * FPE + e] = w;
-          }
-        bar_compute();
-        if (warp == 0) {
-          float pv = 0.f;
-          if (lane < RF) {
-#pragma unroll
-            for (int w = 0; w < RP_CW; ++w) pv += wpart[w * RF + lane];
-          }
-          float tot = pv;
-          if (G > 1) {
-            constexpr int PER = 32 / RF;  // peers served per pass over the warp
-            const int k = lane % RF;
-            const float pk = __shfl_sync(0xffffffffu, pv, k);
-            if (lane == 0) mbar_expect_tx(&ybar[par], G * RF * 4u);
-            if (lane < PER * RF)
-              for (unsigned peer = lane / RF; peer < G; peer += PER)
-                dsmem_post(&ybuf[(par * RP_MAXG + rank) * RF + k], &ybar[par], peer, pk);
-            mbar_wait<false>(&ybar[par], ypar, s_abort, p.abort_flag);
-            tot = 0.f;
-            if (lane < RF)
-              for (unsigned c = 0; c < G; ++c) tot += ybuf[(par * RP_MAXG + c) * RF + lane];
-          }
-          if (lane < RF) {
-            ysm[lane] = tot;
-            if (MODE == RP_GEMV_N && rank == 0 && (lane / FPE) < rv) p.yout[(rr * R) * FPE + lane] = tot;
-          }
-        }
-        bar_compute();
-#pragma unroll
-        for (int k = 0; k < RF; ++k) y[k] = ysm[k];
-        par ^= 1u;
-        if (par == 0) ypar ^= 1u;
-      }
-      if (MODE != RP_GEMV_N) {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int v = 0; v < V; ++v) axpy_conj<FPE>(g[v], a[r][v], y[r * FPE], y[r * FPE + FPE - 1]);
-      }
-    }
-    if (MODE != RP_GEMV_N) {
-      float* out = p.gpart + (size_t)cid * p.gstride + col0;
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (valid[v]) *reinterpret_cast<float4*>(out + 4 * (tid + v * RP_CT)) = g[v];
-    }
-  }
-  __syncwarp();
-  cluster_sync_all();  // nobody leaves while a peer may still post into its shared memory
-}
-
-// ------------------------------------------------------------------------------------
-// v2: the same decomposition without any CTA-wide barrier and with the cluster exchange taken off
-// the critical path.  16 warps, all computing (128 registers per thread).  Rows are held in
-// registers in two sets: while the partial dot products of round i travel through the cluster,
-// every warp already streams round i+1 into the other set, and folds round i into g afterwards.
-//   * no producer warp: the LAST warp to have read a ring stage (shared-memory counter) re-arms the
-//     stage and issues the bulk copy of the row NS places further on
-//   * no bar.sync: the LAST warp to deposit its partial sums of a round adds the 16 partials in a fixed
-//     order and posts the CTA's sums to all peers (st.async + complete_tx into a 4-deep slot ring)
-//   * every thread waits on the slot's mbarrier only when it needs y, one round later
-// Slot ring depth 4: a peer can post round i+4 only after this CTA posted round i+2, which every
-// local warp does after it has folded round i (derivation in DESIGN.md).
-// ------------------------------------------------------------------------------------
-constexpr int RP2_R = 2;
-constexpr int RP2_THREADS = RP_CT;
-constexpr int RP2_SLOTS = 4;
-
-template <int FPE, int V>
-__global__ void __launch_bounds__(RP2_THREADS, 1) rowpass2_kernel(RowpassArgs p) {
-  if (p.gate && *p.gate) return;
-  constexpr int R = RP2_R;
-  constexpr int RF = R * FPE;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const unsigned G = cluster_size(), rank = cluster_rank(), cid = cluster_id(), ncl = cluster_count();
-  const int W = p.W, NS = p.NS;
-
-  float* ring = reinterpret_cast<float*>(smem);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NS * W * 4);
-  uint64_t* ybar = full + NS;                                    // [RP2_SLOTS]
-  float* ybuf = reinterpret_cast<float*>(ybar + RP2_SLOTS);      // [RP2_SLOTS][RP_MAXG][RF]   (16-byte aligned)
-  float* wpart = ybuf + RP2_SLOTS * RP_MAXG * RF;                // [RP2_SLOTS][RP_CW][RF]
-  int* rel = reinterpret_cast<int*>(wpart + RP2_SLOTS * RP_CW * RF);  // [NS] readers that released the stage
-  int* wcnt = rel + NS;                                          // [RP2_SLOTS] warps that deposited their partials
-  volatile int* s_abort = reinterpret_cast<volatile int*>(wcnt + RP2_SLOTS);
-
-  const int nf_pad = (p.nf + 3) & ~3;
-  const int col0 = (int)rank * W;
-  const int slice = max(0, min(W, nf_pad - col0));
-  const int64_t nrounds = (p.m + R - 1) / R;
-  const int nr = (int)((nrounds - cid + ncl - 1) / ncl);         // rounds of this cluster (>= 1)
+  const int nr = (int)((nrounds - cid + ncl - 1) / ncl);  // rounds of this cluster (>= 1)
   const int rv_last = (int)min((int64_t)R, p.m - ((int64_t)cid + (int64_t)(nr - 1) * ncl) * R);
-  const int Q = (nr - 1) * R + rv_last;                          // rows this cluster streams
+  const int Q = (nr - 1) * R + rv_last;                   // rows this cluster streams, in sequence q = 0..Q-1
 
   unsigned long long pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  auto issue = [&](int q, int s) {  // row q of this cluster's sequence into stage s
+  // bulk copy of row q of this cluster's sequence into ring stage st (one elected thread)
+  auto issue = [&](int q, int st) {
     if (slice > 0) {
       const int64_t row = ((int64_t)cid + (int64_t)(q / R) * ncl) * R + (q % R);
-      mbar_expect_tx(&full[s], (unsigned)slice * 4u);
-      bulk_load(ring + (size_t)s * W, p.A + row * p.ldf + col0, (unsigned)slice * 4u, &full[s], pol);
+      mbar_expect_tx(&full[st], (unsigned)slice * 4u);
+      bulk_load(ring + (size_t)st * W, p.A + row * p.ldf + col0, (unsigned)slice * 4u, &full[st], pol);
     } else {
-      mbar_arrive(&full[s]);
+      mbar_arrive(&full[st]);
     }
   };
 
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); rel[s] = 0; }
-    for (int k = 0; k < RP2_SLOTS; ++k) { mbar_init(&ybar[k], 1); wcnt[k] = 0; }
+    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+    mbar_init(&ybar[0], 1);  // one local arrive.expect_tx per round; the peers' st.async complete the bytes
+    mbar_init(&ybar[1], 1);
     *s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int q = 0; q < min(NS, Q); ++q) issue(q, q);
+    for (int q = 0; q < min(NS, Q); ++q) issue(q, q);  // prologue: fill the ring
   }
   __syncthreads();
-  cluster_sync_all();
+  cluster_sync_all();  // peers' barriers are initialised before anyone posts to them
 
   bool valid[V];
   float4 xr[V], g[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const int q4 = 4 * (tid + v * RP_CT);
-    valid[v] = q4 < slice;
+    valid[v] = FULL || q4 < slice;
     g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     xr[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid[v]) {
+    if (MODE != RP_GEMV_C && valid[v]) {
       const int c = col0 + q4;
       if (c + 3 < p.nf) xr[v] = *reinterpret_cast<const float4*>(p.x + c);
       else {
@@ -378,13 +195,19 @@ __global__ void __launch_bounds__(RP2_THREADS, 1) rowpass2_kernel(RowpassArgs p)
       }
     }
   }
-
-  int s = 0, q = 0;
-  unsigned phase = 0;
-  // stream round i into register set a, deposit / post its partial dot products
-  auto stream_round = [&](int i, float4 (&a)[R][V]) {
+  int s = 0, q0 = 0;
+  unsigned phase = 0, par = 0, ypar = 0;
+  for (int i = 0; i < nr; ++i) {
     const int rv = (i == nr - 1) ? rv_last : R;
+    const int64_t row0 = ((int64_t)cid + (int64_t)i * ncl) * R;
+    const int s0 = s;
+    float4 a[R][V];
     float acc[R][FPE];
+    float y[RF];
+    if (MODE == RP_GEMV_C) {
+#pragma unroll
+      for (int k = 0; k < RF; ++k) y[k] = (k / FPE) < rv ? __ldg(p.yin + row0 * FPE + k) : 0.f;
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
 #pragma unroll
@@ -394,100 +217,102 @@ __global__ void __launch_bounds__(RP2_THREADS, 1) rowpass2_kernel(RowpassArgs p)
         const float4* st = reinterpret_cast<const float4*>(ring + (size_t)s * W);
 #pragma unroll
         for (int v = 0; v < V; ++v) a[r][v] = valid[v] ? st[tid + v * RP_CT] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int v = 0; v < V; ++v) dot_acc<FPE>(acc[r], a[r][v], xr[v]);  // consumes the loads: the stage has been read
-        __syncwarp();
-        if (lane == 0) {
-          if (atomicAdd(&rel[s], 1) == RP_CW - 1) {  // last reader: recycle the stage
-            rel[s] = 0;
-            if (q + NS < Q) issue(q + NS, s);
-          }
-        }
-        ++q;
         if (++s == NS) { s = 0; phase ^= 1u; }
+        if (MODE != RP_GEMV_C) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) dot_acc<FPE>(acc[r], a[r][v], xr[v]);
+        }
       } else {
 #pragma unroll
         for (int v = 0; v < V; ++v) a[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    const int slot = i & (RP2_SLOTS - 1);
-    float* wp = wpart + (slot * RP_CW) * RF;
+    if (MODE != RP_GEMV_C) {
+      // warp -> CTA -> cluster reduction of the RF partial dot products, fixed order throughout
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+      for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int e = 0; e < FPE; ++e) {
-        const float w = warp_sum(acc[r][e]);
-        if (lane == 0) wp[warp * RF + r * FPE + e] = w;
-      }
-    int last = 0;
-    if (lane == 0) {
-      __threadfence_block();
-      last = atomicAdd(&wcnt[slot], 1) == RP_CW - 1;
+        for (int e = 0; e < FPE; ++e) {
+          const float w = warp_sum(acc[r][e]);
+          if (lane == 0) wpart[warp * RF + r * FPE + e] = w;
+        }
     }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {  // this warp saw all 16 deposits: fixed-order CTA sum, then post to the cluster
-      if (lane == 0) wcnt[slot] = 0;
-      __threadfence_block();
-      float pv = 0.f;
-      if (lane < RF) {
+    // every warp has moved this round's rows ring -> registers (the dot products / the CSE-proof
+    // asm below consumed them): the stages are free, one thread re-arms them with the rows NS ahead
+    if (MODE == RP_GEMV_C) {
+      // no dot product here: make the barrier wait for the loads with a (never taken) dependent store
+      unsigned u = 0u;
 #pragma unroll
-        for (int w = 0; w < RP_CW; ++w) pv += wp[w * RF + lane];
-      }
-      if (G == 1) {
-        if (lane < RF) ybuf[(slot * RP_MAXG) * RF + lane] = pv;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ybar[slot]);
-      } else {
-        constexpr int PER = 32 / RF;
-        const int k = lane % RF;
-        const float pk = __shfl_sync(0xffffffffu, pv, k);
-        if (lane == 0) mbar_expect_tx(&ybar[slot], G * RF * 4u);
-        for (unsigned peer = lane / RF; peer < G; peer += PER)
-          dsmem_post(&ybuf[(slot * RP_MAXG + rank) * RF + k], &ybar[slot], peer, pk);
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int v = 0; v < V; ++v) u |= __float_as_uint(a[r][v].w) ^ __float_as_uint(a[r][v].x);
+      if (u == 0x7fc12345u) ysm[0] = 1.f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int st = s0;
+      for (int r = 0; r < rv; ++r) {
+        if (q0 + r + NS < Q) issue(q0 + r + NS, st);
+        if (++st == NS) st = 0;
       }
     }
-  };
-  // fold round i (held in register set a) into g once its y has arrived
-  auto fold_round = [&](int i, float4 (&a)[R][V]) {
-    const int slot = i & (RP2_SLOTS - 1);
-    mbar_wait<false>(&ybar[slot], (unsigned)(i / RP2_SLOTS) & 1u, s_abort, p.abort_flag);
-    float y[RF];
+    q0 += rv;
+    if (MODE != RP_GEMV_C) {
+      if (warp == 0) {
+        float pv = 0.f;
+        if (lane < RF) {
 #pragma unroll
-    for (int k = 0; k < RF; ++k) y[k] = 0.f;
-    const float* yb = ybuf + (slot * RP_MAXG) * RF;
-    for (unsigned c = 0; c < G; ++c) {
-      if (RF == 2) {
-        const float2 t = *reinterpret_cast<const float2*>(yb + c * RF);
-        y[0] += t.x; y[1] += t.y;
-      } else {
-        const float4 t = *reinterpret_cast<const float4*>(yb + c * RF);
-        y[0] += t.x; y[1] += t.y; y[RF - 2] += t.z; y[RF - 1] += t.w;
+          for (int w = 0; w < RP_CW; ++w) pv += wpart[w * RF + lane];
+        }
+        float tot = pv;
+        if (G > 1) {
+          constexpr int PER = 32 / RF;  // peers served per pass over the warp
+          const int k = lane % RF;
+          const float pk = __shfl_sync(0xffffffffu, pv, k);
+          if (lane == 0) mbar_expect_tx(&ybar[par], G * RF * 4u);
+          if (lane < PER * RF)
+            for (unsigned peer = lane / RF; peer < G; peer += PER)
+              dsmem_post(&ybuf[(par * RP_MAXG + rank) * RF + k], &ybar[par], peer, pk);
+          mbar_wait<false>(&ybar[par], ypar, s_abort, p.abort_flag);
+          if (lane < RF) {
+            // four interleaved partial sums (independent loads), combined in a fixed order
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+            const float* yb = ybuf + (par * RP_MAXG) * RF + lane;
+            for (unsigned c = 0; c < G; c += 4) {
+              t0 += yb[c * RF];
+              if (c + 1 < G) t1 += yb[(c + 1) * RF];
+              if (c + 2 < G) t2 += yb[(c + 2) * RF];
+              if (c + 3 < G) t3 += yb[(c + 3) * RF];
+            }
+            tot = (t0 + t1) + (t2 + t3);
+          }
+        }
+        if (lane < RF) {
+          ysm[lane] = tot;
+          if (MODE == RP_GEMV_N && rank == 0 && (lane / FPE) < rv) p.yout[row0 * FPE + lane] = tot;
+        }
       }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < RF; ++k) y[k] = ysm[k];
+      par ^= 1u;
+      if (par == 0) ypar ^= 1u;
     }
+    if (MODE != RP_GEMV_N) {
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+      for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int v = 0; v < V; ++v) axpy_conj<FPE>(g[v], a[r][v], y[r * FPE], y[r * FPE + FPE - 1]);
-  };
-
-  float4 a0[R][V], a1[R][V];
-  for (int i = 0; i < nr; i += 2) {
-    stream_round(i, a0);
-    if (i > 0) fold_round(i - 1, a1);
-    if (i + 1 < nr) {
-      stream_round(i + 1, a1);
-      fold_round(i, a0);
+        for (int v = 0; v < V; ++v) axpy_conj<FPE>(g[v], a[r][v], y[r * FPE], y[r * FPE + FPE - 1]);
     }
   }
-  if (nr & 1) fold_round(nr - 1, a0);
-  else fold_round(nr - 1, a1);
-
-  float* out = p.gpart + (size_t)cid * p.gstride + col0;
+  if (MODE != RP_GEMV_N) {
+    float* out = p.gpart + (size_t)cid * p.gstride + col0;
 #pragma unroll
-  for (int v = 0; v < V; ++v)
-    if (valid[v]) *reinterpret_cast<float4*>(out + 4 * (tid + v * RP_CT)) = g[v];
+    for (int v = 0; v < V; ++v)
+      if (valid[v]) *reinterpret_cast<float4*>(out + 4 * (tid + v * RP_CT)) = g[v];
+  }
   __syncwarp();
-  cluster_sync_all();
+  cluster_sync_all();  // nobody leaves while a peer may still post into its shared memory
 }
 
 // res[j] = sum over clusters of gpart[k][j], fixed order
@@ -512,39 +337,36 @@ __global__ void __launch_bounds__(256) rowpass_finish_kernel(const float* __rest
 }
 
 typedef void (*rowpass_fn)(RowpassArgs);
-template <int FPE, int V, int R>
+template <int FPE, int V, int R, bool FULL>
 rowpass_fn pick_mode(int mode) {
   switch (mode) {
-    case RP_NORMAL: return rowpass_kernel<FPE, V, R, RP_NORMAL>;
-    case RP_GEMV_N: return rowpass_kernel<FPE, V, R, RP_GEMV_N>;
-    default: return rowpass_kernel<FPE, V, R, RP_GEMV_C>;
+    case RP_NORMAL: return rowpass_kernel<FPE, V, R, RP_NORMAL, FULL>;
+    case RP_GEMV_N: return rowpass_kernel<FPE, V, R, RP_GEMV_N, FULL>;
+    default: return rowpass_kernel<FPE, V, R, RP_GEMV_C, FULL>;
   }
 }
 template <int FPE, int V>
-rowpass_fn pick_r(int R, int mode) {
+rowpass_fn pick_r(int R, int mode, bool full) {
+  if (full) {
+    switch (R) {
+      case 2: return pick_mode<FPE, V, 2, true>(mode);
+      case 3: return pick_mode<FPE, V, 3, true>(mode);
+      default: return pick_mode<FPE, V, 4, true>(mode);
+    }
+  }
   switch (R) {
-    case 2: return pick_mode<FPE, V, 2>(mode);
-    case 3: return pick_mode<FPE, V, 3>(mode);
-    default: return pick_mode<FPE, V, 4>(mode);
+    case 2: return pick_mode<FPE, V, 2, false>(mode);
+    case 3: return pick_mode<FPE, V, 3, false>(mode);
+    default: return pick_mode<FPE, V, 4, false>(mode);
   }
 }
 template <int FPE>
-rowpass_fn pick_v(int V, int R, int mode) {
+rowpass_fn pick_v(int V, int R, int mode, bool full) {
   switch (V) {
-    case 1: return pick_r<FPE, 1>(R, mode);
-    case 2: return pick_r<FPE, 2>(R, mode);
-    case 3: return pick_r<FPE, 3>(R, mode);
-    default: return pick_r<FPE, 4>(R, mode);
-  }
-}
-
-template <int FPE>
-rowpass_fn pick_v2(int V) {
-  switch (V) {
-    case 1: return rowpass2_kernel<FPE, 1>;
-    case 2: return rowpass2_kernel<FPE, 2>;
-    case 3: return rowpass2_kernel<FPE, 3>;
-    default: return rowpass2_kernel<FPE, 4>;
+    case 1: return pick_r<FPE, 1>(R, mode, full);
+    case 2: return pick_r<FPE, 2>(R, mode, full);
+    case 3: return pick_r<FPE, 3>(R, mode, full);
+    default: return pick_r<FPE, 4>(R, mode, full);
   }
 }
 
@@ -564,10 +386,6 @@ struct RowPlan {
   int fpe = 1, G = 1, V = 4, W = 0, NS = 0, R = 4, ncl = 0;
   size_t smem = 0;
   rowpass_fn fn[3] = {nullptr, nullptr, nullptr};
-  rowpass_fn fn2 = nullptr;  // v2 (pipelined, barrier-free) kernel for the normal operator
-  int NS2 = 0, ncl2 = 0;
-  size_t smem2 = 0;
-  bool use_v2 = false;
   float* gpart = nullptr;
   int64_t gstride = 0;
   int* abort_flag = nullptr;
@@ -582,13 +400,7 @@ void rls_rowpass_plan_destroy(RowPlan* p) {
 
 static size_t rowpass_smem(int NS, int W, int fpe) {
   const int RF = RP_MAXR * fpe;
-  return (size_t)NS * W * 4 + (size_t)(2 * NS + 2) * 8 + (size_t)(RP_CW * RF + 2 * RP_MAXG * RF + RF) * 4 + 16;
-}
-
-static size_t rowpass2_smem(int NS, int W, int fpe) {
-  const int RF = RP2_R * fpe;
-  return (size_t)NS * W * 4 + (size_t)(NS + RP2_SLOTS) * 8 + (size_t)(RP2_SLOTS * RP_MAXG * RF + RP2_SLOTS * RP_CW * RF) * 4 +
-         (size_t)(NS + RP2_SLOTS) * 4 + 16;
+  return (size_t)NS * W * 4 + (size_t)(NS + 2) * 8 + (size_t)(RP_CW * RF + 2 * RP_MAXG * RF + RF) * 4 + 16;
 }
 
 int32_t rls_rowpass_plan_create(rls_ctx_s* c, rls_mat_s* A, RowPlan** out) {
@@ -611,11 +423,13 @@ int32_t rls_rowpass_plan_create(rls_ctx_s* c, rls_mat_s* A, RowPlan** out) {
   int W = (int)(((nf_pad + G - 1) / G + 3) & ~(int64_t)3);
   if (W < 4) W = 4;
   int V = (W + 2047) / 2048;
-  int R = env_int("RLS_ROWPASS_R", V == 4 ? 3 : 4);
+  int R = env_int("RLS_ROWPASS_R", fpe == 2 ? 3 : 4);  // measured on B200 (profiles/r01_rowpass_sweep.txt)
   if (R < 2) R = 2;
   if (R > RP_MAXR) R = RP_MAXR;
   p->G = G; p->W = W; p->V = V; p->R = R;
-  for (int mode = 0; mode < 3; ++mode) p->fn[mode] = fpe == 2 ? pick_v<2>(V, R, mode) : pick_v<1>(V, R, mode);
+  // every CTA's slice is exactly V*2048 floats: no column predicates in the kernel
+  const bool full = (W == V * 4 * RP_CT) && ((int64_t)G * W == nf_pad);
+  for (int mode = 0; mode < 3; ++mode) p->fn[mode] = fpe == 2 ? pick_v<2>(V, R, mode, full) : pick_v<1>(V, R, mode, full);
   // ring: as many stages as fit in the 227 KB of shared memory (at least 2)
   int dev_max = 0;
   cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
@@ -624,8 +438,9 @@ int32_t rls_rowpass_plan_create(rls_ctx_s* c, rls_mat_s* A, RowPlan** out) {
     NS = 2;
     while (NS < 32 && rowpass_smem(NS + 1, W, fpe) <= (size_t)dev_max) ++NS;
     // small slices: no point in more than ~160 KB in flight
-    while (NS > 4 && (size_t)(NS - 1) * W * 4 >= (size_t)160 * 1024) --NS;
+    while (NS > 8 && (size_t)(NS - 1) * W * 4 >= (size_t)200 * 1024) --NS;
   }
+  if (NS < R) NS = R;  // a round's rows are resident together
   p->NS = NS;
   p->smem = rowpass_smem(NS, W, fpe);
   if (p->smem > (size_t)dev_max) { rls_set_error("rowpass: %zu B shared memory needed, device allows %d", p->smem, dev_max); rls_rowpass_plan_destroy(p); return RLS_ERR_UNSUPPORTED; }
@@ -657,37 +472,7 @@ int32_t rls_rowpass_plan_create(rls_ctx_s* c, rls_mat_s* A, RowPlan** out) {
   const int64_t nrounds = (A->m + R - 1) / R;
   if (nrounds < ncl) ncl = (int)std::max<int64_t>(nrounds, 1);
   p->ncl = ncl;
-  // v2 kernel for the normal operator (RLS_ROWPASS_V2=0 falls back to v1)
-  if (env_int("RLS_ROWPASS_V2", 1) != 0) {
-    p->fn2 = fpe == 2 ? pick_v2<2>(V) : pick_v2<1>(V);
-    int NS2 = env_int("RLS_ROWPASS_NS", 0);
-    if (NS2 <= 0) {
-      NS2 = 2;
-      while (NS2 < 32 && rowpass2_smem(NS2 + 1, W, fpe) <= (size_t)dev_max) ++NS2;
-      while (NS2 > 4 && (size_t)(NS2 - 1) * W * 4 >= (size_t)192 * 1024) --NS2;
-    }
-    p->NS2 = NS2;
-    p->smem2 = rowpass2_smem(NS2, W, fpe);
-    cudaError_t e2 = p->smem2 <= (size_t)dev_max ? cudaSuccess : cudaErrorInvalidValue;
-    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute((const void*)p->fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem2);
-    if (e2 == cudaSuccess && G > 8) e2 = cudaFuncSetAttribute((const void*)p->fn2, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    int ncl2 = 0;
-    if (e2 == cudaSuccess) {
-      cfg.blockDim = dim3(RP2_THREADS);
-      cfg.dynamicSmemBytes = p->smem2;
-      e2 = cudaOccupancyMaxActiveClusters(&ncl2, (const void*)p->fn2, &cfg);
-    }
-    if (e2 == cudaSuccess && ncl2 >= 1) {
-      if (cap > 0 && cap < ncl2) ncl2 = cap;
-      const int64_t nrounds2 = (A->m + RP2_R - 1) / RP2_R;
-      if (nrounds2 < ncl2) ncl2 = (int)std::max<int64_t>(nrounds2, 1);
-      p->ncl2 = ncl2;
-      p->use_v2 = true;
-    } else {
-      cudaGetLastError();
-    }
-  }
-  const int ncl_alloc = std::max(std::max(ncl, p->ncl2), 1);
+  const int ncl_alloc = std::max(ncl, 1);
   (void)ncl_max;
   p->gstride = ((int64_t)G * W + 63) & ~(int64_t)63;
   if (cudaMalloc(&p->gpart, (size_t)ncl_alloc * p->gstride * 4) != cudaSuccess || cudaMalloc(&p->abort_flag, 4) != cudaSuccess) {
@@ -709,19 +494,17 @@ static int32_t rowpass_launch(RowPlan* p, int mode, const void* x, const void* y
   a.W = p->W; a.NS = p->NS; a.R = p->R;
   a.x = (const float*)x; a.yin = (const float*)yin; a.yout = (float*)yout;
   a.gpart = p->gpart; a.gstride = p->gstride; a.gate = gate; a.abort_flag = p->abort_flag;
-  const bool v2 = mode == RP_NORMAL && p->use_v2;
-  const int ncl = v2 ? p->ncl2 : p->ncl;
-  if (v2) a.NS = p->NS2;
+  const int ncl = p->ncl;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ncl * p->G);
-  cfg.blockDim = dim3(v2 ? RP2_THREADS : RP_THREADS);
-  cfg.dynamicSmemBytes = v2 ? p->smem2 : p->smem;
+  cfg.blockDim = dim3(RP_THREADS);
+  cfg.dynamicSmemBytes = p->smem;
   cfg.stream = c->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = p->G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  RLS_CUDA(cudaLaunchKernelEx(&cfg, v2 ? p->fn2 : p->fn[mode], a));
+  RLS_CUDA(cudaLaunchKernelEx(&cfg, p->fn[mode], a));
   c->launches++;
   if (mode != RP_GEMV_N) {
     const int nf = a.nf;
@@ -749,11 +532,6 @@ int32_t rls_rowpass_check_abort(RowPlan* p) {
 }
 
 void rls_rowpass_describe(RowPlan* p, char* buf, int len) {
-  if (p->use_v2) {
-    snprintf(buf, len, "onepass/rowmajor v2 (pipelined exchange): clusters=%d x %d CTAs (%d SMs) slice=%d floats (V=%d) rows/round=%d ring=%d x %d B smem=%zu B",
-             p->ncl2, p->G, p->ncl2 * p->G, p->W, p->V, RP2_R, p->NS2, p->W * 4, p->smem2);
-    return;
-  }
   snprintf(buf, len, "onepass/rowmajor: clusters=%d x %d CTAs (%d SMs) slice=%d floats (V=%d) rows/round=%d ring=%d x %d B smem=%zu B",
            p->ncl, p->G, p->ncl * p->G, p->W, p->V, p->R, p->NS, p->W * 4, p->smem);
 }
