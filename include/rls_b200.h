@@ -175,6 +175,8 @@ int32_t rls_normal_apply(rls_normal_t op, rls_vec_t x, rls_vec_t res);
  * Lazy forms on a row-major A run as two tensor-core GEMMs (Y = A X, G = A' Y; FP32-accurate split-precision
  * tcgen05) that read A once each; other cases fall back to K single applies. */
 int32_t rls_normal_apply_batch(rls_normal_t op, int32_t K, const rls_vec_t* xs, const rls_vec_t* outs);
+/* diagnostics: internal operands of the last batched apply (0 = packed X, 1 = Y = A X, 2 = A' Y before unpacking) */
+int32_t rls_normal_batch_debug(rls_normal_t op, int32_t which, float* host, int64_t nfloats);
 /* power_iterations(AHA, b; rtol, maxiter) Utils.jl:262-287; b0 replaces the randn start vector */
 int32_t rls_power_iterations(rls_normal_t op, rls_vec_t b0, double rtol, int32_t maxiter, double* lambda_max);
 

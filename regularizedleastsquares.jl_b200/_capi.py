@@ -114,6 +114,7 @@ SIGNATURES = {
     "rls_normal_describe": [_P, C.c_char_p, _I32],
     "rls_normal_apply": [_P, _P, _P],
     "rls_normal_apply_batch": [_P, _I32, _PP, _PP],
+    "rls_normal_batch_debug": [_P, _I32, _P, _I64],
     "rls_power_iterations": [_P, _P, _F64, _I32, _PF64],
     "rls_prox_l1": [_P, _F32],
     "rls_prox_l2": [_P, _F32],

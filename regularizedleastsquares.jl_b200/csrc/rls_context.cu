@@ -525,9 +525,13 @@ extern "C" int32_t rls_mat_create_layout(rls_ctx_t ctx, int32_t dtype, int64_t m
   if (layout == RLS_LAYOUT_AUTO) {
     // rows of at most 16 x 8192 floats fit the cluster decomposition of rls_rowpass.cu
     const int64_t nf = n * (dtype == RLS_C32 ? 2 : 1);
+    // and pay off once A no longer sits in L2: below ~64 MB an iteration is launch-latency bound and the
+    // two-kernel column-major path is the shorter one (measured on C1: 40 vs 56 us per CGNR iteration)
     const char* force = getenv("RLS_LAYOUT");
+    const double bytes = (double)m * (double)n * (double)rls_elem_size(dtype);
     if (force && force[0] == 'c') layout = RLS_LAYOUT_COLMAJOR;
-    else layout = (nf + 3) / 4 * 4 <= 16 * 8192 ? RLS_LAYOUT_ROWMAJOR : RLS_LAYOUT_COLMAJOR;
+    else if (force && force[0] == 'r') layout = RLS_LAYOUT_ROWMAJOR;
+    else layout = ((nf + 3) / 4 * 4 <= 16 * 8192 && bytes >= 64.0 * 1024 * 1024) ? RLS_LAYOUT_ROWMAJOR : RLS_LAYOUT_COLMAJOR;
   }
   RlsDeviceGuard g(ctx->device);
   // device leading dimension padded to a 16-byte multiple so every column (row) supports 128-bit

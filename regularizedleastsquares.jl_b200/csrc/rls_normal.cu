@@ -691,6 +691,12 @@ extern "C" int32_t rls_normal_apply_batch(rls_normal_t op, int32_t K, const rls_
   return RLS_OK;
 }
 
+// diagnostics (tools/tc_check.py): internal operands of the last batched apply
+extern "C" int32_t rls_normal_batch_debug(rls_normal_t op, int32_t which, float* host, int64_t nfloats) {
+  RLS_CHECK_ARG(op && op->tc && host, "no tensor-core batch plan");
+  return rls_tc_batch_debug(op->tc, which, host, nfloats);
+}
+
 int32_t rls_normal_check_abort(rls_normal_t op) {
   if (op->row) return rls_rowpass_check_abort(op->row);
   if (op->form != RLS_NORMAL_ONEPASS) return RLS_OK;

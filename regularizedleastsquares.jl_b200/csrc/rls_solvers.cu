@@ -474,6 +474,10 @@ struct rls_solver_s {
   int64_t rows[4] = {0, 0, 0, 0};  // rows of regTrafo[i]
   TvWork tv;
   std::vector<Lane> lanes;
+  // multi-RHS: operands of the K normal-operator applies of one batched iteration (tensor-core GEMM path)
+  std::vector<const void*> batch_x;
+  std::vector<void*> batch_res;
+  std::vector<const int*> batch_gate;
   rls_vec_s* b_dev = nullptr;      // staging for host b
   void* pin_b = nullptr;
   void* pin_x = nullptr;
@@ -665,8 +669,13 @@ static int32_t composite_apply(rls_solver_s* s, Lane& L, const T* v, T* out, con
   return RLS_OK;
 }
 
+// phase 0: the whole iteration.  The multi-RHS driver splits it around the normal-operator apply so that the K
+// applies of one batched iteration run as two tensor-core GEMMs: phase 1 = everything before the apply (its
+// operands are recorded in s->batch_*), phase 2 = everything after it.
+enum { IT_ALL = 0, IT_PRE = 1, IT_POST = 2 };
+
 template <typename T>
-static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L) {
+static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L, int phase = IT_ALL) {
   rls_ctx_s* c = s->ctx;
   cudaStream_t st = c->stream;
   const int64_t n = s->n;
@@ -677,14 +686,20 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L) {
   const bool ew = rls_reg_is_elementwise(reg.kind);
   double* part = c->red_partials;
   unsigned* tick = c->red_ticket;
+  auto record = [&](const void* x, void* res) {
+    s->batch_x.push_back(x); s->batch_res.push_back(res); s->batch_gate.push_back(gate);
+  };
   switch (s->desc.kind) {
     case RLS_FISTA: {
-      swap_roles(s, L); L.enq_swaps++;
-      fista_momentum_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_XOLD]), n, S);
-      RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_RES]->d, gate));
+      if (phase != IT_POST) {
+        swap_roles(s, L); L.enq_swaps++;
+        fista_momentum_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_XOLD]), n, S);
+      }
+      if (phase == IT_PRE) { record(L.v[V_X]->d, L.v[V_RES]->d); c->launches++; break; }
+      if (phase == IT_ALL) RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_RES]->d, gate));
       if (ew) {
         fista_main_kernel<T, 0><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick);
-        c->launches += 2;
+        c->launches += phase == IT_ALL ? 2 : 1;
       } else {
         fista_main_kernel<T, 1><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick);
         RLS_TRY(rls_prox_launch(c, s->dtype, L.v[V_X]->d, n, &reg, 0.f, &S->thr, gate, &s->tv));
@@ -694,8 +709,9 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L) {
       break;
     }
     case RLS_POGM: {
-      scalar_kernel<<<1, 32, 0, st>>>(S, STEP_POGM_PRE, 0, gate);
-      RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_RES]->d, gate));
+      if (phase != IT_POST) scalar_kernel<<<1, 32, 0, st>>>(S, STEP_POGM_PRE, 0, gate);
+      if (phase == IT_PRE) { record(L.v[V_X]->d, L.v[V_RES]->d); c->launches++; break; }
+      if (phase == IT_ALL) RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_RES]->d, gate));
       T* bx = P<T>(L.v[V_X]); T* by = P<T>(L.v[V_Y]);
       if (ew) {
         pogm_main_kernel<T, 0><<<g, EB, 0, st>>>(bx, by, P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), P<T>(L.v[V_Z]), P<T>(L.v[V_W]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick);
@@ -710,8 +726,9 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L) {
       break;
     }
     case RLS_OPTISTA: {
-      scalar_kernel<<<1, 32, 0, st>>>(S, STEP_OPTISTA_PRE, 0, gate);
-      RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_RES]->d, gate));
+      if (phase != IT_POST) scalar_kernel<<<1, 32, 0, st>>>(S, STEP_OPTISTA_PRE, 0, gate);
+      if (phase == IT_PRE) { record(L.v[V_X]->d, L.v[V_RES]->d); c->launches++; break; }
+      if (phase == IT_ALL) RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_RES]->d, gate));
       if (ew) {
         optista_main_kernel<T, 0><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_Y]), P<T>(L.v[V_Z]), P<T>(L.v[V_ZOLD]), P<T>(L.v[V_X0]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick);
         c->launches += 2;
@@ -724,7 +741,8 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L) {
       break;
     }
     case RLS_CGNR: {
-      RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_P]->d, L.v[V_V]->d, gate));
+      if (phase == IT_PRE) { record(L.v[V_P]->d, L.v[V_V]->d); break; }
+      if (phase == IT_ALL) RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_P]->d, L.v[V_V]->d, gate));
       cgnr_dot_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_P]), P<T>(L.v[V_V]), n, S, part, tick);
       cgnr_update_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_X0]), P<T>(L.v[V_P]), P<T>(L.v[V_V]), n, S, part, tick);
       cgnr_p_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_P]), P<T>(L.v[V_X0]), n, S, part, tick);
@@ -805,9 +823,9 @@ static int32_t init_lane(rls_solver_s* s, Lane& L, const void* b, int64_t blen, 
   if (s->dtype == RLS_C32) return init_lane_t<float2>(s, L, b, blen, x0);
   return init_lane_t<float>(s, L, b, blen, x0);
 }
-static int32_t enqueue_iteration(rls_solver_s* s, Lane& L) {
-  if (s->dtype == RLS_C32) return enqueue_iteration_t<float2>(s, L);
-  return enqueue_iteration_t<float>(s, L);
+static int32_t enqueue_iteration(rls_solver_s* s, Lane& L, int phase = IT_ALL) {
+  if (s->dtype == RLS_C32) return enqueue_iteration_t<float2>(s, L, phase);
+  return enqueue_iteration_t<float>(s, L, phase);
 }
 
 static void fill_scalars(const DevState* h, rls_solver_scalars* o) {
@@ -1106,8 +1124,20 @@ extern "C" int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_hos
       status = init_lane(s, s->lanes[k], (const char*)Bd->d + (size_t)k * blen * es, blen, nullptr);
     if (status != RLS_OK) break;
     const int cap = s->desc.kind == RLS_CGNR ? (int)std::min<int64_t>(s->desc.iterations, s->n) : s->desc.iterations;
-    for (int it = 0; it < cap && status == RLS_OK; ++it)
-      for (int k = 0; k < K && status == RLS_OK; ++k) status = enqueue_iteration(s, s->lanes[k]);
+    // one apply per iteration (FISTA / POGM / OptISTA / CGNR): the K applies of a batched iteration go through
+    // rls_normal_apply_batch_raw — two tensor-core GEMMs reading A once each when A is row-major — between the
+    // per-column pre and post kernels.  ADMM (1 + n_cg applies with data-dependent gates) keeps the per-column loop.
+    const bool split = K > 1 && s->desc.kind != RLS_ADMM;
+    for (int it = 0; it < cap && status == RLS_OK; ++it) {
+      if (!split) {
+        for (int k = 0; k < K && status == RLS_OK; ++k) status = enqueue_iteration(s, s->lanes[k]);
+        continue;
+      }
+      s->batch_x.clear(); s->batch_res.clear(); s->batch_gate.clear();
+      for (int k = 0; k < K && status == RLS_OK; ++k) status = enqueue_iteration(s, s->lanes[k], IT_PRE);
+      if (status == RLS_OK) status = rls_normal_apply_batch_raw(s->AHA, K, s->batch_x.data(), s->batch_res.data(), s->batch_gate.data());
+      for (int k = 0; k < K && status == RLS_OK; ++k) status = enqueue_iteration(s, s->lanes[k], IT_POST);
+    }
     if (status != RLS_OK) break;
     for (int k = 0; k < K && status == RLS_OK; ++k) {
       Lane& L = s->lanes[k];

@@ -32,7 +32,7 @@ namespace {
 
 constexpr int TC_BM = 128;        // UMMA M
 constexpr int TC_BK = 32;         // floats per k-block: one 128-byte swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2-5 lo converters, warps 6-9 drain + epilogue
 constexpr int TC_CONV_THREADS = 128;
 constexpr int TC_BOX_BYTES = 32 * 32 * 4;  // one TMA box: 32 rows x 128 bytes
 
@@ -86,13 +86,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 }
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte
 // offsets in 16-byte units, version 1 (sm_100), 128-byte swizzle
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fffu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
-  d |= (uint64_t)1 << 46;   // version
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  d |= (uint64_t)1 << 46;             // version
+  d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -104,35 +104,60 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ float4 lo_part(float4 v) {
-  float4 r;
-  r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-  r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-  r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-  r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-  return r;
+// lo(a) = rn_tf32(a - hi(a)): the difference is exact in FP32; rounding it to TF32 here (to nearest, ties away)
+// instead of leaving it to the tensor core's truncation halves the error of the cross terms and removes its bias
+__device__ __forceinline__ float lo1(float a) {
+  const float d = a - __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 lo_part(float4 v) { return make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w)); }
+
+// TMEM -> registers: 32 consecutive FP32 columns of this thread's lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Accumulation.  The tensor core adds into its FP32 accumulator with round-toward-zero, a bias that grows
+// linearly with the length of the accumulation chain (measured: 4e-5 relative at a reduction length of 4096).
+// The dominant hi*hi products are therefore accumulated in TMEM over ONE k-block only (4 MMAs) into one of two
+// alternating accumulators; four drain warps pull each finished partial into FP32 registers and add it there
+// with round-to-nearest while the tensor core fills the other accumulator.  The two cross terms are 2^-11 of
+// the result, so their chain may run over the whole reduction in a third accumulator (its bias is 2^-11 smaller).
+template <int NPAD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle atoms
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Npad = p.Npad, NS = p.stages;
-  const uint32_t a_bytes = TC_BM * TC_BK * 4;             // 16 KB
-  const uint32_t b_bytes = (uint32_t)Npad * TC_BK * 4;
-  const uint32_t hi_bytes = a_bytes + b_bytes;
-  const uint32_t stage_bytes = 2 * hi_bytes;              // [A hi | B hi | A lo | B lo]
+  constexpr int Npad = NPAD;
+  const int NS = p.stages;
+  constexpr uint32_t a_bytes = TC_BM * TC_BK * 4;             // 16 KB
+  constexpr uint32_t b_bytes = (uint32_t)Npad * TC_BK * 4;
+  constexpr uint32_t hi_bytes = a_bytes + b_bytes;
+  constexpr uint32_t stage_bytes = 2 * hi_bytes;              // [A hi | B hi | A lo | B lo]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NS * stage_bytes);
   uint64_t* conv = full + NS;
   uint64_t* empty = conv + NS;
-  uint64_t* done = empty + NS;
+  uint64_t* accf = empty + NS;   // [2] partial accumulator b complete (tcgen05.commit)
+  uint64_t* acce = accf + 2;     // [2] partial accumulator b drained (128 drain threads)
+  uint64_t* done = acce + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
   volatile int* s_abort = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], TC_CONV_THREADS); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&accf[b], 1); mbar_init(&acce[b], TC_CONV_THREADS); }
     mbar_init(done, 1);
     *s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -145,10 +170,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_small = tmem_base + 2u * Npad;  // columns [0,N) and [N,2N): alternating partials; [2N,3N): cross terms
 
   const int m0 = blockIdx.x * TC_BM;       // output rows of this tile
   const int n0 = p.b_col0_from_y ? blockIdx.y * Npad : 0;
-  const int ngb = Npad / 32;               // 32-wide groups of the B tile
+  constexpr int ngb = Npad / 32;           // 32-wide groups of the B tile
 
   if (warp == 0) {
     // ------------------------------ TMA producer --------------------------------------
@@ -176,15 +202,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.transposed << 15) | ((uint32_t)p.transposed << 16) |
                              ((uint32_t)(Npad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      // K-major: 8-row groups 1024 B apart, k-step = 32 B inside the swizzle row.
-      // MN-major: 32-wide groups one box (4096 B) apart (LBO), 8-k-row groups 1024 B apart (SBO), k-step = 1024 B.
+      // K-major (SWIZZLE_128B): 8-row groups 1024 B apart, k-step = 32 B inside the swizzle row.
+      // MN-major: 32-bit operands only exist in the 128B swizzle with 32-byte atoms (SWIZZLE_128B_BASE32B, the TMA
+      // mode 128B_ATOM_32B): atom = 32 floats (MN) x 4 k-rows; 32-wide MN groups one box (4096 B) apart (LBO),
+      // 4-k-row groups 512 B apart (SBO), k-step (8 k-rows) = 1024 B.
       const uint32_t lbo = p.transposed ? (uint32_t)TC_BOX_BYTES : 16u;
-      const uint32_t sbo = 1024u;
+      const uint32_t sbo = p.transposed ? 512u : 1024u;
       const uint32_t kstep = p.transposed ? 1024u : 32u;
+      const uint32_t lt = p.transposed ? 1u : 2u;
       int s = 0;
       unsigned ph = 0;
-      uint32_t acc = 0;
       for (int kb = 0; kb < p.nkb; ++kb) {
+        const int b = kb & 1;
+        mbar_wait(&acce[b], (((unsigned)kb >> 1) & 1u) ^ 1u, s_abort, p.abort_flag);  // partial accumulator b has been drained
         mbar_wait(&full[s], ph, s_abort, p.abort_flag);   // hi tiles (TMA)
         mbar_wait(&conv[s], ph, s_abort, p.abort_flag);   // lo tiles (converter warps)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -192,26 +222,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t b_hi = a_hi + a_bytes;
         const uint32_t a_lo = a_hi + hi_bytes;
         const uint32_t b_lo = b_hi + hi_bytes;
+        const uint32_t tmem_main = tmem_base + (uint32_t)b * Npad;
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint64_t dah = make_desc(a_hi + k * kstep, lbo, sbo), dbh = make_desc(b_hi + k * kstep, lbo, sbo);
-          const uint64_t dal = make_desc(a_lo + k * kstep, lbo, sbo), dbl = make_desc(b_lo + k * kstep, lbo, sbo);
-          umma_tf32(tmem_base, dal, dbh, idesc, acc);
-          acc = 1;
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          const uint64_t dah = make_desc(a_hi + k * kstep, lbo, sbo, lt), dbh = make_desc(b_hi + k * kstep, lbo, sbo, lt);
+          umma_tf32(tmem_main, dah, dbh, idesc, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&accf[b]);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint64_t dah = make_desc(a_hi + k * kstep, lbo, sbo, lt), dbh = make_desc(b_hi + k * kstep, lbo, sbo, lt);
+          const uint64_t dal = make_desc(a_lo + k * kstep, lbo, sbo, lt), dbl = make_desc(b_lo + k * kstep, lbo, sbo, lt);
+          umma_tf32(tmem_small, dal, dbh, idesc, (kb | k) > 0 ? 1u : 0u);
+          umma_tf32(tmem_small, dah, dbl, idesc, 1u);
         }
         umma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
       umma_commit(done);
     }
-  } else {
-    // ------------------------------ lo converters, then epilogue ----------------------
+  } else if (warp < 6) {
+    // ------------------------------ lo converters -------------------------------------
     const int ct = threadIdx.x - 64;  // 0..127
     int s = 0;
     unsigned ph = 0;
-    const int n16 = (int)(hi_bytes >> 4);
+    constexpr int n16 = (int)(hi_bytes >> 4);
     for (int kb = 0; kb < p.nkb; ++kb) {
       mbar_wait(&full[s], ph, s_abort, p.abort_flag);
       const float4* hi = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes);
@@ -222,34 +257,48 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_arrive(&conv[s]);
       if (++s == NS) { s = 0; ph ^= 1u; }
     }
-    // epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q+32)
+  } else {
+    // ------------------------------ drain warps + epilogue ----------------------------
+    // warp q = warp % 4 owns TMEM lanes [32q, 32q+32); thread = one output row, NPAD running sums in registers
+    const int q = warp & 3;
+    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+    float acc[NPAD];
+#pragma unroll
+    for (int j = 0; j < NPAD; ++j) acc[j] = 0.f;
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int b = kb & 1;
+      mbar_wait(&accf[b], ((unsigned)kb >> 1) & 1u, s_abort, p.abort_flag);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c0 = 0; c0 < NPAD; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + (uint32_t)(b * NPAD + c0), r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&acce[b]);
+    }
     mbar_wait(done, 0u, s_abort, p.abort_flag);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3;
     const int64_t row = (int64_t)m0 + 32 * q + lane;
     float* drow = p.D + row * p.ldd + n0;
-    for (int c0 = 0; c0 < Npad; c0 += 32) {
+#pragma unroll
+    for (int c0 = 0; c0 < NPAD; c0 += 32) {
       uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr) : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tmem_ld32(tmem_small + lane_base + (uint32_t)c0, r);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
       if (row < p.Mtot) {
         const int nv = min(32, p.Nvalid - c0);
         if (nv == 32 && ((p.ldd | n0) & 3) == 0) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(drow + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            *reinterpret_cast<float4*>(drow + c0 + j) = make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (j < nv) drow[c0 + j] = __uint_as_float(r[j]);
+            if (j < nv) drow[c0 + j] = acc[c0 + j];
         }
       }
     }
@@ -321,8 +370,9 @@ encode_tiled_fn get_encode() {
   fn = (encode_tiled_fn)p;
   return fn;
 }
-// row-major float matrix [rows][ld], box = 32 floats x 32 rows, 128-byte swizzle, zero fill out of bounds
-int32_t make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+// row-major float matrix [rows][ld], box = 32 floats x 32 rows, zero fill out of bounds.  128-byte swizzle with
+// 16-byte atoms for K-major operands, with 32-byte atoms for MN-major (transposed) ones.
+int32_t make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, bool mn_major) {
   encode_tiled_fn enc = get_encode();
   if (!enc) { rls_set_error("cuTensorMapEncodeTiled is not available from this driver"); return RLS_ERR_UNSUPPORTED; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -330,14 +380,17 @@ int32_t make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols
   cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { rls_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return RLS_ERR_UNSUPPORTED; }
   return RLS_OK;
 }
 
+int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+
 size_t tc_smem(int stages, int Npad) {
   const size_t stage = 2 * ((size_t)TC_BM * TC_BK * 4 + (size_t)Npad * TC_BK * 4);
-  return (size_t)stages * stage + (size_t)(3 * stages + 1) * 8 + 16 + 1024;
+  return (size_t)stages * stage + (size_t)(3 * stages + 5) * 8 + 16 + 1024;
 }
 
 int32_t tc_launch(rls_ctx_s* c, const CUtensorMap& mapA, const CUtensorMap& mapB, TcArgs a, int grid_x, int grid_y) {
@@ -347,14 +400,16 @@ int32_t tc_launch(rls_ctx_s* c, const CUtensorMap& mapA, const CUtensorMap& mapB
   while (stages > 2 && tc_smem(stages, a.Npad) > (size_t)dev_max) --stages;
   a.stages = stages;
   const size_t smem = tc_smem(stages, a.Npad);
-  RLS_CUDA(cudaFuncSetAttribute((const void*)tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc_gemm_kernel<<<dim3(grid_x, grid_y), TC_THREADS, smem, c->stream>>>(mapA, mapB, a);
+  a.tmem_cols = pow2_cols(3 * a.Npad);
+  void (*fn)(const CUtensorMap, const CUtensorMap, TcArgs) =
+      a.Npad == 32 ? tc_gemm_kernel<32> : a.Npad == 64 ? tc_gemm_kernel<64> : a.Npad == 96 ? tc_gemm_kernel<96> : tc_gemm_kernel<128>;
+  RLS_CHECK_ARG(a.Npad == 32 || a.Npad == 64 || a.Npad == 96 || a.Npad == 128, "tensor-core GEMM: N tile %d not in {32,64,96,128}", a.Npad);
+  RLS_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fn<<<dim3(grid_x, grid_y), TC_THREADS, smem, c->stream>>>(mapA, mapB, a);
   c->launches++;
   RLS_CUDA(cudaGetLastError());
   return RLS_OK;
 }
-
-int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 
 }  // namespace
 
@@ -373,7 +428,7 @@ struct TcBatchPlan {
   float** d_outs = nullptr;
   const int** d_gates = nullptr;
   int* abort_flag = nullptr;
-  CUtensorMap mapA, mapXT, mapY;
+  CUtensorMap mapA, mapAt, mapXT, mapY;  // mapAt: A described for the transposed (MN-major) use
 };
 
 void rls_tc_batch_destroy(TcBatchPlan* p) {
@@ -386,7 +441,7 @@ void rls_tc_batch_destroy(TcBatchPlan* p) {
 bool rls_tc_batch_supported(const rls_mat_s* A, int K) {
   if (!A || A->layout != RLS_LAYOUT_ROWMAJOR || K < 2) return false;
   const int fpe = A->dtype == RLS_C32 ? 2 : 1;
-  if (K * fpe > 256) return false;
+  if (K * fpe > 128) return false;  // one 128 x N tile per CTA, N <= 128 (three N-wide accumulators in TMEM)
   if (((uintptr_t)A->d & 15) != 0 || (A->ld * fpe) % 4 != 0) return false;
   if (A->m * (int64_t)fpe > 0x7fffffff || A->n * (int64_t)fpe > 0x7fffffff) return false;
   return A->ctx->cc_major == 10;
@@ -408,9 +463,10 @@ int32_t rls_tc_batch_create(rls_mat_s* A, int K, TcBatchPlan** out) {
             cudaMalloc((void**)&p->d_gates, sizeof(void*) * K) == cudaSuccess && cudaMalloc(&p->abort_flag, 4) == cudaSuccess;
   if (!ok) { cudaGetLastError(); rls_tc_batch_destroy(p); rls_set_error("tensor-core batch path: out of device memory"); return RLS_ERR_NOMEM; }
   cudaMemsetAsync(p->abort_flag, 0, 4, A->ctx->stream);
-  int32_t s = make_map(&p->mapA, (const float*)A->d, A->m, p->nf, A->ld * p->fpe);
-  if (s == RLS_OK) s = make_map(&p->mapXT, p->XT, p->Npad, p->nf, p->ldx);
-  if (s == RLS_OK) s = make_map(&p->mapY, p->Y, A->m, p->Npad, p->Npad);
+  int32_t s = make_map(&p->mapA, (const float*)A->d, A->m, p->nf, A->ld * p->fpe, false);
+  if (s == RLS_OK) s = make_map(&p->mapAt, (const float*)A->d, A->m, p->nf, A->ld * p->fpe, true);
+  if (s == RLS_OK) s = make_map(&p->mapXT, p->XT, p->Npad, p->nf, p->ldx, false);
+  if (s == RLS_OK) s = make_map(&p->mapY, p->Y, A->m, p->Npad, p->Npad, true);
   if (s != RLS_OK) { rls_tc_batch_destroy(p); return s; }
   *out = p;
   return RLS_OK;
@@ -434,7 +490,7 @@ int32_t rls_tc_batch_apply(TcBatchPlan* p, const void* const* xs, void* const* o
     c->launches++;
   }
   TcArgs a{};
-  a.Npad = p->Npad; a.tmem_cols = pow2_cols(p->Npad); a.b_col0_from_y = 0; a.abort_flag = p->abort_flag;
+  a.Npad = p->Npad; a.b_col0_from_y = 0; a.abort_flag = p->abort_flag;
   // mode N: Y~ = A~ . B
   a.transposed = 0; a.nkb = (int)((p->nf + TC_BK - 1) / TC_BK);
   a.D = p->Y; a.ldd = p->Npad; a.Mtot = A->m; a.Nvalid = p->Npad; a.Ntot = p->Npad;
@@ -442,7 +498,7 @@ int32_t rls_tc_batch_apply(TcBatchPlan* p, const void* const* xs, void* const* o
   // mode T: P = A~^T . Y~
   a.transposed = 1; a.nkb = (int)((A->m + TC_BK - 1) / TC_BK);
   a.D = p->P; a.ldd = p->Npad; a.Mtot = p->nf;
-  RLS_TRY(tc_launch(c, p->mapA, p->mapY, a, (int)((p->nf + TC_BM - 1) / TC_BM), 1));
+  RLS_TRY(tc_launch(c, p->mapAt, p->mapY, a, (int)((p->nf + TC_BM - 1) / TC_BM), 1));
   if (c->nranks > 1) RLS_TRY(rls_allreduce_raw(c, p->P, p->nf * p->Npad));
   {
     dim3 block(32, 8);
@@ -459,6 +515,14 @@ int32_t rls_tc_check_abort(rls_ctx_s* c, int* abort_flag) {
   RLS_CUDA(cudaMemcpyAsync(&flag, abort_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   RLS_CUDA(cudaStreamSynchronize(c->stream));
   if (flag) { rls_set_error("tensor-core GEMM timed out on a barrier (abort flag set)"); return RLS_ERR_CUDA; }
+  return RLS_OK;
+}
+// diagnostics: copy an internal operand (0 = B^T of mode N, 1 = Y~, 2 = P) to the host
+int32_t rls_tc_batch_debug(TcBatchPlan* p, int which, float* host, int64_t nfloats) {
+  const float* src = which == 0 ? p->XT : which == 1 ? p->Y : p->P;
+  const int64_t have = which == 0 ? (int64_t)p->Npad * p->ldx : which == 1 ? p->A->m * (int64_t)p->Npad : p->nf * (int64_t)p->Npad;
+  RLS_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  RLS_CUDA(cudaMemcpy(host, src, sizeof(float) * std::min(nfloats, have), cudaMemcpyDeviceToHost));
   return RLS_OK;
 }
 int32_t rls_tc_batch_check_abort(TcBatchPlan* p) { return rls_tc_check_abort(p->ctx, p->abort_flag); }
@@ -491,10 +555,10 @@ int32_t rls_tc_gram(rls_mat_s* A, rls_mat_s* G) {
   }
   cudaMemsetAsync(abort_flag, 0, 4, c->stream);
   CUtensorMap mapA;
-  int32_t s = make_map(&mapA, (const float*)A->d, A->m, nf, A->ld * fpe);
+  int32_t s = make_map(&mapA, (const float*)A->d, A->m, nf, A->ld * fpe, true);
   if (s == RLS_OK) {
     TcArgs a{};
-    a.transposed = 1; a.Npad = Npad; a.tmem_cols = 128; a.b_col0_from_y = 1; a.abort_flag = abort_flag;
+    a.transposed = 1; a.Npad = Npad; a.b_col0_from_y = 1; a.abort_flag = abort_flag;
     a.nkb = (int)((A->m + TC_BK - 1) / TC_BK);
     a.D = P; a.ldd = ldp; a.Mtot = nf; a.Nvalid = Npad; a.Ntot = ldp;
     s = tc_launch(c, mapA, mapA, a, (int)((nf + TC_BM - 1) / TC_BM), (int)(ldp / Npad));
