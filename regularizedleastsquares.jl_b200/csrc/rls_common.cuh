@@ -140,6 +140,29 @@ int32_t rls_normal_apply_batch_raw(rls_normal_t op, int K, const void* const* xs
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------
+// programmatic dependent launch: the kernels of one solver iteration are chained on the stream;
+// launched with this attribute, the next kernel's CTAs are resident and parked at
+// griddepcontrol.wait while the previous kernel drains, which removes most of the ~15 us
+// kernel-boundary gap around the big cluster kernel (profiles/r01_launch_gap_probe.txt).
+// Every kernel launched through rls_launch_pdl starts with pdl_prologue().
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool rls_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t rls_launch_pdl(cudaStream_t st, dim3 grid, dim3 block, void (*kernel)(KArgs...), Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = rls_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------
 // Individually rounded float arithmetic (no FMA contraction): the reference's

@@ -20,6 +20,12 @@ void rls_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* rls_last_error(void) { return g_err; }
+
+bool rls_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("RLS_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on != 0;
+}
 extern "C" int32_t rls_abi_version(void) { return RLS_B200_ABI_VERSION; }
 
 extern "C" int32_t rls_device_count(int32_t* count) {

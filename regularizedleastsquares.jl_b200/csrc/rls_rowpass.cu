@@ -130,6 +130,7 @@ template <> __device__ __forceinline__ void axpy_conj<2>(float4& g, float4 a, fl
 
 template <int FPE, int V, int R, int MODE, bool FULL>
 __global__ void __launch_bounds__(RP_THREADS, 1) rowpass_kernel(RowpassArgs p) {
+  pdl_prologue();
   if (p.gate && *p.gate) return;  // device-side done() gate: uniform over the grid
   constexpr int RF = R * FPE;     // floats exchanged per round
   extern __shared__ __align__(128) unsigned char smem[];
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowpass_kernel(RowpassArgs p) {
 // res[j] = sum over clusters of gpart[k][j], fixed order
 __global__ void __launch_bounds__(256) rowpass_finish_kernel(const float* __restrict__ gpart, int64_t gstride, int ncl, int nf,
                                                             float* __restrict__ res, const int* gate) {
+  pdl_prologue();
   if (gate && *gate) return;
   const int nf4 = nf >> 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf4; i += gridDim.x * blockDim.x) {
@@ -366,7 +368,10 @@ rowpass_fn pick_v(int V, int R, int mode, bool full) {
     case 1: return pick_r<FPE, 1>(R, mode, full);
     case 2: return pick_r<FPE, 2>(R, mode, full);
     case 3: return pick_r<FPE, 3>(R, mode, full);
-    default: return pick_r<FPE, 4>(R, mode, full);
+    case 4: return pick_r<FPE, 4>(R, mode, full);
+    // wide slices (cluster sizes that are not powers of two, e.g. 6 CTAs x 10924 floats): two rows per round
+    case 5: return pick_mode<FPE, 5, 2, false>(mode);
+    default: return pick_mode<FPE, 6, 2, false>(mode);
   }
 }
 
@@ -418,14 +423,21 @@ int32_t rls_rowpass_plan_create(rls_ctx_s* c, rls_mat_s* A, RowPlan** out) {
   p->ctx = c; p->A = A; p->fpe = fpe;
   int G = 1;
   while ((int64_t)G * 4 * 2048 < nf_pad) G *= 2;
-  G = std::max(G, env_int("RLS_ROWPASS_G", 1));
+  {
+    // cluster sizes need not be powers of two: what counts is how many SMs the co-resident clusters cover
+    // (GPCs of 20/18/14 SMs: 8 -> 120 SMs, 6 -> 138, 4 -> 132, 2 and 1 -> 148) against the slice width
+    const int g_env = env_int("RLS_ROWPASS_G", 0);
+    if (g_env > 0 && (int64_t)g_env * 6 * 2048 >= nf_pad) G = g_env;
+  }
   if (G > RP_MAXG) G = RP_MAXG;
   int W = (int)(((nf_pad + G - 1) / G + 3) & ~(int64_t)3);
   if (W < 4) W = 4;
   int V = (W + 2047) / 2048;
+  if (V > 6) { rls_set_error("rowpass: slice of %d floats too wide", W); rls_rowpass_plan_destroy(p); return RLS_ERR_UNSUPPORTED; }
   int R = env_int("RLS_ROWPASS_R", fpe == 2 ? 3 : 4);  // measured on B200 (profiles/r01_rowpass_sweep.txt)
   if (R < 2) R = 2;
   if (R > RP_MAXR) R = RP_MAXR;
+  if (V > 4) R = 2;
   p->G = G; p->W = W; p->V = V; p->R = R;
   // every CTA's slice is exactly V*2048 floats: no column predicates in the kernel
   const bool full = (W == V * 4 * RP_CT) && ((int64_t)G * W == nf_pad);
@@ -500,18 +512,19 @@ static int32_t rowpass_launch(RowPlan* p, int mode, const void* x, const void* y
   cfg.blockDim = dim3(RP_THREADS);
   cfg.dynamicSmemBytes = p->smem;
   cfg.stream = c->stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = p->G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = rls_pdl_enabled() ? 2 : 1;
   RLS_CUDA(cudaLaunchKernelEx(&cfg, p->fn[mode], a));
   c->launches++;
   if (mode != RP_GEMV_N) {
     const int nf = a.nf;
     int grid = std::min(c->sm_count * 2, std::max(1, (nf / 4 + 255) / 256));
-    rowpass_finish_kernel<<<grid, 256, 0, c->stream>>>(p->gpart, p->gstride, ncl, nf, (float*)res, gate);
+    RLS_CUDA(rls_launch_pdl(c->stream, dim3(grid), dim3(256), rowpass_finish_kernel, (const float*)p->gpart, p->gstride, ncl, nf, (float*)res, gate));
     c->launches++;
-    RLS_CUDA(cudaGetLastError());
   }
   return RLS_OK;
 }

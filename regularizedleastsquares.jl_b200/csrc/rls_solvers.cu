@@ -26,6 +26,7 @@ static inline int ew_grid(const rls_ctx_s* c, int64_t n) {
 }
 
 __global__ void scalar_kernel(DevState* S, int step, int arg, const int* gate) {
+  pdl_prologue();
   if (gate && *gate) return;
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(EB) norm_step_kernel(const T* __restrict__ x, 
 template <typename T>
 __global__ void __launch_bounds__(EB) fista_momentum_kernel(T* __restrict__ x, const T* __restrict__ xold, int64_t n,
                                                              const DevState* __restrict__ S) {
+  pdl_prologue();
   if (S->done) return;
   // x holds xᵒˡᵈ after the pointer swap: x = x*(1-θᵒˡᵈ)/θ ; x += ((θᵒˡᵈ-1)/θ + 1)*xᵒˡᵈ   FISTA.jl:144-148
   const float c1 = fdiv(fsub(1.f, S->theta_old), S->theta);
@@ -72,6 +74,7 @@ template <typename T, int PART>
 __global__ void __launch_bounds__(EB) fista_main_kernel(T* __restrict__ x, T* __restrict__ res, const T* __restrict__ x0,
                                                          const T* __restrict__ xold, int64_t n, DevState* S, int reg_kind,
                                                          double* partials, unsigned* ticket) {
+  pdl_prologue();
   if (S->done) return;
   const float rho = S->rho, thr = thr_from(S, 0, S->rho);   // ρ*λ(reg)   FISTA.jl:164
   const int proj = S->proj_mask, restart = S->restart;
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(EB) pogm_main_kernel(T* __restrict__ bufX, T* 
                                                         T* __restrict__ xold, T* __restrict__ z, T* __restrict__ w,
                                                         T* __restrict__ res, int64_t n, DevState* S, int reg_kind,
                                                         double* partials, unsigned* ticket) {
+  pdl_prologue();
   if (S->done) return;
   const float rho = S->rho, alpha = S->alpha, beta = S->beta, gamma = S->gamma, gamma_old = S->gamma_old, thr = S->thr;
   const int proj = S->proj_mask, restart = S->restart;
@@ -157,6 +161,7 @@ __global__ void __launch_bounds__(EB) optista_main_kernel(T* __restrict__ x, T* 
                                                            T* __restrict__ zold, const T* __restrict__ x0,
                                                            T* __restrict__ res, int64_t n, DevState* S, int reg_kind,
                                                            double* partials, unsigned* ticket) {
+  pdl_prologue();
   if (S->done) return;
   const float alpha = S->alpha, beta = S->beta, gamma = S->gamma, thr = S->thr;
   const float rg = fmul(S->rho, gamma);                                  // ρ*γ
@@ -204,6 +209,7 @@ __device__ __forceinline__ float2 negs(float2 a) { return make_float2(-a.x, -a.y
 template <typename T>
 __global__ void __launch_bounds__(EB) cgnr_dot_kernel(const T* __restrict__ p, const T* __restrict__ v, int64_t n, DevState* S,
                                                        double* partials, unsigned* ticket) {
+  pdl_prologue();
   if (S->done) return;
   double acc[2] = {0.0, 0.0};
   EW_LOOP(i, n) Elem<T>::dotc(p[i], v[i], acc[0], acc[1]);               // dot(pl, vl)   CGNR.jl:154
@@ -215,6 +221,7 @@ template <typename T>
 __global__ void __launch_bounds__(EB) cgnr_update_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
                                                           const T* __restrict__ v, int64_t n, DevState* S,
                                                           double* partials, unsigned* ticket) {
+  pdl_prologue();
   if (S->done) return;
   const T al = scal<T>(S->cg_alpha);
   const T nal = negs(al);
@@ -236,6 +243,7 @@ __global__ void __launch_bounds__(EB) cgnr_update_kernel(T* __restrict__ x, T* _
 template <typename T>
 __global__ void __launch_bounds__(EB) cgnr_p_kernel(T* __restrict__ p, const T* __restrict__ r, int64_t n, DevState* S,
                                                      double* partials, unsigned* ticket) {
+  pdl_prologue();
   if (S->done) return;
   const T be = scal<T>(S->cg_beta);
   double acc[1] = {0.0};
@@ -693,49 +701,49 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L, int phase = IT_ALL)
     case RLS_FISTA: {
       if (phase != IT_POST) {
         swap_roles(s, L); L.enq_swaps++;
-        fista_momentum_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_XOLD]), n, S);
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), fista_momentum_kernel<T>, P<T>(L.v[V_X]), P<T>(L.v[V_XOLD]), n, S));
       }
       if (phase == IT_PRE) { record(L.v[V_X]->d, L.v[V_RES]->d); c->launches++; break; }
       if (phase == IT_ALL) RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_RES]->d, gate));
       if (ew) {
-        fista_main_kernel<T, 0><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick);
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), fista_main_kernel<T, 0>, P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick));
         c->launches += phase == IT_ALL ? 2 : 1;
       } else {
-        fista_main_kernel<T, 1><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick);
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), fista_main_kernel<T, 1>, P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick));
         RLS_TRY(rls_prox_launch(c, s->dtype, L.v[V_X]->d, n, &reg, 0.f, &S->thr, gate, &s->tv));
-        fista_main_kernel<T, 2><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick);
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), fista_main_kernel<T, 2>, P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick));
         c->launches += 3;
       }
       break;
     }
     case RLS_POGM: {
-      if (phase != IT_POST) scalar_kernel<<<1, 32, 0, st>>>(S, STEP_POGM_PRE, 0, gate);
+      if (phase != IT_POST) RLS_CUDA(rls_launch_pdl(st, dim3(1), dim3(32), scalar_kernel, S, STEP_POGM_PRE, 0, gate));
       if (phase == IT_PRE) { record(L.v[V_X]->d, L.v[V_RES]->d); c->launches++; break; }
       if (phase == IT_ALL) RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_RES]->d, gate));
       T* bx = P<T>(L.v[V_X]); T* by = P<T>(L.v[V_Y]);
       if (ew) {
-        pogm_main_kernel<T, 0><<<g, EB, 0, st>>>(bx, by, P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), P<T>(L.v[V_Z]), P<T>(L.v[V_W]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick);
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), pogm_main_kernel<T, 0>, bx, by, P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), P<T>(L.v[V_Z]), P<T>(L.v[V_W]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick));
         c->launches += 2;
       } else {
-        pogm_main_kernel<T, 1><<<g, EB, 0, st>>>(bx, by, P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), P<T>(L.v[V_Z]), P<T>(L.v[V_W]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick);
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), pogm_main_kernel<T, 1>, bx, by, P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), P<T>(L.v[V_Z]), P<T>(L.v[V_W]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick));
         RLS_TRY(rls_prox_launch(c, s->dtype, by, n, &reg, 0.f, &S->thr, gate, &s->tv));
-        pogm_main_kernel<T, 2><<<g, EB, 0, st>>>(bx, by, P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), P<T>(L.v[V_Z]), P<T>(L.v[V_W]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick);
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), pogm_main_kernel<T, 2>, bx, by, P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), P<T>(L.v[V_Z]), P<T>(L.v[V_W]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick));
         c->launches += 3;
       }
       swap_roles(s, L); L.enq_swaps++;   // x <-> y  (POGM.jl:206-208)
       break;
     }
     case RLS_OPTISTA: {
-      if (phase != IT_POST) scalar_kernel<<<1, 32, 0, st>>>(S, STEP_OPTISTA_PRE, 0, gate);
+      if (phase != IT_POST) RLS_CUDA(rls_launch_pdl(st, dim3(1), dim3(32), scalar_kernel, S, STEP_OPTISTA_PRE, 0, gate));
       if (phase == IT_PRE) { record(L.v[V_X]->d, L.v[V_RES]->d); c->launches++; break; }
       if (phase == IT_ALL) RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_RES]->d, gate));
       if (ew) {
-        optista_main_kernel<T, 0><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_Y]), P<T>(L.v[V_Z]), P<T>(L.v[V_ZOLD]), P<T>(L.v[V_X0]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick);
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), optista_main_kernel<T, 0>, P<T>(L.v[V_X]), P<T>(L.v[V_Y]), P<T>(L.v[V_Z]), P<T>(L.v[V_ZOLD]), P<T>(L.v[V_X0]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick));
         c->launches += 2;
       } else {
-        optista_main_kernel<T, 1><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_Y]), P<T>(L.v[V_Z]), P<T>(L.v[V_ZOLD]), P<T>(L.v[V_X0]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick);
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), optista_main_kernel<T, 1>, P<T>(L.v[V_X]), P<T>(L.v[V_Y]), P<T>(L.v[V_Z]), P<T>(L.v[V_ZOLD]), P<T>(L.v[V_X0]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick));
         RLS_TRY(rls_prox_launch(c, s->dtype, L.v[V_Y]->d, n, &reg, 0.f, &S->thr, gate, &s->tv));
-        optista_main_kernel<T, 2><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_Y]), P<T>(L.v[V_Z]), P<T>(L.v[V_ZOLD]), P<T>(L.v[V_X0]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick);
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), optista_main_kernel<T, 2>, P<T>(L.v[V_X]), P<T>(L.v[V_Y]), P<T>(L.v[V_Z]), P<T>(L.v[V_ZOLD]), P<T>(L.v[V_X0]), P<T>(L.v[V_RES]), n, S, reg.kind, part, tick));
         c->launches += 3;
       }
       break;
@@ -743,9 +751,9 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L, int phase = IT_ALL)
     case RLS_CGNR: {
       if (phase == IT_PRE) { record(L.v[V_P]->d, L.v[V_V]->d); break; }
       if (phase == IT_ALL) RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_P]->d, L.v[V_V]->d, gate));
-      cgnr_dot_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_P]), P<T>(L.v[V_V]), n, S, part, tick);
-      cgnr_update_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_X0]), P<T>(L.v[V_P]), P<T>(L.v[V_V]), n, S, part, tick);
-      cgnr_p_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_P]), P<T>(L.v[V_X0]), n, S, part, tick);
+      RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), cgnr_dot_kernel<T>, P<T>(L.v[V_P]), P<T>(L.v[V_V]), n, S, part, tick));
+      RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), cgnr_update_kernel<T>, P<T>(L.v[V_X]), P<T>(L.v[V_X0]), P<T>(L.v[V_P]), P<T>(L.v[V_V]), n, S, part, tick));
+      RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), cgnr_p_kernel<T>, P<T>(L.v[V_P]), P<T>(L.v[V_X0]), n, S, part, tick));
       c->launches += 3;
       break;
     }
@@ -1116,12 +1124,14 @@ extern "C" int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_hos
   s->lanes.resize(K);
   for (int k = 0; k < K; ++k) RLS_TRY(alloc_lane(s, s->lanes[k]));
   rls_vec_s* Bd = nullptr;
-  RLS_TRY(rls_vec_create_internal(s->ctx, s->dtype, blen * K, &Bd));
+  // device copy of B with every column on a 16-byte boundary (the kernels use 128-bit loads)
+  const int64_t bstride = (blen + 3) & ~(int64_t)3;
+  RLS_TRY(rls_vec_create_internal(s->ctx, s->dtype, bstride * K, &Bd));
   int32_t status = RLS_OK;
   do {
-    if ((status = (cudaMemcpy2DAsync(Bd->d, blen * es, B_host, ldb * es, blen * es, K, cudaMemcpyHostToDevice, s->ctx->stream) == cudaSuccess) ? RLS_OK : RLS_ERR_CUDA) != RLS_OK) break;
+    if ((status = (cudaMemcpy2DAsync(Bd->d, bstride * es, B_host, ldb * es, blen * es, K, cudaMemcpyHostToDevice, s->ctx->stream) == cudaSuccess) ? RLS_OK : RLS_ERR_CUDA) != RLS_OK) break;
     for (int k = 0; k < K && status == RLS_OK; ++k)
-      status = init_lane(s, s->lanes[k], (const char*)Bd->d + (size_t)k * blen * es, blen, nullptr);
+      status = init_lane(s, s->lanes[k], (const char*)Bd->d + (size_t)k * bstride * es, blen, nullptr);
     if (status != RLS_OK) break;
     const int cap = s->desc.kind == RLS_CGNR ? (int)std::min<int64_t>(s->desc.iterations, s->n) : s->desc.iterations;
     // one apply per iteration (FISTA / POGM / OptISTA / CGNR): the K applies of a batched iteration go through

@@ -58,8 +58,12 @@ def test_library_is_sm100a_and_uses_tma(rls):
     out = subprocess.run(["cuobjdump", "-lelf", rls._capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", rls._capi.LIB_PATH], capture_output=True, text=True).stdout
-    assert "UTMALDG" in sass, "the one-pass kernel must stage A with TMA"
-    assert "HMMA" not in sass
+    import re
+    assert "UTMALDG" in sass, "the column-major one-pass kernel and the tensor-core GEMM stage tiles with TMA tensor copies"
+    assert "UBLKCP" in sass, "the row-major one-pass kernel streams row slices with 1-D bulk copies"
+    assert "UTCHMMA" in sass and "LDTM" in sass, "the multi-RHS / Gram GEMM must run on tcgen05 with TMEM accumulators"
+    assert "STAS" in sass, "the cluster exchange of the one-pass kernel uses st.async into peer shared memory"
+    assert not re.search(r"(?<![A-Z])HMMA", sass), "no warp-level mma.sync / wmma tensor-core code"
 
 
 def test_no_gpu_means_loud_failure_not_fallback(rls):

@@ -209,3 +209,45 @@ def test_tv_denoises_piecewise_constant(rls, ctx):
     assert np.linalg.norm(x - x_tv) <= np.linalg.norm(x - x_l1)
     tv = lambda v: 2 * sigma * np.sum(np.abs(O.grad_op(v, (N, N), (1, 2))))
     assert 0.5 * np.linalg.norm(noisy - x_tv) ** 2 + tv(x_tv) <= tv(noisy)
+
+
+# ---------------------------------------------------------------- tensor-core paths (csrc/rls_tc.cu)
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape_k", [(128, 128, 32), (300, 200, 5), (1000, 516, 64), (77, 1030, 3), (2050, 4100, 17)])
+def test_normal_apply_batch_tensor_cores(rls, ctx, dtype, shape_k):
+    """K right-hand sides through two tcgen05 GEMMs (kind::tf32, three-term split, FP32 accumulation outside the
+    tensor core) against NumPy float64 and against K single CUDA-core applies."""
+    m, n, K = shape_k
+    A, _ = rand_matrix(dtype, m, n, 51)
+    X = np.stack([rand_vector(dtype, n, 60 + k) for k in range(K)], axis=1)
+    op = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx, layout="row"), form="onepass")
+    xs = [rls.B200Vector.from_numpy(np.ascontiguousarray(X[:, k]), ctx) for k in range(K)]
+    G = np.stack([o.to_numpy() for o in op.apply_batch(xs)], axis=1)
+    A64 = A.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
+    ref = A64.conj().T @ (A64 @ X)
+    for k in range(K):
+        assert rel(G[:, k], ref[:, k]) < 1.5e-6, (k, rel(G[:, k], ref[:, k]))
+    # column-major storage: no tensor-core plan, falls back to K single applies with identical results
+    opc = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx, layout="col"), form="twopass")
+    Gc = np.stack([o.to_numpy() for o in opc.apply_batch(xs)], axis=1)
+    assert np.array_equal(Gc[:, 0], opc.apply(xs[0]).to_numpy())
+    assert rel(Gc, ref) < 3e-6
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(256, 128), (300, 200), (1000, 516)])
+def test_gram_on_tensor_cores(rls, ctx, dtype, shape, monkeypatch):
+    m, n = shape
+    A, _ = rand_matrix(dtype, m, n, 71)
+    x = rand_vector(dtype, n, 72)
+    Ad = rls.B200Matrix.from_numpy(A, ctx, layout="row")
+    op = rls.B200NormalOp(Ad, form="gram")
+    assert "tensor cores" in op.describe()
+    A64 = A.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
+    ref = (A64.conj().T @ A64) @ x
+    g = op.apply(rls.B200Vector.from_numpy(x, ctx)).to_numpy()
+    assert rel(g, ref) < 1.5e-6
+    monkeypatch.setenv("RLS_GRAM_CUDA_CORES", "1")
+    op2 = rls.B200NormalOp(Ad, form="gram")
+    assert "tensor cores" not in op2.describe()
+    assert rel(op2.apply(rls.B200Vector.from_numpy(x, ctx)).to_numpy(), g) < 2e-6

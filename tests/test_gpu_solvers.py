@@ -225,7 +225,7 @@ def test_multi_rhs(rls, ctx, solver, tensor_cores, monkeypatch):
     applies) they are bit-identical."""
     monkeypatch.setenv("RLS_BATCH_TENSOR_CORES", "1" if tensor_cores else "0")
     dtype = np.complex64
-    A, _, _ = problem(dtype, 200, 96)
+    A, _, _ = problem(dtype, 201, 96)      # odd m: the columns of B are not 16-byte multiples
     X = np.stack([sparse_truth(dtype, 96, 300 + k, every=7) for k in range(5)], axis=1)
     B = (A @ X).astype(dtype)
     kw = dict(iterations=30)
