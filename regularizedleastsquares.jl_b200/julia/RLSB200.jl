@@ -102,11 +102,23 @@ end
 mutable struct B200Matrix{T} <: AbstractMatrix{T}
   handle::Ptr{Cvoid}; m::Int; n::Int
 end
-function B200Matrix(A::Matrix{T}) where T        # column-major, exactly as Julia stores it
+# The Julia side hands over its column-major `Matrix`; the DEVICE layout is the library's choice
+# (layout = :auto -> rows contiguous whenever the one-pass cluster kernel supports the shape, so that
+# A'(A x) sweeps HBM once; :col mirrors the host storage; :row forces it).  Upload / download translate.
+const LAYOUTS = Dict(:col => Int32(0), :row => Int32(1), :auto => Int32(2))
+function B200Matrix(A::Matrix{T}; layout::Symbol = :auto) where T
   h = Ref{Ptr{Cvoid}}(C_NULL)
-  GC.@preserve A check(ccall((:rls_mat_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}),
-                             ctx().handle, dtypecode(T), size(A, 1), size(A, 2), pointer(A), stride(A, 2), h))
+  GC.@preserve A check(ccall((:rls_mat_create_layout, LIB), Int32,
+                             (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Int64, Int32, Ref{Ptr{Cvoid}}),
+                             ctx().handle, dtypecode(T), size(A, 1), size(A, 2), pointer(A), stride(A, 2), LAYOUTS[layout], h))
   finalizer(M -> ccall((:rls_mat_destroy, LIB), Int32, (Ptr{Cvoid},), M.handle), B200Matrix{T}(h[], size(A)...))
+end
+# adopt a CuArray without copying (column-major, CUDA.jl's layout): two-sweep / TMA panel kernels
+function B200Matrix(dA::Ptr{Cvoid}, ::Type{T}, m::Int, n::Int, ld::Int) where T
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:rls_mat_wrap_device, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}),
+              ctx().handle, dtypecode(T), m, n, dA, ld, h))
+  finalizer(M -> ccall((:rls_mat_destroy, LIB), Int32, (Ptr{Cvoid},), M.handle), B200Matrix{T}(h[], m, n))
 end
 Base.size(A::B200Matrix) = (A.m, A.n)
 
@@ -124,6 +136,13 @@ Base.eltype(::B200NormalOp{T}) where T = T
 Base.size(op::B200NormalOp, d...) = size(op.A, 2)
 function LinearAlgebra.mul!(res::B200Vector, op::B200NormalOp, x::B200Vector)                # FISTA.jl:152
   check(ccall((:rls_normal_apply, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), op.handle, x.handle, res.handle)); res
+end
+# K right-hand sides at once (MultiThreading.jl:45-78 applies AHA per column): two tensor-core GEMMs
+function mul_batch!(res::Vector{<:B200Vector}, op::B200NormalOp, xs::Vector{<:B200Vector})
+  xh = Ptr{Cvoid}[x.handle for x in xs]; rh = Ptr{Cvoid}[r.handle for r in res]
+  GC.@preserve xh rh check(ccall((:rls_normal_apply_batch, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
+                                 op.handle, length(xs), pointer(xh), pointer(rh)))
+  res
 end
 function LinearAlgebra.mul!(g::B200Vector, At::Adjoint{T,B200Matrix{T}}, y::B200Vector) where T  # FISTA.jl:114
   check(ccall((:rls_gemv_c, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), parent(At).handle, y.handle, g.handle)); g
