@@ -117,11 +117,19 @@ int32_t rls_normal_shape(rls_normal_t op, int64_t* n, int32_t* dtype);
 rls_ctx_s* rls_normal_ctx(rls_normal_t op);
 rls_mat_s* rls_normal_matrix(rls_normal_t op);
 int32_t rls_normal_check_abort(rls_normal_t op);
+// per-cluster partial results of a one-pass apply whose final sum is left to the consuming kernel (ncl == 0: none)
+struct NormalPartials { const float* gpart; int64_t gstride; int ncl; };
+// apply with the finish (and optionally the FISTA momentum x*c1 + xold*c2) fused into neighbouring kernels; returns
+// with np->ncl == 0 and nothing launched when the operator cannot defer (not row-major one-pass, or row-sharded)
+int32_t rls_normal_apply_deferred_raw(rls_normal_t op, const void* x, const float* xold, const float* th_old, const float* th,
+                                      const int* gate, NormalPartials* np);
 // row-major one-pass kernels (rls_rowpass.cu)
 struct RowPlan;
 int32_t rls_rowpass_plan_create(rls_ctx_s* c, rls_mat_s* A, RowPlan** out);
 void rls_rowpass_plan_destroy(RowPlan* p);
 int32_t rls_rowpass_normal(RowPlan* p, const void* x, void* res, const int* gate);
+int32_t rls_rowpass_normal_deferred(RowPlan* p, const void* x, const float* xold, const float* th_old, const float* th, const int* gate,
+                                    const float** gpart, int64_t* gstride, int* ncl);
 int32_t rls_rowpass_gemv_n(RowPlan* p, const void* x, void* y, const int* gate);
 int32_t rls_rowpass_gemv_c(RowPlan* p, const void* y, void* g, const int* gate);
 int32_t rls_rowpass_check_abort(RowPlan* p);
@@ -151,6 +159,11 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 bool rls_pdl_enabled();
+// RLS_TRACE_EVENTS=1: CUDA events around selected launches, dumped (durations and gaps, ms) by rls_trace_dump()
+bool rls_trace_enabled();
+void rls_trace_begin(cudaStream_t st, const char* name);
+void rls_trace_end(cudaStream_t st);
+void rls_trace_dump();
 template <typename... KArgs, typename... Args>
 static inline cudaError_t rls_launch_pdl(cudaStream_t st, dim3 grid, dim3 block, void (*kernel)(KArgs...), Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -21,6 +21,65 @@ void rls_set_error(const char* fmt, ...) {
 
 extern "C" const char* rls_last_error(void) { return g_err; }
 
+struct TraceRec { const char* name; cudaEvent_t a, b; };
+static std::vector<TraceRec> g_trace;
+bool rls_trace_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("RLS_TRACE_EVENTS"); on = (e && atoi(e) != 0) ? 1 : 0; }
+  return on != 0;
+}
+void rls_trace_begin(cudaStream_t st, const char* name) {
+  if (!rls_trace_enabled() || g_trace.size() >= 4096) return;
+  TraceRec r{name, nullptr, nullptr};
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  g_trace.push_back(r);
+}
+void rls_trace_end(cudaStream_t st) {
+  if (!rls_trace_enabled() || g_trace.empty() || g_trace.size() > 4096) return;
+  cudaEventRecord(g_trace.back().b, st);
+}
+void rls_trace_dump() {
+  if (!rls_trace_enabled() || g_trace.empty()) return;
+  cudaDeviceSynchronize();
+  const size_t n = g_trace.size(), from = n > 24 ? n - 24 : 0;
+  {
+    float span = 0.f;
+    cudaEventElapsedTime(&span, g_trace[0].a, g_trace[n - 1].b);
+    double sum = 0, gaps = 0, worst = 0; size_t iw = 0;
+    for (size_t i = 0; i < n; ++i) {
+      float d = 0.f, g = 0.f;
+      cudaEventElapsedTime(&d, g_trace[i].a, g_trace[i].b);
+      if (i) cudaEventElapsedTime(&g, g_trace[i - 1].b, g_trace[i].a);
+      sum += d; gaps += g;
+      if (d + g > worst) { worst = d + g; iw = i; }
+    }
+    fprintf(stderr, "[trace] %zu records: span %.3f ms, sum of durations %.3f ms, sum of gaps %.3f ms, worst record #%zu %.4f ms\n", n, span, sum, gaps, iw, worst);
+    for (size_t q = 0; q < 8 && n >= 16; ++q) {  // mean duration of the large records per eighth of the trace
+      double m = 0; int cnt = 0;
+      for (size_t i = q * n / 8; i < (q + 1) * n / 8; ++i) {
+        float d = 0.f; cudaEventElapsedTime(&d, g_trace[i].a, g_trace[i].b);
+        if (d > 0.1f) { m += d; ++cnt; }
+      }
+      if (cnt) fprintf(stderr, "[trace] eighth %zu: mean large-kernel duration %.4f ms (%d launches)\n", q, m / cnt, cnt);
+    }
+    for (size_t i = 0; i < n && i < 4; ++i) {
+      float d = 0.f, g = 0.f;
+      cudaEventElapsedTime(&d, g_trace[i].a, g_trace[i].b);
+      if (i) cudaEventElapsedTime(&g, g_trace[i - 1].b, g_trace[i].a);
+      fprintf(stderr, "[trace] #%zu %-28s %8.4f ms   gap before %8.4f ms\n", i, g_trace[i].name, d, g);
+    }
+  }
+  for (size_t i = from; i < n; ++i) {
+    float dur = 0.f, gap = 0.f;
+    cudaEventElapsedTime(&dur, g_trace[i].a, g_trace[i].b);
+    if (i > from) cudaEventElapsedTime(&gap, g_trace[i - 1].b, g_trace[i].a);
+    fprintf(stderr, "[trace] %-28s %8.4f ms   gap before %8.4f ms\n", g_trace[i].name, dur, gap);
+  }
+  for (auto& r : g_trace) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_trace.clear();
+}
+
 bool rls_pdl_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("RLS_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }

@@ -697,6 +697,15 @@ extern "C" int32_t rls_normal_batch_debug(rls_normal_t op, int32_t which, float*
   return rls_tc_batch_debug(op->tc, which, host, nfloats);
 }
 
+int32_t rls_normal_apply_deferred_raw(rls_normal_t op, const void* x, const float* xold, const float* th_old, const float* th,
+                                      const int* gate, NormalPartials* np) {
+  np->gpart = nullptr; np->gstride = 0; np->ncl = 0;
+  const char* off = getenv("RLS_FUSE_ITERATION");
+  if ((off && atoi(off) == 0) || !op->row || op->form != RLS_NORMAL_ONEPASS || op->ctx->nranks > 1 || !op->A || op->A->m == 0 || op->A->n == 0)
+    return RLS_OK;
+  return rls_rowpass_normal_deferred(op->row, x, xold, th_old, th, gate, &np->gpart, &np->gstride, &np->ncl);
+}
+
 int32_t rls_normal_check_abort(rls_normal_t op) {
   if (op->row) return rls_rowpass_check_abort(op->row);
   if (op->form != RLS_NORMAL_ONEPASS) return RLS_OK;

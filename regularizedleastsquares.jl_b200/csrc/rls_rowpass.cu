@@ -44,6 +44,9 @@ struct RowpassArgs {
   int NS;             // ring stages
   int R;              // rows per round (host-side copy of the template parameter)
   const float* x;     // n-vector            (NORMAL, GEMV_N)
+  const float* xold;  // fused FISTA momentum (FISTA.jl:144-148): the operator is applied to x*c1 + xold*c2 with
+  const float* th_old;//   c1 = (1-θold)/θ, c2 = (θold-1)/θ + 1 formed from the device-resident θ's; NULL = plain x
+  const float* th;
   const float* yin;   // m-vector            (GEMV_C)
   float* yout;        // m-vector            (GEMV_N)
   float* gpart;       // [nclusters][gstride] (NORMAL, GEMV_C)
@@ -193,6 +196,23 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowpass_kernel(RowpassArgs p) {
         xr[v].x = c < p.nf ? p.x[c] : 0.f;
         xr[v].y = c + 1 < p.nf ? p.x[c + 1] : 0.f;
         xr[v].z = c + 2 < p.nf ? p.x[c + 2] : 0.f;
+      }
+      if (MODE == RP_NORMAL && p.xold) {
+        // same individually rounded operations as fista_momentum_kernel, so the operand is bit-identical to the
+        // vector the epilogue kernel forms for itself
+        float4 xo = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c + 3 < p.nf) xo = *reinterpret_cast<const float4*>(p.xold + c);
+        else {
+          xo.x = c < p.nf ? p.xold[c] : 0.f;
+          xo.y = c + 1 < p.nf ? p.xold[c + 1] : 0.f;
+          xo.z = c + 2 < p.nf ? p.xold[c + 2] : 0.f;
+        }
+        const float tho = *p.th_old, thn = *p.th;
+        const float c1 = fdiv(fsub(1.f, tho), thn), c2 = fadd(fdiv(fsub(tho, 1.f), thn), 1.f);
+        xr[v].x = fadd(fmul(xr[v].x, c1), fmul(xo.x, c2));
+        xr[v].y = fadd(fmul(xr[v].y, c1), fmul(xo.y, c2));
+        xr[v].z = fadd(fmul(xr[v].z, c1), fmul(xo.z, c2));
+        xr[v].w = fadd(fmul(xr[v].w, c1), fmul(xo.w, c2));
       }
     }
   }
@@ -498,10 +518,12 @@ int32_t rls_rowpass_plan_create(rls_ctx_s* c, rls_mat_s* A, RowPlan** out) {
   return RLS_OK;
 }
 
-static int32_t rowpass_launch(RowPlan* p, int mode, const void* x, const void* yin, void* yout, void* res, const int* gate) {
+static int32_t rowpass_launch(RowPlan* p, int mode, const void* x, const void* yin, void* yout, void* res, const int* gate,
+                              const float* xold = nullptr, const float* th_old = nullptr, const float* th = nullptr, bool defer_finish = false) {
   rls_ctx_s* c = p->ctx;
   rls_mat_s* A = p->A;
   RowpassArgs a;
+  a.xold = xold; a.th_old = th_old; a.th = th;
   a.A = (const float*)A->d; a.ldf = A->ld * p->fpe; a.m = A->m; a.nf = (int)(A->n * p->fpe);
   a.W = p->W; a.NS = p->NS; a.R = p->R;
   a.x = (const float*)x; a.yin = (const float*)yin; a.yout = (float*)yout;
@@ -518,9 +540,11 @@ static int32_t rowpass_launch(RowPlan* p, int mode, const void* x, const void* y
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = rls_pdl_enabled() ? 2 : 1;
+  rls_trace_begin(c->stream, mode == RP_NORMAL ? "rowpass normal" : mode == RP_GEMV_N ? "rowpass gemv_n" : "rowpass gemv_c");
   RLS_CUDA(cudaLaunchKernelEx(&cfg, p->fn[mode], a));
+  rls_trace_end(c->stream);
   c->launches++;
-  if (mode != RP_GEMV_N) {
+  if (mode != RP_GEMV_N && !defer_finish) {
     const int nf = a.nf;
     int grid = std::min(c->sm_count * 2, std::max(1, (nf / 4 + 255) / 256));
     RLS_CUDA(rls_launch_pdl(c->stream, dim3(grid), dim3(256), rowpass_finish_kernel, (const float*)p->gpart, p->gstride, ncl, nf, (float*)res, gate));
@@ -530,6 +554,14 @@ static int32_t rowpass_launch(RowPlan* p, int mode, const void* x, const void* y
 }
 
 int32_t rls_rowpass_normal(RowPlan* p, const void* x, void* res, const int* gate) { return rowpass_launch(p, RP_NORMAL, x, nullptr, nullptr, res, gate); }
+// the cluster kernel only: the caller's epilogue kernel sums the per-cluster partials itself (fixed order, the same
+// arithmetic as rowpass_finish_kernel) — one kernel boundary less per iteration.  Optional fused FISTA momentum.
+int32_t rls_rowpass_normal_deferred(RowPlan* p, const void* x, const float* xold, const float* th_old, const float* th, const int* gate,
+                                    const float** gpart, int64_t* gstride, int* ncl) {
+  RLS_TRY(rowpass_launch(p, RP_NORMAL, x, nullptr, nullptr, nullptr, gate, xold, th_old, th, true));
+  *gpart = p->gpart; *gstride = p->gstride; *ncl = p->ncl;
+  return RLS_OK;
+}
 int32_t rls_rowpass_gemv_n(RowPlan* p, const void* x, void* y, const int* gate) { return rowpass_launch(p, RP_GEMV_N, x, nullptr, y, nullptr, gate); }
 int32_t rls_rowpass_gemv_c(RowPlan* p, const void* y, void* g, const int* gate) { return rowpass_launch(p, RP_GEMV_C, nullptr, y, nullptr, g, gate); }
 

@@ -68,23 +68,47 @@ __global__ void __launch_bounds__(EB) fista_momentum_kernel(T* __restrict__ x, c
   EW_LOOP(i, n) x[i] = Elem<T>::add(Elem<T>::scale(x[i], c1), Elem<T>::scale(xold[i], c2));
 }
 
+// sum of the per-cluster partials of a deferred one-pass apply, in rowpass_finish_kernel's order
+template <typename T> __device__ __forceinline__ T sum_partials(const NormalPartials& np, int64_t i);
+template <> __device__ __forceinline__ float sum_partials<float>(const NormalPartials& np, int64_t i) {
+  float s = __ldcg(np.gpart + i);
+  for (int k = 1; k < np.ncl; ++k) s += __ldcg(np.gpart + (size_t)k * np.gstride + i);
+  return s;
+}
+template <> __device__ __forceinline__ float2 sum_partials<float2>(const NormalPartials& np, int64_t i) {
+  float2 s = __ldcg(reinterpret_cast<const float2*>(np.gpart) + i);
+  for (int k = 1; k < np.ncl; ++k) {
+    const float2 t = __ldcg(reinterpret_cast<const float2*>(np.gpart + (size_t)k * np.gstride) + i);
+    s.x += t.x; s.y += t.y;
+  }
+  return s;
+}
+
 // PART 0: everything; PART 1: up to the gradient step (a non-elementwise prox follows);
 // PART 2: projections + restart dot after that prox.
+// Fused form (single GPU, row-major one-pass operator): np.ncl > 0 — AHA x arrives as per-cluster partials that this
+// kernel adds up itself; fuse_mom — the momentum step FISTA.jl:144-148 is applied here (and, identically, inside the
+// operator kernel's x load) instead of by fista_momentum_kernel.
 template <typename T, int PART>
 __global__ void __launch_bounds__(EB) fista_main_kernel(T* __restrict__ x, T* __restrict__ res, const T* __restrict__ x0,
                                                          const T* __restrict__ xold, int64_t n, DevState* S, int reg_kind,
-                                                         double* partials, unsigned* ticket) {
+                                                         double* partials, unsigned* ticket, NormalPartials np, int fuse_mom) {
   pdl_prologue();
   if (S->done) return;
   const float rho = S->rho, thr = thr_from(S, 0, S->rho);   // ρ*λ(reg)   FISTA.jl:164
   const int proj = S->proj_mask, restart = S->restart;
+  const float c1 = fdiv(fsub(1.f, S->theta_old), S->theta);
+  const float c2 = fadd(fdiv(fsub(S->theta_old, 1.f), S->theta), 1.f);
   double acc[2] = {0.0, 0.0};
   EW_LOOP(i, n) {
     T r, xv;
     if (PART != 2) {
-      r = Elem<T>::sub(res[i], x0[i]);                 // res = AHA x - x₀        :152-153
+      T xin = x[i];
+      if (fuse_mom) xin = Elem<T>::add(Elem<T>::scale(xin, c1), Elem<T>::scale(xold[i], c2));   // :144-148
+      const T ahax = np.ncl > 0 ? sum_partials<T>(np, i) : res[i];
+      r = Elem<T>::sub(ahax, x0[i]);                   // res = AHA x - x₀        :152-153
       res[i] = r;
-      xv = Elem<T>::sub(x[i], Elem<T>::scale(r, rho)); // x -= ρ res              :154
+      xv = Elem<T>::sub(xin, Elem<T>::scale(r, rho));  // x -= ρ res              :154
       acc[0] += Elem<T>::abs2(r);
       if (PART == 1) { x[i] = xv; continue; }
       xv = prox_elementwise(xv, reg_kind, thr);        // prox!(reg, x, ρλ)       :164
@@ -699,20 +723,33 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L, int phase = IT_ALL)
   };
   switch (s->desc.kind) {
     case RLS_FISTA: {
-      if (phase != IT_POST) {
-        swap_roles(s, L); L.enq_swaps++;
-        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), fista_momentum_kernel<T>, P<T>(L.v[V_X]), P<T>(L.v[V_XOLD]), n, S));
+      NormalPartials np{nullptr, 0, 0};
+      int fuse = 0;
+      if (phase != IT_POST) { swap_roles(s, L); L.enq_swaps++; }
+      if (phase == IT_ALL) {
+        // single GPU + row-major one-pass operator: momentum fused into the operator's x load and into the
+        // epilogue, finish fused into the epilogue — two kernels per iteration instead of four
+        RLS_TRY(rls_normal_apply_deferred_raw(s->AHA, L.v[V_X]->d, (const float*)L.v[V_XOLD]->d, &S->theta_old, &S->theta, gate, &np));
+        fuse = np.ncl > 0;
       }
-      if (phase == IT_PRE) { record(L.v[V_X]->d, L.v[V_RES]->d); c->launches++; break; }
-      if (phase == IT_ALL) RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_RES]->d, gate));
+      if (!fuse) {
+        if (phase != IT_POST) {
+          RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), fista_momentum_kernel<T>, P<T>(L.v[V_X]), P<T>(L.v[V_XOLD]), n, S));
+          c->launches++;
+        }
+        if (phase == IT_PRE) { record(L.v[V_X]->d, L.v[V_RES]->d); break; }
+        if (phase == IT_ALL) RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_RES]->d, gate));
+      }
       if (ew) {
-        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), fista_main_kernel<T, 0>, P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick));
-        c->launches += phase == IT_ALL ? 2 : 1;
+        rls_trace_begin(st, "fista_main");
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), fista_main_kernel<T, 0>, P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick, np, fuse));
+        rls_trace_end(st);
+        c->launches += 1;
       } else {
-        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), fista_main_kernel<T, 1>, P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick));
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), fista_main_kernel<T, 1>, P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick, np, fuse));
         RLS_TRY(rls_prox_launch(c, s->dtype, L.v[V_X]->d, n, &reg, 0.f, &S->thr, gate, &s->tv));
-        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), fista_main_kernel<T, 2>, P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick));
-        c->launches += 3;
+        RLS_CUDA(rls_launch_pdl(st, dim3(g), dim3(EB), fista_main_kernel<T, 2>, P<T>(L.v[V_X]), P<T>(L.v[V_RES]), P<T>(L.v[V_X0]), P<T>(L.v[V_XOLD]), n, S, reg.kind, part, tick, NormalPartials{nullptr, 0, 0}, 0));
+        c->launches += 2;
       }
       break;
     }
@@ -1052,6 +1089,7 @@ extern "C" int32_t rls_solver_solve(rls_solver_t s, rls_vec_t b, rls_vec_t x0, i
   Lane& L = s->lanes[0];
   RLS_TRY(solve_lane_async(s, L, b->d, b->len, x0 ? x0->d : nullptr));
   RLS_TRY(pull_state(s, L));
+  rls_trace_dump();
   reconcile_roles(s, L);
   if (iterations_done) *iterations_done = L.hS->iteration;
   if (scalars) fill_scalars(L.hS, scalars);

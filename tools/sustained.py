@@ -8,6 +8,8 @@ m, n, dtype, secs = int(sys.argv[1]), int(sys.argv[2]), np.dtype(sys.argv[3]), f
 ctx = rls.B200Context.default(0)
 A = rls.B200Matrix.philox(dtype, m, n, seed=1, scale=1.0 / np.sqrt(m), ctx=ctx, layout="row")
 x = rls.B200Vector(ctx, dtype, n).fill_philox(2, stream=1, dist=1)
+if os.environ.get("SPARSE_X"):
+    xh = x.to_numpy(); xh[np.arange(n) % 100 != 0] = 0; x.upload(xh)
 op = rls.B200NormalOp(A, form="onepass")
 g = rls.B200Vector(ctx, dtype, n)
 by = m * n * dtype.itemsize
@@ -24,5 +26,6 @@ while time.time() < t_end:
     clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-i", "0"], capture_output=True, text=True).stdout.strip()
     out.append((ms, clk))
 print(op.describe())
-for ms, clk in out[:3] + out[-3:]:
+print("x:", "sparse (1 % non-zeros)" if os.environ.get("SPARSE_X") else "dense")
+for ms, clk in out[:2] + out[len(out)//2:len(out)//2+1] + out[-2:]:
     print(f"  {ms:.4f} ms/apply {by / ms / 1e6:.0f} GB/s   sm MHz, W: {clk}")
