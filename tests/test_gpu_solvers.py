@@ -291,3 +291,38 @@ def test_errors_are_reference_errors(rls, ctx):
         rls.solve_(S, np.ones(5, np.float32))     # wrong length b: status code, no abort
     with pytest.warns(UserWarning, match="filtered out"):
         rls.createLinearSolver(rls.CGNR, A, iterations=3, rho=0.1)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_multi_rhs_per_column_stopping(rls, ctx, dtype):
+    """MultiThreading.jl:45-78 keeps a per-column convergence mask: columns of very different difficulty stop at
+    different iterations; the batched (tensor-core) driver must reproduce every column's count and iterate."""
+    m, n, K = 384, 160, 6
+    A, _ = rand_matrix(dtype, m, n, 900)
+    rho = rho_for(A)
+    X = np.stack([sparse_truth(dtype, n, 910 + k, every=5 + 3 * k) for k in range(K)], axis=1)
+    X[:, 1] *= 0                     # a zero right-hand side converges at once
+    X[:, 4] *= np.float32(1e3)
+    B = (A @ X).astype(dtype)
+    S = rls.FISTA(A, reg=rls.L1Regularization(np.float32(1e-3)), iterations=60, rho=rho, relTol=np.float32(2e-3))
+    Xb = rls.solve_(S, B)
+    counts = list(S.batch_iterations)
+    seq = []
+    for k in range(K):
+        xk = rls.solve_(S, B[:, k].copy())
+        seq.append(S.iteration)
+        assert rel(Xb[:, k], xk) < TOL or np.linalg.norm(xk) == 0, k
+    assert counts == seq, (counts, seq)
+    assert len(set(counts)) > 1, "the columns were meant to stop at different iterations"
+
+
+def test_multi_rhs_more_columns_than_one_gemm_tile(rls, ctx):
+    """K * 2 > 128 complex columns do not fit one 128-wide GEMM tile: the driver falls back to per-column applies."""
+    dtype = np.complex64
+    m, n, K = 96, 64, 70
+    A, _ = rand_matrix(dtype, m, n, 950)
+    B = np.stack([rand_vector(dtype, m, 960 + k) for k in range(K)], axis=1)
+    S = rls.CGNR(A, iterations=8, relTol=0.0)
+    Xb = rls.solve_(S, B)
+    for k in (0, 33, 69):
+        assert np.array_equal(Xb[:, k], rls.solve_(S, B[:, k].copy()))
