@@ -142,6 +142,8 @@ int32_t rls_tc_batch_create(rls_mat_s* A, int K, TcBatchPlan** out);
 void rls_tc_batch_destroy(TcBatchPlan* p);
 int32_t rls_tc_batch_apply(TcBatchPlan* p, const void* const* xs, void* const* outs, const int* const* gates);
 int32_t rls_tc_batch_check_abort(TcBatchPlan* p);
+int32_t rls_tc_batch_adjoint(TcBatchPlan* p, const void* const* bs, void* const* outs);
+int32_t rls_normal_adjoint_batch_raw(rls_normal_t op, int K, const void* const* bs, void* const* outs, bool* done);
 int32_t rls_tc_batch_debug(TcBatchPlan* p, int which, float* host, int64_t nfloats);
 int32_t rls_tc_gram(rls_mat_s* A, rls_mat_s* G);
 int32_t rls_normal_apply_batch_raw(rls_normal_t op, int K, const void* const* xs, void* const* outs, const int* const* gates);

@@ -674,6 +674,22 @@ int32_t rls_normal_apply_batch_raw(rls_normal_t op, int K, const void* const* xs
   return RLS_OK;
 }
 
+// outs_k = A' b_k for the K columns of a multi-RHS init!, as one tensor-core GEMM when the batch plan applies;
+// *done = false leaves the back-projections to the caller (per-column gemv_c)
+int32_t rls_normal_adjoint_batch_raw(rls_normal_t op, int K, const void* const* bs, void* const* outs, bool* done) {
+  *done = false;
+  const char* off = getenv("RLS_BATCH_TENSOR_CORES");
+  if ((off && atoi(off) == 0) || op->form == RLS_NORMAL_GRAM || !op->A || !rls_tc_batch_supported(op->A, K)) return RLS_OK;
+  if (op->tc && op->tc_K != K) { rls_tc_batch_destroy(op->tc); op->tc = nullptr; }
+  if (!op->tc) {
+    if (rls_tc_batch_create(op->A, K, &op->tc) != RLS_OK) { op->tc = nullptr; return RLS_OK; }
+    op->tc_K = K;
+  }
+  RLS_TRY(rls_tc_batch_adjoint(op->tc, bs, outs));
+  *done = true;
+  return RLS_OK;
+}
+
 extern "C" int32_t rls_normal_apply_batch(rls_normal_t op, int32_t K, const rls_vec_t* xs, const rls_vec_t* outs) {
   RLS_CHECK_ARG(op && xs && outs && K >= 1, "bad argument");
   std::vector<const void*> xp(K);

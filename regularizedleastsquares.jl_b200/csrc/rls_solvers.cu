@@ -7,6 +7,7 @@
 // momentum/inertia) whose last block runs the scalar recurrences on the device.  All
 // kernels are gated by the device-side done() flag, so a callback-free solve! is enqueued
 // back to back with a single synchronisation at the end.
+#include <chrono>
 #include <map>
 
 #include "rls_prox.cuh"
@@ -612,7 +613,7 @@ template <typename T> static T* P(rls_vec_s* v) { return v ? (T*)v->d : nullptr;
 
 // ---------------------------------- init! ---------------------------------------------
 template <typename T>
-static int32_t init_lane_t(rls_solver_s* s, Lane& L, const void* b_dev, int64_t b_len, const void* x0_dev) {
+static int32_t init_lane_t(rls_solver_s* s, Lane& L, const void* b_dev, int64_t b_len, const void* x0_dev, bool have_atb = false) {
   rls_ctx_s* c = s->ctx;
   cudaStream_t st = c->stream;
   const int64_t n = s->n;
@@ -625,7 +626,9 @@ static int32_t init_lane_t(rls_solver_s* s, Lane& L, const void* b_dev, int64_t 
   L.base_iter = 0;
   // x₀ / β_y = A' b   (or b itself when only AHA was given)
   T* x0v = P<T>(kind == RLS_ADMM ? L.v[V_BETAY] : L.v[V_X0]);
-  if (s->A) {
+  if (s->A && have_atb) {
+    // the multi-RHS driver already formed A'b for all columns with one GEMM (and all-reduced it)
+  } else if (s->A) {
     RLS_TRY(rls_gemv_c_raw(s->A, b_dev, x0v, nullptr));
     if (c->nranks > 1) RLS_TRY(rls_allreduce_raw(c, x0v, n * (Elem<T>::is_complex ? 2 : 1)));
   } else {
@@ -864,9 +867,9 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L, int phase = IT_ALL)
   return RLS_OK;
 }
 
-static int32_t init_lane(rls_solver_s* s, Lane& L, const void* b, int64_t blen, const void* x0) {
-  if (s->dtype == RLS_C32) return init_lane_t<float2>(s, L, b, blen, x0);
-  return init_lane_t<float>(s, L, b, blen, x0);
+static int32_t init_lane(rls_solver_s* s, Lane& L, const void* b, int64_t blen, const void* x0, bool have_atb = false) {
+  if (s->dtype == RLS_C32) return init_lane_t<float2>(s, L, b, blen, x0, have_atb);
+  return init_lane_t<float>(s, L, b, blen, x0, have_atb);
 }
 static int32_t enqueue_iteration(rls_solver_s* s, Lane& L, int phase = IT_ALL) {
   if (s->dtype == RLS_C32) return enqueue_iteration_t<float2>(s, L, phase);
@@ -1157,6 +1160,11 @@ extern "C" int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_hos
   RLS_CHECK_ARG(ldb >= blen && ldx >= s->n, "leading dimensions too small");
   RlsDeviceGuard g(s->ctx->device);
   const size_t es = rls_elem_size(s->dtype);
+  // RLS_TRACE_BATCH=1: wall time of the phases (with a stream sync at every phase boundary)
+  const bool tr = getenv("RLS_TRACE_BATCH") != nullptr;
+  auto now = [&]() { if (tr) cudaStreamSynchronize(s->ctx->stream); return std::chrono::steady_clock::now(); };
+  auto ms_since = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   const size_t old = s->lanes.size();
   if ((size_t)K < old) for (size_t k = K; k < old; ++k) free_lane(s->lanes[k]);
   s->lanes.resize(K);
@@ -1168,9 +1176,23 @@ extern "C" int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_hos
   int32_t status = RLS_OK;
   do {
     if ((status = (cudaMemcpy2DAsync(Bd->d, bstride * es, B_host, ldb * es, blen * es, K, cudaMemcpyHostToDevice, s->ctx->stream) == cudaSuccess) ? RLS_OK : RLS_ERR_CUDA) != RLS_OK) break;
+    const auto t1 = now();
+    // back-projections A'b_k of all columns as one tensor-core GEMM (row-major A, K >= 8), else per column in init!
+    bool have_atb = false;
+    if (s->A && K > 1) {
+      std::vector<const void*> bp(K);
+      std::vector<void*> xp(K);
+      for (int k = 0; k < K; ++k) {
+        bp[k] = (const char*)Bd->d + (size_t)k * bstride * es;
+        xp[k] = s->lanes[k].v[s->desc.kind == RLS_ADMM ? V_BETAY : V_X0]->d;
+      }
+      status = rls_normal_adjoint_batch_raw(s->AHA, K, bp.data(), xp.data(), &have_atb);
+      if (status != RLS_OK) break;
+    }
     for (int k = 0; k < K && status == RLS_OK; ++k)
-      status = init_lane(s, s->lanes[k], (const char*)Bd->d + (size_t)k * bstride * es, blen, nullptr);
+      status = init_lane(s, s->lanes[k], (const char*)Bd->d + (size_t)k * bstride * es, blen, nullptr, have_atb);
     if (status != RLS_OK) break;
+    const auto t2 = now();
     const int cap = s->desc.kind == RLS_CGNR ? (int)std::min<int64_t>(s->desc.iterations, s->n) : s->desc.iterations;
     // one apply per iteration (FISTA / POGM / OptISTA / CGNR): the K applies of a batched iteration go through
     // rls_normal_apply_batch_raw — two tensor-core GEMMs reading A once each when A is row-major — between the
@@ -1187,6 +1209,8 @@ extern "C" int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_hos
       for (int k = 0; k < K && status == RLS_OK; ++k) status = enqueue_iteration(s, s->lanes[k], IT_POST);
     }
     if (status != RLS_OK) break;
+    const auto t3 = now();
+    if (tr) fprintf(stderr, "[batch] K=%d: alloc + H2D %.2f ms, init (A'b per column) %.2f ms, iterations %.2f ms\n", K, ms_since(t0, t1), ms_since(t1, t2), ms_since(t2, t3));
     for (int k = 0; k < K && status == RLS_OK; ++k) {
       Lane& L = s->lanes[k];
       if (s->desc.kind == RLS_CGNR && s->desc.proj_mask)

@@ -312,37 +312,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ---- pack / unpack between K lane vectors and the GEMM operands -------------------------
+// The K device pointers travel as kernel parameters (<= 128 columns per GEMM pass): no per-iteration H2D copy.
+constexpr int TC_MAXK = 128;
+struct PtrTable { const void* p[TC_MAXK]; };
+
 // B^T of mode N, [Npad][ldb] floats.  complex: row 2k = conj(x_k), row 2k+1 = i conj(x_k); real: row k = x_k.
-__global__ void tc_pack_x_kernel(const float* const* __restrict__ xs, int K, int fpe, int64_t n, float* __restrict__ BT, int64_t ldb, int Npad) {
+__global__ void tc_pack_x_kernel(const __grid_constant__ PtrTable xs, int K, int fpe, int64_t n, float* __restrict__ BT, int64_t ldb, int Npad) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int rowp = blockIdx.y;  // B^T row
   if (j >= n) return;
   if (fpe == 1) {
-    BT[(int64_t)rowp * ldb + j] = rowp < K ? xs[rowp][j] : 0.f;
+    BT[(int64_t)rowp * ldb + j] = rowp < K ? reinterpret_cast<const float*>(xs.p[rowp])[j] : 0.f;
   } else {
     const int k = rowp >> 1;
     float2 v = make_float2(0.f, 0.f);
-    if (k < K) v = reinterpret_cast<const float2*>(xs[k])[j];
+    if (k < K) v = reinterpret_cast<const float2*>(xs.p[k])[j];
     const float2 o = (rowp & 1) ? make_float2(v.y, v.x) : make_float2(v.x, -v.y);
     reinterpret_cast<float2*>(BT + (int64_t)rowp * ldb)[j] = o;
   }
 }
 // res_k[j] from P [nf][ldp]: complex (P[2j,2k] + P[2j+1,2k+1]) + i (P[2j,2k+1] - P[2j+1,2k]); real P[j,k].  Lane k is
 // skipped when its done() gate is set.
-__global__ void tc_unpack_g_kernel(const float* __restrict__ P, int64_t ldp, int K, int fpe, int64_t n, float* const* __restrict__ outs,
-                                   const int* const* __restrict__ gates) {
+__global__ void tc_unpack_g_kernel(const float* __restrict__ P, int64_t ldp, int K, int fpe, int64_t n, const __grid_constant__ PtrTable outs,
+                                   const __grid_constant__ PtrTable gates, int have_gates) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
   const int k = threadIdx.x + blockIdx.y * blockDim.x;
   if (j >= n || k >= K) return;
-  const int* gate = gates ? gates[k] : nullptr;
+  const int* gate = have_gates ? reinterpret_cast<const int*>(gates.p[k]) : nullptr;
   if (gate && *gate) return;
   if (fpe == 1) {
-    outs[k][j] = P[j * ldp + k];
+    reinterpret_cast<float*>(const_cast<void*>(outs.p[k]))[j] = P[j * ldp + k];
   } else {
     const float2 a = *reinterpret_cast<const float2*>(P + (2 * j) * ldp + 2 * k);
     const float2 b = *reinterpret_cast<const float2*>(P + (2 * j + 1) * ldp + 2 * k);
-    reinterpret_cast<float2*>(outs[k])[j] = make_float2(a.x + b.y, a.y - b.x);
+    reinterpret_cast<float2*>(const_cast<void*>(outs.p[k]))[j] = make_float2(a.x + b.y, a.y - b.x);
   }
+}
+// Y~ of mode T from K m-vectors (the batched back-projection A'B of init!): Y~[i][fpe*k + c] = b_k[i*fpe + c]
+__global__ void tc_pack_y_kernel(const __grid_constant__ PtrTable bs, int K, int fpe, int64_t m, float* __restrict__ Y, int Npad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+  const int col = threadIdx.x + blockIdx.y * blockDim.x;  // float column of Y~
+  if (i >= m || col >= Npad) return;
+  const int k = col / fpe, c = col - k * fpe;
+  Y[i * Npad + col] = k < K ? reinterpret_cast<const float*>(bs.p[k])[i * fpe + c] : 0.f;
 }
 // Gram epilogue: G (n x n, column-major) from P = A~^T A~ (nf x ldp).  complex: G[j,j'] = conj-combined 2x2 block.
 __global__ void tc_gram_finish_kernel(const float* __restrict__ P, int64_t ldp, int fpe, int64_t n, float* __restrict__ G, int64_t ldg) {
@@ -424,22 +436,23 @@ struct TcBatchPlan {
   float* XT = nullptr;    // [Npad][ldx]   B^T of mode N
   float* Y = nullptr;     // [m][Npad]     Y~
   float* P = nullptr;     // [nf][Npad]    A~^T Y~
-  const float** d_xs = nullptr;
-  float** d_outs = nullptr;
-  const int** d_gates = nullptr;
   int* abort_flag = nullptr;
   CUtensorMap mapA, mapAt, mapXT, mapY;  // mapAt: A described for the transposed (MN-major) use
 };
 
 void rls_tc_batch_destroy(TcBatchPlan* p) {
   if (!p) return;
-  cudaFree(p->XT); cudaFree(p->Y); cudaFree(p->P); cudaFree((void*)p->d_xs); cudaFree(p->d_outs); cudaFree((void*)p->d_gates);
+  cudaFree(p->XT); cudaFree(p->Y); cudaFree(p->P);
   cudaFree(p->abort_flag);
   delete p;
 }
 
 bool rls_tc_batch_supported(const rls_mat_s* A, int K) {
-  if (!A || A->layout != RLS_LAYOUT_ROWMAJOR || K < 2) return false;
+  // below ~8 columns K one-pass sweeps (K x m n s bytes at HBM speed) are cheaper than two GEMMs whose time is
+  // nearly independent of N (measured at the C4 shape: 3.4 ms for N = 32 against 0.33 ms per one-pass apply)
+  const char* mk = getenv("RLS_BATCH_MIN_K");
+  const int min_k = mk ? atoi(mk) : 8;
+  if (!A || A->layout != RLS_LAYOUT_ROWMAJOR || K < 2 || K < min_k) return false;
   const int fpe = A->dtype == RLS_C32 ? 2 : 1;
   if (K * fpe > 128) return false;  // one 128 x N tile per CTA, N <= 128 (three N-wide accumulators in TMEM)
   if (((uintptr_t)A->d & 15) != 0 || (A->ld * fpe) % 4 != 0) return false;
@@ -459,8 +472,7 @@ int32_t rls_tc_batch_create(rls_mat_s* A, int K, TcBatchPlan** out) {
   bool ok = cudaMalloc(&p->XT, (size_t)p->Npad * p->ldx * 4) == cudaSuccess &&
             cudaMalloc(&p->Y, (size_t)std::max<int64_t>(A->m, 1) * p->Npad * 4) == cudaSuccess &&
             cudaMalloc(&p->P, (size_t)p->nf * p->Npad * 4) == cudaSuccess &&
-            cudaMalloc((void**)&p->d_xs, sizeof(void*) * K) == cudaSuccess && cudaMalloc((void**)&p->d_outs, sizeof(void*) * K) == cudaSuccess &&
-            cudaMalloc((void**)&p->d_gates, sizeof(void*) * K) == cudaSuccess && cudaMalloc(&p->abort_flag, 4) == cudaSuccess;
+            cudaMalloc(&p->abort_flag, 4) == cudaSuccess;
   if (!ok) { cudaGetLastError(); rls_tc_batch_destroy(p); rls_set_error("tensor-core batch path: out of device memory"); return RLS_ERR_NOMEM; }
   cudaMemsetAsync(p->abort_flag, 0, 4, A->ctx->stream);
   int32_t s = make_map(&p->mapA, (const float*)A->d, A->m, p->nf, A->ld * p->fpe, false);
@@ -481,12 +493,11 @@ int32_t rls_tc_batch_apply(TcBatchPlan* p, const void* const* xs, void* const* o
     for (int k = 0; k < K; ++k) RLS_CUDA(cudaMemsetAsync(outs[k], 0, A->n * rls_elem_size(A->dtype), c->stream));
     return RLS_OK;
   }
-  RLS_CUDA(cudaMemcpyAsync((void*)p->d_xs, xs, sizeof(void*) * K, cudaMemcpyHostToDevice, c->stream));
-  RLS_CUDA(cudaMemcpyAsync((void*)p->d_outs, outs, sizeof(void*) * K, cudaMemcpyHostToDevice, c->stream));
-  if (gates) RLS_CUDA(cudaMemcpyAsync((void*)p->d_gates, gates, sizeof(void*) * K, cudaMemcpyHostToDevice, c->stream));
+  PtrTable tx{}, to{}, tg{};
+  for (int k = 0; k < K; ++k) { tx.p[k] = xs[k]; to.p[k] = outs[k]; tg.p[k] = gates ? gates[k] : nullptr; }
   {
     dim3 grid((unsigned)((A->n + 255) / 256), (unsigned)p->Npad);
-    tc_pack_x_kernel<<<grid, 256, 0, c->stream>>>(p->d_xs, K, p->fpe, A->n, p->XT, p->ldx, p->Npad);
+    tc_pack_x_kernel<<<grid, 256, 0, c->stream>>>(tx, K, p->fpe, A->n, p->XT, p->ldx, p->Npad);
     c->launches++;
   }
   TcArgs a{};
@@ -503,7 +514,40 @@ int32_t rls_tc_batch_apply(TcBatchPlan* p, const void* const* xs, void* const* o
   {
     dim3 block(32, 8);
     dim3 grid((unsigned)((A->n + 7) / 8), (unsigned)((K + 31) / 32));
-    tc_unpack_g_kernel<<<grid, block, 0, c->stream>>>(p->P, p->Npad, K, p->fpe, A->n, p->d_outs, gates ? p->d_gates : nullptr);
+    tc_unpack_g_kernel<<<grid, block, 0, c->stream>>>(p->P, p->Npad, K, p->fpe, A->n, to, tg, gates ? 1 : 0);
+    c->launches++;
+  }
+  RLS_CUDA(cudaGetLastError());
+  return RLS_OK;
+}
+
+// outs_k = A' b_k for K m-vectors (init!: mul!(x0, adjoint(A), b), FISTA.jl:114, CGNR.jl:132, ADMM.jl:198) as ONE mode-T GEMM
+int32_t rls_tc_batch_adjoint(TcBatchPlan* p, const void* const* bs, void* const* outs) {
+  rls_ctx_s* c = p->ctx;
+  rls_mat_s* A = p->A;
+  const int K = p->K;
+  if (A->m == 0 || A->n == 0) {
+    for (int k = 0; k < K; ++k) RLS_CUDA(cudaMemsetAsync(outs[k], 0, A->n * rls_elem_size(A->dtype), c->stream));
+    return RLS_OK;
+  }
+  PtrTable tb{}, to{}, tg{};
+  for (int k = 0; k < K; ++k) { tb.p[k] = bs[k]; to.p[k] = outs[k]; }
+  {
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((A->m + 7) / 8), (unsigned)((p->Npad + 31) / 32));
+    tc_pack_y_kernel<<<grid, block, 0, c->stream>>>(tb, K, p->fpe, A->m, p->Y, p->Npad);
+    c->launches++;
+  }
+  TcArgs a{};
+  a.Npad = p->Npad; a.b_col0_from_y = 0; a.abort_flag = p->abort_flag;
+  a.transposed = 1; a.nkb = (int)((A->m + TC_BK - 1) / TC_BK);
+  a.D = p->P; a.ldd = p->Npad; a.Mtot = p->nf; a.Nvalid = p->Npad; a.Ntot = p->Npad;
+  RLS_TRY(tc_launch(c, p->mapAt, p->mapY, a, (int)((p->nf + TC_BM - 1) / TC_BM), 1));
+  if (c->nranks > 1) RLS_TRY(rls_allreduce_raw(c, p->P, p->nf * p->Npad));
+  {
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((A->n + 7) / 8), (unsigned)((K + 31) / 32));
+    tc_unpack_g_kernel<<<grid, block, 0, c->stream>>>(p->P, p->Npad, K, p->fpe, A->n, to, tg, 0);
     c->launches++;
   }
   RLS_CUDA(cudaGetLastError());

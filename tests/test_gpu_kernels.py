@@ -214,9 +214,10 @@ def test_tv_denoises_piecewise_constant(rls, ctx):
 # ---------------------------------------------------------------- tensor-core paths (csrc/rls_tc.cu)
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape_k", [(128, 128, 32), (300, 200, 5), (1000, 516, 64), (77, 1030, 3), (2050, 4100, 17)])
-def test_normal_apply_batch_tensor_cores(rls, ctx, dtype, shape_k):
+def test_normal_apply_batch_tensor_cores(rls, ctx, dtype, shape_k, monkeypatch):
     """K right-hand sides through two tcgen05 GEMMs (kind::tf32, three-term split, FP32 accumulation outside the
     tensor core) against NumPy float64 and against K single CUDA-core applies."""
+    monkeypatch.setenv("RLS_BATCH_MIN_K", "2")
     m, n, K = shape_k
     A, _ = rand_matrix(dtype, m, n, 51)
     X = np.stack([rand_vector(dtype, n, 60 + k) for k in range(K)], axis=1)

@@ -224,6 +224,7 @@ def test_multi_rhs(rls, ctx, solver, tensor_cores, monkeypatch):
     agree with the sequential solves to the per-iterate parity bound; with RLS_BATCH_TENSOR_CORES=0 (K single
     applies) they are bit-identical."""
     monkeypatch.setenv("RLS_BATCH_TENSOR_CORES", "1" if tensor_cores else "0")
+    monkeypatch.setenv("RLS_BATCH_MIN_K", "2")      # the GEMM path normally starts at 8 columns
     dtype = np.complex64
     A, _, _ = problem(dtype, 201, 96)      # odd m: the columns of B are not 16-byte multiples
     X = np.stack([sparse_truth(dtype, 96, 300 + k, every=7) for k in range(5)], axis=1)
@@ -294,9 +295,10 @@ def test_errors_are_reference_errors(rls, ctx):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_multi_rhs_per_column_stopping(rls, ctx, dtype):
+def test_multi_rhs_per_column_stopping(rls, ctx, dtype, monkeypatch):
     """MultiThreading.jl:45-78 keeps a per-column convergence mask: columns of very different difficulty stop at
     different iterations; the batched (tensor-core) driver must reproduce every column's count and iterate."""
+    monkeypatch.setenv("RLS_BATCH_MIN_K", "2")
     m, n, K = 384, 160, 6
     A, _ = rand_matrix(dtype, m, n, 900)
     rho = rho_for(A)

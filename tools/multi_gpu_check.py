@@ -5,6 +5,8 @@ match it (rel-L2 <= 1e-5; the only difference is the summation order of the n-ve
 import os
 import sys
 
+os.environ.setdefault("RLS_BATCH_MIN_K", "2")   # exercise the tensor-core multi-RHS path with 3 columns
+
 import numpy as np
 import torch
 import torch.distributed as dist

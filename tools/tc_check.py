@@ -3,6 +3,8 @@ plus timing at the C4 shape.  usage: python tools/tc_check.py [check] [time]"""
 import os
 import sys
 
+os.environ.setdefault("RLS_BATCH_MIN_K", "2")
+
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
