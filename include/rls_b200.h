@@ -111,6 +111,12 @@ int32_t rls_ctx_flush_l2(rls_ctx_t ctx);
 int32_t rls_comm_unique_id(void* id128);
 int32_t rls_ctx_comm_init(rls_ctx_t ctx, int32_t rank, int32_t nranks, const void* id128);
 int32_t rls_ctx_comm_info(rls_ctx_t ctx, int32_t* rank, int32_t* nranks);
+/* optional: one-shot all-reduce over NVLink peer memory, fused with the final sum of the one-pass kernel (replaces
+ * finish kernel + ncclAllReduce + copy by one kernel per apply).  Every rank exports a 64-byte CUDA IPC handle of its
+ * exchange buffer (vectors of up to max_floats floats), the host gathers the nranks handles with its own transport
+ * and every rank imports the table.  Needs peer access between the GPUs (one NVSwitch box). */
+int32_t rls_ctx_peer_export(rls_ctx_t ctx, int64_t max_floats, void* handle64);
+int32_t rls_ctx_peer_import(rls_ctx_t ctx, const void* handles /* nranks x 64 bytes, rank order */, int32_t nranks);
 /* sum-allreduce of a device vector across ranks (the n-vector A_i' r_i) */
 int32_t rls_vec_allreduce(rls_vec_t v);
 

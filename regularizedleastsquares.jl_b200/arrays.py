@@ -80,6 +80,22 @@ class B200Context:
         self.rank, self.nranks = int(rank), int(nranks)
 
 
+def _peer_export(self, max_floats):
+    buf = C.create_string_buffer(64)
+    capi.call("rls_ctx_peer_export", self.handle, int(max_floats), buf)
+    return buf.raw
+
+
+def _peer_import(self, handles):
+    blob = b"".join(bytes(h) for h in handles)
+    buf = C.create_string_buffer(blob, len(blob))
+    capi.call("rls_ctx_peer_import", self.handle, buf, len(handles))
+
+
+B200Context.peer_export = _peer_export
+B200Context.peer_import = _peer_import
+
+
 def _ctx(ctx):
     return ctx if ctx is not None else B200Context.default()
 

@@ -43,6 +43,7 @@ void rls_set_error(const char* fmt, ...);
 // ------------------------------------------------------------------------------------
 // host-side handle structs
 // ------------------------------------------------------------------------------------
+constexpr int RLS_MAX_PEERS = 16;          // ranks of the one-shot NVLink all-reduce (one box)
 constexpr int RLS_MAX_RED_BLOCKS = 4096;  // upper bound on grid size of reducing kernels
 constexpr int RLS_MAX_ACC = 8;            // accumulators per reducing kernel
 
@@ -68,6 +69,12 @@ struct rls_ctx_s {
   // communicator (one rank per process)
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
+  // one-shot all-reduce over NVLink peer memory (rls_p2p.cu): exchange buffers shared through CUDA IPC
+  float* peer_own = nullptr;
+  float* peer_base[RLS_MAX_PEERS] = {};
+  int64_t peer_cap = 0;
+  int* peer_abort = nullptr;
+  bool peer_ready = false;
 };
 
 struct rls_vec_s {
@@ -110,6 +117,10 @@ int32_t rls_ensure_gemv_scratch(rls_ctx_s* ctx, size_t bytes);
 // internal (non-ABI) helpers used across translation units
 int32_t rls_vec_create_internal(rls_ctx_s* ctx, int32_t dtype, int64_t len, rls_vec_s** out);
 int32_t rls_allreduce_raw(rls_ctx_s* ctx, void* buf, int64_t nfloats);  // float sum-allreduce in place
+bool rls_p2p_available(const rls_ctx_s* c, int64_t nfloats);
+int32_t rls_p2p_allreduce(rls_ctx_s* c, const float* src, int64_t sstride, int nsrc, int64_t nf, float* res, const int* gate);
+int32_t rls_p2p_check_abort(rls_ctx_s* c);
+void rls_ctx_peer_release(rls_ctx_s* c);
 int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const int* gate);
 int32_t rls_gemv_n_raw(rls_mat_s* A, const void* x, void* y, const int* gate);
 int32_t rls_gemv_c_raw(rls_mat_s* A, const void* y, void* g, const int* gate);

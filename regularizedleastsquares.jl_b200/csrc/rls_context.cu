@@ -138,6 +138,7 @@ static void* g_nccl_lib = nullptr;
 extern "C" int32_t rls_ctx_destroy(rls_ctx_t c) {
   if (!c) return RLS_OK;
   RlsDeviceGuard g(c->device);
+  rls_ctx_peer_release(c);
   cudaStreamSynchronize(c->stream);
   if (c->nccl_comm && g_nccl_lib) {
     nccl_destroy_fn f = (nccl_destroy_fn)dlsym(g_nccl_lib, "ncclCommDestroy");

@@ -627,7 +627,14 @@ int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const in
   // n-vector over NVLink, then a (gated) copy into res.  A gated-off launch still joins the
   // collective so that ranks stay in lock-step, but never touches res.
   void* out = res;
+  const int64_t nf_all = op->n_ * (op->dtype_ == RLS_C32 ? 2 : 1);
   if (c->nranks > 1) {
+    // one-pass kernel on rows + peer-memory exchange: cluster partials -> (sum, NVLink all-reduce, gated write) in ONE kernel
+    if (op->row && op->form == RLS_NORMAL_ONEPASS && op->A->m > 0 && rls_p2p_available(c, nf_all)) {
+      const float* gp = nullptr; int64_t gs = 0; int ncl = 0;
+      RLS_TRY(rls_rowpass_normal_deferred(op->row, x, nullptr, nullptr, nullptr, gate, &gp, &gs, &ncl));
+      return rls_p2p_allreduce(c, gp, gs, ncl, nf_all, (float*)res, gate);
+    }
     if (!op->gpart) RLS_TRY(rls_vec_create_internal(c, op->dtype_, op->n_, &op->gpart));
     out = op->gpart->d;
   }
@@ -647,7 +654,8 @@ int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const in
       return RLS_ERR_INVALID;
   }
   if (c->nranks > 1) {
-    const int64_t nf = op->n_ * (op->dtype_ == RLS_C32 ? 2 : 1);
+    const int64_t nf = nf_all;
+    if (rls_p2p_available(c, nf)) return rls_p2p_allreduce(c, (const float*)out, 0, 1, nf, (float*)res, gate);
     RLS_TRY(rls_allreduce_raw(c, out, nf));
     gated_copy_kernel<<<c->sm_count, 256, 0, c->stream>>>((float*)res, (const float*)out, nf, gate);
     c->launches++;
@@ -723,6 +731,7 @@ int32_t rls_normal_apply_deferred_raw(rls_normal_t op, const void* x, const floa
 }
 
 int32_t rls_normal_check_abort(rls_normal_t op) {
+  RLS_TRY(rls_p2p_check_abort(op->ctx));
   if (op->row) return rls_rowpass_check_abort(op->row);
   if (op->form != RLS_NORMAL_ONEPASS) return RLS_OK;
   if (op->tma) return rls_tma_check_abort(op->tma);

@@ -21,7 +21,7 @@ def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def init_comm(ctx, rank=None, nranks=None):
+def init_comm(ctx, rank=None, nranks=None, peer_floats=1 << 18):
     """Join this context to the job's NCCL communicator.  Requires torch.distributed to be
     initialised (any backend) for the id exchange."""
     import torch
@@ -33,6 +33,24 @@ def init_comm(ctx, rank=None, nranks=None):
     payload = [ctx.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(payload, src=0)
     ctx.comm_init(rank, nranks, payload[0])
+    if peer_floats and os.environ.get("RLS_P2P", "0") == "1":
+        # exchange buffers of the one-shot NVLink all-reduce (csrc/rls_p2p.cu): CUDA IPC handles through the host
+        # transport; a box without peer access keeps the NCCL path
+        try:
+            mine = ctx.peer_export(peer_floats)
+            handles = [None] * nranks
+            dist.all_gather_object(handles, mine)
+            ctx.peer_import(handles)
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            import warnings
+            warnings.warn(f"peer-memory all-reduce unavailable, using NCCL: {e}")
+        else:
+            ok = 1
+        t = torch.tensor([ok], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t[0]) == 0:
+            os.environ["RLS_P2P"] = "0"   # all ranks must take the same path
     return ctx
 
 
