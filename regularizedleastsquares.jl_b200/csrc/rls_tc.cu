@@ -5,12 +5,11 @@
 // each, and the `A'*A` constructor default (FISTA.jl:58, CGNR.jl:49, ADMM.jl:81) by one GEMM.
 //
 // FP32-accurate split precision on tcgen05 (kind::tf32, FP32 accumulators in TMEM).  The tensor core
-// uses the upper 19 bits of every FP32 operand it is handed, so with
-//     hi(a) = a & 0xffffe000      (what the tensor core sees when it is given a itself)
-//     lo(a) = a - hi(a)           (exact in FP32, |lo| < 2^-10 |a|)
-// the product is accumulated as  hi(A) hi(B) + hi(A) lo(B) + lo(A) hi(B)  — three MMAs per k-step; the
-// dropped lo*lo term and the truncation of lo are O(2^-21) relative.  The hi operand is the raw FP32
-// tile exactly as TMA delivered it; four converter warps write the lo tiles next to it.
+// uses the upper 19 bits of every FP32 operand it is handed.  Four converter warps split every tile TMA delivers,
+//     hi(a) = rn_tf32(a)          (written back over the tile)
+//     lo(a) = rn_tf32(a - hi(a))  (|lo| <= 2^-11 |a|; written next to it)
+// and the product is accumulated as  hi(A) hi(B) + hi(A) lo(B) + lo(A) hi(B)  — three MMAs per k-step; the
+// dropped lo*lo term and the rounding of lo are O(2^-22) relative.
 //
 // Complex data stay interleaved.  With A~ the m x 2n real view of A (row-major: rows contiguous):
 //   mode N:  Y~ (m x 2K)  = A~ (m x 2n) . B,  B rows (2j,2j+1) x cols (2k,2k+1) = [xr xi; -xi xr]
@@ -104,15 +103,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// lo(a) = rn_tf32(a - hi(a)): the difference is exact in FP32; rounding it to TF32 here (to nearest, ties away)
-// instead of leaving it to the tensor core's truncation halves the error of the cross terms and removes its bias
-__device__ __forceinline__ float lo1(float a) {
-  const float d = a - __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+// Split a = hi + lo with BOTH parts rounded to TF32 to nearest (cvt.rna): |lo| <= 2^-11 |a| and the representation
+// error |a - hi - lo| <= 2^-22 |a|, half of what the tensor core's own truncation of a raw FP32 operand would leave
+// (hi = trunc(a), |lo| < 2^-10 |a|).  The price is that hi has to be written back over the tile TMA delivered.
+__device__ __forceinline__ float rna_tf32(float a) {
   uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
   return __uint_as_float(r);
 }
-__device__ __forceinline__ float4 lo_part(float4 v) { return make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w)); }
+__device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
+  hi = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+  lo = make_float4(rna_tf32(v.x - hi.x), rna_tf32(v.y - hi.y), rna_tf32(v.z - hi.z), rna_tf32(v.w - hi.w));
+}
 
 // TMEM -> registers: 32 consecutive FP32 columns of this thread's lane
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -249,10 +251,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     constexpr int n16 = (int)(hi_bytes >> 4);
     for (int kb = 0; kb < p.nkb; ++kb) {
       mbar_wait(&full[s], ph, s_abort, p.abort_flag);
-      const float4* hi = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes);
+      float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
       float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + hi_bytes);
 #pragma unroll 4
-      for (int i = ct; i < n16; i += TC_CONV_THREADS) lo[i] = lo_part(hi[i]);
+      for (int i = ct; i < n16; i += TC_CONV_THREADS) {
+        float4 h, l;
+        split4(hi[i], h, l);
+        hi[i] = h;
+        lo[i] = l;
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
       mbar_arrive(&conv[s]);
       if (++s == NS) { s = 0; ph ^= 1u; }

@@ -328,3 +328,47 @@ def test_multi_rhs_more_columns_than_one_gemm_tile(rls, ctx):
     Xb = rls.solve_(S, B)
     for k in (0, 33, 69):
         assert np.array_equal(Xb[:, k], rls.solve_(S, B[:, k].copy()))
+
+
+# ---------------------------------------------------------------- row-major device layout (one-pass cluster kernel)
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("solver,kw", [("FISTA", dict(restart="none")), ("FISTA", dict(restart="gradient")),
+                                       ("POGM", dict(restart="gradient")), ("OptISTA", {}), ("CGNR", {})])
+def test_row_major_per_iterate(rls, ctx, dtype, solver, kw):
+    """The layout the library chooses for large systems, forced here on a small one: every iterate against the
+    oracle.  FISTA runs in its fused two-kernel form (momentum inside the operator's x load, finish inside the
+    epilogue), the others through the one-pass operator + finish kernel."""
+    A, xt, b = problem(dtype, 384, 1024)
+    Ad = rls.B200Matrix.from_numpy(A, ctx, layout="row")
+    assert Ad.layout == "row"
+    if solver == "CGNR":
+        S = rls.CGNR(Ad, reg=rls.L2Regularization(np.float32(1e-3)), iterations=20, relTol=0.0)
+        R = O.CGNR(A, reg=O.L2Regularization(np.float32(1e-3)), iterations=20, relTol=0.0)
+        stepwise(S, R, b, 20, tol=5e-5)
+        return
+    rho = rho_for(A)
+    lam = np.float32(2e-2)
+    S = getattr(rls, solver)(Ad, reg=rls.L1Regularization(lam), iterations=40, rho=rho, relTol=0.0, **kw)
+    assert S.AHA.form == "onepass" and "rowmajor" in S.AHA.describe()
+    R = getattr(O, solver)(A, reg=O.L1Regularization(lam), iterations=40, rho=rho, relTol=0.0, **kw)
+    stepwise(S, R, b, 40)
+
+
+@pytest.mark.parametrize("regname", ["TV", "L21", "L1+Positive"])
+def test_row_major_fista_split_epilogue_and_projections(rls, ctx, regname, monkeypatch):
+    """non-elementwise prox (the fused FISTA epilogue splits into PART 1 / prox kernels / PART 2) and projections on the
+    fused path; RLS_FUSE_ITERATION=0 (four-kernel chain) must give bit-identical iterates."""
+    dtype = np.complex64
+    A, xt, b = problem(dtype, 256, 32 * 24)
+    Ad = rls.B200Matrix.from_numpy(A, ctx, layout="row")
+    rho = rho_for(A)
+    mk = {"TV": lambda M: M.TVRegularization(np.float32(5e-3), shape=(32, 24)),
+          "L21": lambda M: M.L21Regularization(np.float32(5e-3), slices=8),
+          "L1+Positive": lambda M: [M.L1Regularization(np.float32(1e-2)), M.PositiveRegularization()]}[regname]
+    S = rls.FISTA(Ad, reg=mk(rls), iterations=25, rho=rho, relTol=0.0, restart="gradient")
+    R = O.FISTA(A, reg=mk(O), iterations=25, rho=rho, relTol=0.0, restart="gradient")
+    stepwise(S, R, b, 25, tol=2e-5)
+    x_fused = rls.solve_(S, b)
+    monkeypatch.setenv("RLS_FUSE_ITERATION", "0")
+    x_chain = rls.solve_(S, b)
+    assert np.array_equal(x_fused, x_chain)
