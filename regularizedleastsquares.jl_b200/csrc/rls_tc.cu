@@ -42,6 +42,8 @@ struct TcArgs {
   int stages;
   int tmem_cols;      // power of two >= Npad
   int b_col0_from_y;  // mode T: B tile column origin = blockIdx.y * Npad (Gram), else 0
+  int b_presplit;     // 1: the B operand arrives already split (hi via mapB, lo via mapBlo); the converters touch A only
+  float* Dlo;         // != NULL: write the result split, D = rn_tf32(acc), Dlo = rn_tf32(acc - D) (it is the next GEMM's B)
   float* D;           // output, row-major [Mtot][ldd]
   int64_t ldd;
   int64_t Mtot;       // valid output rows
@@ -137,7 +139,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // the result, so their chain may run over the whole reduction in a third accumulator (its bias is 2^-11 smaller).
 template <int NPAD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
+               TcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle atoms
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -186,15 +189,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int kb = 0; kb < p.nkb; ++kb) {
         mbar_wait(&empty[s], ph ^ 1u, s_abort, p.abort_flag);
         unsigned char* st = smem + (size_t)s * stage_bytes;
-        mbar_expect_tx(&full[s], hi_bytes);
+        mbar_expect_tx(&full[s], hi_bytes + (p.b_presplit ? b_bytes : 0u));
         if (!p.transposed) {
           // K-major tiles: rows = output index, 32 reduction floats per row
           for (int g = 0; g < TC_BM / 32; ++g) tma_load_2d(st + g * TC_BOX_BYTES, &mapA, kb * TC_BK, m0 + 32 * g, &full[s]);
           for (int g = 0; g < ngb; ++g) tma_load_2d(st + a_bytes + g * TC_BOX_BYTES, &mapB, kb * TC_BK, n0 + 32 * g, &full[s]);
+          if (p.b_presplit)
+            for (int g = 0; g < ngb; ++g) tma_load_2d(st + hi_bytes + a_bytes + g * TC_BOX_BYTES, &mapBlo, kb * TC_BK, n0 + 32 * g, &full[s]);
         } else {
           // MN-major tiles: rows = reduction index (32 of them), 32 output floats per row, one box per 32-wide group
           for (int g = 0; g < TC_BM / 32; ++g) tma_load_2d(st + g * TC_BOX_BYTES, &mapA, m0 + 32 * g, kb * TC_BK, &full[s]);
           for (int g = 0; g < ngb; ++g) tma_load_2d(st + a_bytes + g * TC_BOX_BYTES, &mapB, n0 + 32 * g, kb * TC_BK, &full[s]);
+          if (p.b_presplit)
+            for (int g = 0; g < ngb; ++g) tma_load_2d(st + hi_bytes + a_bytes + g * TC_BOX_BYTES, &mapBlo, n0 + 32 * g, kb * TC_BK, &full[s]);
         }
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
@@ -248,7 +255,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int ct = threadIdx.x - 64;  // 0..127
     int s = 0;
     unsigned ph = 0;
-    constexpr int n16 = (int)(hi_bytes >> 4);
+    const int n16 = (int)((p.b_presplit ? a_bytes : hi_bytes) >> 4);  // [A | B] are contiguous: A only when B is pre-split
     for (int kb = 0; kb < p.nkb; ++kb) {
       mbar_wait(&full[s], ph, s_abort, p.abort_flag);
       float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
@@ -298,7 +305,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
       if (row < p.Mtot) {
         const int nv = min(32, p.Nvalid - c0);
-        if (nv == 32 && ((p.ldd | n0) & 3) == 0) {
+        if (p.Dlo) {  // Npad-wide, aligned: the result is the next GEMM's B operand, stored split
+          float* lrow = p.Dlo + row * p.ldd + n0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 h, l;
+            split4(make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]), h, l);
+            *reinterpret_cast<float4*>(drow + c0 + j) = h;
+            *reinterpret_cast<float4*>(lrow + c0 + j) = l;
+          }
+        } else if (nv == 32 && ((p.ldd | n0) & 3) == 0) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(drow + c0 + j) = make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
@@ -324,18 +340,24 @@ constexpr int TC_MAXK = 128;
 struct PtrTable { const void* p[TC_MAXK]; };
 
 // B^T of mode N, [Npad][ldb] floats.  complex: row 2k = conj(x_k), row 2k+1 = i conj(x_k); real: row k = x_k.
-__global__ void tc_pack_x_kernel(const __grid_constant__ PtrTable xs, int K, int fpe, int64_t n, float* __restrict__ BT, int64_t ldb, int Npad) {
+__global__ void tc_pack_x_kernel(const __grid_constant__ PtrTable xs, int K, int fpe, int64_t n, float* __restrict__ BT, float* __restrict__ BTlo,
+                                 int64_t ldb, int Npad) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int rowp = blockIdx.y;  // B^T row
   if (j >= n) return;
   if (fpe == 1) {
-    BT[(int64_t)rowp * ldb + j] = rowp < K ? reinterpret_cast<const float*>(xs.p[rowp])[j] : 0.f;
+    const float v = rowp < K ? reinterpret_cast<const float*>(xs.p[rowp])[j] : 0.f;
+    const float h = rna_tf32(v);
+    BT[(int64_t)rowp * ldb + j] = h;
+    BTlo[(int64_t)rowp * ldb + j] = rna_tf32(v - h);
   } else {
     const int k = rowp >> 1;
     float2 v = make_float2(0.f, 0.f);
     if (k < K) v = reinterpret_cast<const float2*>(xs.p[k])[j];
     const float2 o = (rowp & 1) ? make_float2(v.y, v.x) : make_float2(v.x, -v.y);
-    reinterpret_cast<float2*>(BT + (int64_t)rowp * ldb)[j] = o;
+    const float2 h = make_float2(rna_tf32(o.x), rna_tf32(o.y));
+    reinterpret_cast<float2*>(BT + (int64_t)rowp * ldb)[j] = h;
+    reinterpret_cast<float2*>(BTlo + (int64_t)rowp * ldb)[j] = make_float2(rna_tf32(o.x - h.x), rna_tf32(o.y - h.y));
   }
 }
 // res_k[j] from P [nf][ldp]: complex (P[2j,2k] + P[2j+1,2k+1]) + i (P[2j,2k+1] - P[2j+1,2k]); real P[j,k].  Lane k is
@@ -356,12 +378,15 @@ __global__ void tc_unpack_g_kernel(const float* __restrict__ P, int64_t ldp, int
   }
 }
 // Y~ of mode T from K m-vectors (the batched back-projection A'B of init!): Y~[i][fpe*k + c] = b_k[i*fpe + c]
-__global__ void tc_pack_y_kernel(const __grid_constant__ PtrTable bs, int K, int fpe, int64_t m, float* __restrict__ Y, int Npad) {
+__global__ void tc_pack_y_kernel(const __grid_constant__ PtrTable bs, int K, int fpe, int64_t m, float* __restrict__ Y, float* __restrict__ Ylo, int Npad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
   const int col = threadIdx.x + blockIdx.y * blockDim.x;  // float column of Y~
   if (i >= m || col >= Npad) return;
   const int k = col / fpe, c = col - k * fpe;
-  Y[i * Npad + col] = k < K ? reinterpret_cast<const float*>(bs.p[k])[i * fpe + c] : 0.f;
+  const float v = k < K ? reinterpret_cast<const float*>(bs.p[k])[i * fpe + c] : 0.f;
+  const float h = rna_tf32(v);
+  Y[i * Npad + col] = h;
+  Ylo[i * Npad + col] = rna_tf32(v - h);
 }
 // Gram epilogue: G (n x n, column-major) from P = A~^T A~ (nf x ldp).  complex: G[j,j'] = conj-combined 2x2 block.
 __global__ void tc_gram_finish_kernel(const float* __restrict__ P, int64_t ldp, int fpe, int64_t n, float* __restrict__ G, int64_t ldg) {
@@ -412,7 +437,7 @@ size_t tc_smem(int stages, int Npad) {
   return (size_t)stages * stage + (size_t)(3 * stages + 5) * 8 + 16 + 1024;
 }
 
-int32_t tc_launch(rls_ctx_s* c, const CUtensorMap& mapA, const CUtensorMap& mapB, TcArgs a, int grid_x, int grid_y) {
+int32_t tc_launch(rls_ctx_s* c, const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBlo, TcArgs a, int grid_x, int grid_y) {
   int dev_max = 0;
   cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
   int stages = 6;
@@ -420,11 +445,11 @@ int32_t tc_launch(rls_ctx_s* c, const CUtensorMap& mapA, const CUtensorMap& mapB
   a.stages = stages;
   const size_t smem = tc_smem(stages, a.Npad);
   a.tmem_cols = pow2_cols(3 * a.Npad);
-  void (*fn)(const CUtensorMap, const CUtensorMap, TcArgs) =
+  void (*fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, TcArgs) =
       a.Npad == 32 ? tc_gemm_kernel<32> : a.Npad == 64 ? tc_gemm_kernel<64> : a.Npad == 96 ? tc_gemm_kernel<96> : tc_gemm_kernel<128>;
   RLS_CHECK_ARG(a.Npad == 32 || a.Npad == 64 || a.Npad == 96 || a.Npad == 128, "tensor-core GEMM: N tile %d not in {32,64,96,128}", a.Npad);
   RLS_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fn<<<dim3(grid_x, grid_y), TC_THREADS, smem, c->stream>>>(mapA, mapB, a);
+  fn<<<dim3(grid_x, grid_y), TC_THREADS, smem, c->stream>>>(mapA, mapB, mapBlo, a);
   c->launches++;
   RLS_CUDA(cudaGetLastError());
   return RLS_OK;
@@ -440,16 +465,18 @@ struct TcBatchPlan {
   rls_mat_s* A = nullptr;
   int K = 0, fpe = 1, Npad = 0;
   int64_t nf = 0, ldx = 0;
-  float* XT = nullptr;    // [Npad][ldx]   B^T of mode N
-  float* Y = nullptr;     // [m][Npad]     Y~
+  float* XT = nullptr;    // [Npad][ldx]   B^T of mode N, TF32 hi part
+  float* XTlo = nullptr;  //               ... lo part
+  float* Y = nullptr;     // [m][Npad]     Y~, hi part (written split by mode N's epilogue / tc_pack_y_kernel)
+  float* Ylo = nullptr;   //               ... lo part
   float* P = nullptr;     // [nf][Npad]    A~^T Y~
   int* abort_flag = nullptr;
-  CUtensorMap mapA, mapAt, mapXT, mapY;  // mapAt: A described for the transposed (MN-major) use
+  CUtensorMap mapA, mapAt, mapXT, mapXTlo, mapY, mapYlo;  // mapAt: A described for the transposed (MN-major) use
 };
 
 void rls_tc_batch_destroy(TcBatchPlan* p) {
   if (!p) return;
-  cudaFree(p->XT); cudaFree(p->Y); cudaFree(p->P);
+  cudaFree(p->XT); cudaFree(p->XTlo); cudaFree(p->Y); cudaFree(p->Ylo); cudaFree(p->P);
   cudaFree(p->abort_flag);
   delete p;
 }
@@ -476,8 +503,9 @@ int32_t rls_tc_batch_create(rls_mat_s* A, int K, TcBatchPlan** out) {
   p->nf = A->n * p->fpe;
   p->Npad = ((K * p->fpe + 31) / 32) * 32;
   p->ldx = (p->nf + 3) & ~(int64_t)3;
-  bool ok = cudaMalloc(&p->XT, (size_t)p->Npad * p->ldx * 4) == cudaSuccess &&
+  bool ok = cudaMalloc(&p->XT, (size_t)p->Npad * p->ldx * 4) == cudaSuccess && cudaMalloc(&p->XTlo, (size_t)p->Npad * p->ldx * 4) == cudaSuccess &&
             cudaMalloc(&p->Y, (size_t)std::max<int64_t>(A->m, 1) * p->Npad * 4) == cudaSuccess &&
+            cudaMalloc(&p->Ylo, (size_t)std::max<int64_t>(A->m, 1) * p->Npad * 4) == cudaSuccess &&
             cudaMalloc(&p->P, (size_t)p->nf * p->Npad * 4) == cudaSuccess &&
             cudaMalloc(&p->abort_flag, 4) == cudaSuccess;
   if (!ok) { cudaGetLastError(); rls_tc_batch_destroy(p); rls_set_error("tensor-core batch path: out of device memory"); return RLS_ERR_NOMEM; }
@@ -485,7 +513,9 @@ int32_t rls_tc_batch_create(rls_mat_s* A, int K, TcBatchPlan** out) {
   int32_t s = make_map(&p->mapA, (const float*)A->d, A->m, p->nf, A->ld * p->fpe, false);
   if (s == RLS_OK) s = make_map(&p->mapAt, (const float*)A->d, A->m, p->nf, A->ld * p->fpe, true);
   if (s == RLS_OK) s = make_map(&p->mapXT, p->XT, p->Npad, p->nf, p->ldx, false);
+  if (s == RLS_OK) s = make_map(&p->mapXTlo, p->XTlo, p->Npad, p->nf, p->ldx, false);
   if (s == RLS_OK) s = make_map(&p->mapY, p->Y, A->m, p->Npad, p->Npad, true);
+  if (s == RLS_OK) s = make_map(&p->mapYlo, p->Ylo, A->m, p->Npad, p->Npad, true);
   if (s != RLS_OK) { rls_tc_batch_destroy(p); return s; }
   *out = p;
   return RLS_OK;
@@ -504,19 +534,20 @@ int32_t rls_tc_batch_apply(TcBatchPlan* p, const void* const* xs, void* const* o
   for (int k = 0; k < K; ++k) { tx.p[k] = xs[k]; to.p[k] = outs[k]; tg.p[k] = gates ? gates[k] : nullptr; }
   {
     dim3 grid((unsigned)((A->n + 255) / 256), (unsigned)p->Npad);
-    tc_pack_x_kernel<<<grid, 256, 0, c->stream>>>(tx, K, p->fpe, A->n, p->XT, p->ldx, p->Npad);
+    tc_pack_x_kernel<<<grid, 256, 0, c->stream>>>(tx, K, p->fpe, A->n, p->XT, p->XTlo, p->ldx, p->Npad);
     c->launches++;
   }
   TcArgs a{};
   a.Npad = p->Npad; a.b_col0_from_y = 0; a.abort_flag = p->abort_flag;
   // mode N: Y~ = A~ . B
   a.transposed = 0; a.nkb = (int)((p->nf + TC_BK - 1) / TC_BK);
-  a.D = p->Y; a.ldd = p->Npad; a.Mtot = A->m; a.Nvalid = p->Npad; a.Ntot = p->Npad;
-  RLS_TRY(tc_launch(c, p->mapA, p->mapXT, a, (int)((A->m + TC_BM - 1) / TC_BM), 1));
+  a.b_presplit = 1;
+  a.D = p->Y; a.Dlo = p->Ylo; a.ldd = p->Npad; a.Mtot = A->m; a.Nvalid = p->Npad; a.Ntot = p->Npad;
+  RLS_TRY(tc_launch(c, p->mapA, p->mapXT, p->mapXTlo, a, (int)((A->m + TC_BM - 1) / TC_BM), 1));
   // mode T: P = A~^T . Y~
   a.transposed = 1; a.nkb = (int)((A->m + TC_BK - 1) / TC_BK);
-  a.D = p->P; a.ldd = p->Npad; a.Mtot = p->nf;
-  RLS_TRY(tc_launch(c, p->mapAt, p->mapY, a, (int)((p->nf + TC_BM - 1) / TC_BM), 1));
+  a.D = p->P; a.Dlo = nullptr; a.ldd = p->Npad; a.Mtot = p->nf;
+  RLS_TRY(tc_launch(c, p->mapAt, p->mapY, p->mapYlo, a, (int)((p->nf + TC_BM - 1) / TC_BM), 1));
   if (c->nranks > 1) RLS_TRY(rls_allreduce_raw(c, p->P, p->nf * p->Npad));
   {
     dim3 block(32, 8);
@@ -542,14 +573,15 @@ int32_t rls_tc_batch_adjoint(TcBatchPlan* p, const void* const* bs, void* const*
   {
     dim3 block(32, 8);
     dim3 grid((unsigned)((A->m + 7) / 8), (unsigned)((p->Npad + 31) / 32));
-    tc_pack_y_kernel<<<grid, block, 0, c->stream>>>(tb, K, p->fpe, A->m, p->Y, p->Npad);
+    tc_pack_y_kernel<<<grid, block, 0, c->stream>>>(tb, K, p->fpe, A->m, p->Y, p->Ylo, p->Npad);
     c->launches++;
   }
   TcArgs a{};
   a.Npad = p->Npad; a.b_col0_from_y = 0; a.abort_flag = p->abort_flag;
   a.transposed = 1; a.nkb = (int)((A->m + TC_BK - 1) / TC_BK);
+  a.b_presplit = 1;
   a.D = p->P; a.ldd = p->Npad; a.Mtot = p->nf; a.Nvalid = p->Npad; a.Ntot = p->Npad;
-  RLS_TRY(tc_launch(c, p->mapAt, p->mapY, a, (int)((p->nf + TC_BM - 1) / TC_BM), 1));
+  RLS_TRY(tc_launch(c, p->mapAt, p->mapY, p->mapYlo, a, (int)((p->nf + TC_BM - 1) / TC_BM), 1));
   if (c->nranks > 1) RLS_TRY(rls_allreduce_raw(c, p->P, p->nf * p->Npad));
   {
     dim3 block(32, 8);
@@ -612,7 +644,7 @@ int32_t rls_tc_gram(rls_mat_s* A, rls_mat_s* G) {
     a.transposed = 1; a.Npad = Npad; a.b_col0_from_y = 1; a.abort_flag = abort_flag;
     a.nkb = (int)((A->m + TC_BK - 1) / TC_BK);
     a.D = P; a.ldd = ldp; a.Mtot = nf; a.Nvalid = Npad; a.Ntot = ldp;
-    s = tc_launch(c, mapA, mapA, a, (int)((nf + TC_BM - 1) / TC_BM), (int)(ldp / Npad));
+    s = tc_launch(c, mapA, mapA, mapA, a, (int)((nf + TC_BM - 1) / TC_BM), (int)(ldp / Npad));
   }
   if (s == RLS_OK) {
     dim3 block(32, 8);
