@@ -128,6 +128,63 @@ __global__ void __launch_bounds__(EB) fista_main_kernel(T* __restrict__ x, T* __
   grid_reduce_finalize<2, EB>(acc, partials, ticket, [=](double* t) { scalar_step(S, step, 0, t); });
 }
 
+// ---- multi-RHS: the K per-column pre / post kernels of one batched FISTA iteration as ONE launch each --------
+// blockIdx.y = column (lane); pointers travel as kernel parameters; every lane keeps its own done() gate, its own
+// reduction slots (partials + lane*stride) and its own ticket, so each column's arithmetic — and therefore its
+// iterates — are exactly those of the per-column kernels above.
+constexpr int BATCH_MAXK = 128;
+template <typename T>
+struct FistaLanes {
+  T* x[BATCH_MAXK];
+  T* res[BATCH_MAXK];
+  const T* x0[BATCH_MAXK];
+  const T* xold[BATCH_MAXK];
+  DevState* S[BATCH_MAXK];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(EB) fista_momentum_batch_kernel(const __grid_constant__ FistaLanes<T> L, int64_t n) {
+  pdl_prologue();
+  const int k = blockIdx.y;
+  const DevState* S = L.S[k];
+  if (S->done) return;
+  T* __restrict__ x = L.x[k];
+  const T* __restrict__ xold = L.xold[k];
+  const float c1 = fdiv(fsub(1.f, S->theta_old), S->theta);
+  const float c2 = fadd(fdiv(fsub(S->theta_old, 1.f), S->theta), 1.f);
+  EW_LOOP(i, n) x[i] = Elem<T>::add(Elem<T>::scale(x[i], c1), Elem<T>::scale(xold[i], c2));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EB) fista_main_batch_kernel(const __grid_constant__ FistaLanes<T> L, int64_t n, int reg_kind, double* partials,
+                                                               int64_t pstride, unsigned* tickets) {
+  pdl_prologue();
+  const int k = blockIdx.y;
+  DevState* S = L.S[k];
+  if (S->done) return;
+  T* __restrict__ x = L.x[k];
+  T* __restrict__ res = L.res[k];
+  const T* __restrict__ x0 = L.x0[k];
+  const T* __restrict__ xold = L.xold[k];
+  const float rho = S->rho, thr = thr_from(S, 0, S->rho);
+  const int proj = S->proj_mask, restart = S->restart;
+  double acc[2] = {0.0, 0.0};
+  EW_LOOP(i, n) {
+    const T r = Elem<T>::sub(res[i], x0[i]);
+    res[i] = r;
+    T xv = Elem<T>::sub(x[i], Elem<T>::scale(r, rho));
+    acc[0] += Elem<T>::abs2(r);
+    xv = prox_elementwise(xv, reg_kind, thr);
+    if (proj) xv = proj_elem(xv, proj);
+    x[i] = xv;
+    if (restart) {
+      double im = 0.0;
+      Elem<T>::dotc(r, Elem<T>::sub(xv, xold[i]), acc[1], im);
+    }
+  }
+  grid_reduce_finalize<2, EB>(acc, partials + (size_t)k * pstride, tickets + k, [=](double* t) { scalar_step(S, STEP_FISTA_POST, 0, t); });
+}
+
 // ================================ POGM ===============================================
 // bufX holds x on entry and y on exit; bufY holds y on entry and x on exit (the host swaps roles).
 template <typename T, int PART>
@@ -1150,6 +1207,38 @@ extern "C" int32_t rls_solver_vec(rls_solver_t s, const char* name, rls_vec_t* o
   return RLS_ERR_INVALID;
 }
 
+// FISTA with an elementwise prox: the K momentum kernels and the K epilogues of a batched iteration are one launch
+// each (fista_*_batch_kernel); everything else keeps the per-column kernels
+static bool fista_batched_kernels(rls_solver_s* s, int K) {
+  const char* off = getenv("RLS_BATCH_LANE_KERNELS");
+  if (off && atoi(off) == 0) return false;
+  if (s->desc.kind != RLS_FISTA || !rls_reg_is_elementwise(s->desc.reg[0].kind) || K > BATCH_MAXK || K > 4096) return false;
+  const int g = ew_grid(s->ctx, s->n);
+  return (int64_t)K * g * 2 <= (int64_t)RLS_MAX_RED_BLOCKS * RLS_MAX_ACC;
+}
+
+template <typename T>
+static int32_t fista_batch_iteration(rls_solver_s* s, int K) {
+  rls_ctx_s* c = s->ctx;
+  cudaStream_t st = c->stream;
+  const int g = ew_grid(c, s->n);
+  FistaLanes<T> tab{};
+  for (int k = 0; k < K; ++k) {
+    Lane& L = s->lanes[k];
+    swap_roles(s, L); L.enq_swaps++;
+    tab.x[k] = P<T>(L.v[V_X]); tab.res[k] = P<T>(L.v[V_RES]); tab.x0[k] = P<T>(L.v[V_X0]); tab.xold[k] = P<T>(L.v[V_XOLD]);
+    tab.S[k] = L.dS;
+    s->batch_x.push_back(L.v[V_X]->d); s->batch_res.push_back(L.v[V_RES]->d); s->batch_gate.push_back(&L.dS->done);
+  }
+  fista_momentum_batch_kernel<T><<<dim3(g, K), EB, 0, st>>>(tab, s->n);
+  c->launches++;
+  RLS_TRY(rls_normal_apply_batch_raw(s->AHA, K, s->batch_x.data(), s->batch_res.data(), s->batch_gate.data()));
+  fista_main_batch_kernel<T><<<dim3(g, K), EB, 0, st>>>(tab, s->n, s->desc.reg[0].kind, c->red_partials, (int64_t)g * 2, c->gemv_tickets);
+  c->launches++;
+  RLS_CUDA(cudaGetLastError());
+  return RLS_OK;
+}
+
 // multi-RHS: K lanes sharing A / AHA / reg, per-column device-side done() masks
 // (MultiThreading.jl:30-80).  Iterations are interleaved lane by lane on the stream.
 extern "C" int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_host, int64_t ldb, int32_t K, void* X_host,
@@ -1204,6 +1293,10 @@ extern "C" int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_hos
         continue;
       }
       s->batch_x.clear(); s->batch_res.clear(); s->batch_gate.clear();
+      if (fista_batched_kernels(s, K)) {
+        status = s->dtype == RLS_C32 ? fista_batch_iteration<float2>(s, K) : fista_batch_iteration<float>(s, K);
+        continue;
+      }
       for (int k = 0; k < K && status == RLS_OK; ++k) status = enqueue_iteration(s, s->lanes[k], IT_PRE);
       if (status == RLS_OK) status = rls_normal_apply_batch_raw(s->AHA, K, s->batch_x.data(), s->batch_res.data(), s->batch_gate.data());
       for (int k = 0; k < K && status == RLS_OK; ++k) status = enqueue_iteration(s, s->lanes[k], IT_POST);
