@@ -113,6 +113,9 @@ struct RlsDeviceGuard {
 };
 
 int32_t rls_ensure_gemv_scratch(rls_ctx_s* ctx, size_t bytes);
+// diagnostic switches read from the environment (re-read on every call: tests flip them between solves; a getenv
+// costs ~100 ns against >= 0.3 ms per normal-operator apply)
+bool rls_env_flag(const char* name, bool dflt);
 
 // internal (non-ABI) helpers used across translation units
 int32_t rls_vec_create_internal(rls_ctx_s* ctx, int32_t dtype, int64_t len, rls_vec_s** out);

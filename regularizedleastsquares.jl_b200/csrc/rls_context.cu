@@ -80,6 +80,11 @@ void rls_trace_dump() {
   g_trace.clear();
 }
 
+bool rls_env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) != 0 : dflt;
+}
+
 bool rls_pdl_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("RLS_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }

@@ -667,8 +667,7 @@ int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const in
 // res_k = AHA x_k for K right-hand sides.  Lazy forms on a row-major A: two tensor-core GEMMs that read A once
 // each (rls_tc.cu); otherwise K single applies.
 int32_t rls_normal_apply_batch_raw(rls_normal_t op, int K, const void* const* xs, void* const* outs, const int* const* gates) {
-  const char* off = getenv("RLS_BATCH_TENSOR_CORES");
-  const bool want = !(off && atoi(off) == 0);
+  const bool want = rls_env_flag("RLS_BATCH_TENSOR_CORES", true);
   if (want && op->form != RLS_NORMAL_GRAM && op->A && rls_tc_batch_supported(op->A, K)) {
     if (op->tc && op->tc_K != K) { rls_tc_batch_destroy(op->tc); op->tc = nullptr; }
     if (!op->tc) {
@@ -686,8 +685,7 @@ int32_t rls_normal_apply_batch_raw(rls_normal_t op, int K, const void* const* xs
 // *done = false leaves the back-projections to the caller (per-column gemv_c)
 int32_t rls_normal_adjoint_batch_raw(rls_normal_t op, int K, const void* const* bs, void* const* outs, bool* done) {
   *done = false;
-  const char* off = getenv("RLS_BATCH_TENSOR_CORES");
-  if ((off && atoi(off) == 0) || op->form == RLS_NORMAL_GRAM || !op->A || !rls_tc_batch_supported(op->A, K)) return RLS_OK;
+  if (!rls_env_flag("RLS_BATCH_TENSOR_CORES", true) || op->form == RLS_NORMAL_GRAM || !op->A || !rls_tc_batch_supported(op->A, K)) return RLS_OK;
   if (op->tc && op->tc_K != K) { rls_tc_batch_destroy(op->tc); op->tc = nullptr; }
   if (!op->tc) {
     if (rls_tc_batch_create(op->A, K, &op->tc) != RLS_OK) { op->tc = nullptr; return RLS_OK; }
@@ -724,8 +722,7 @@ extern "C" int32_t rls_normal_batch_debug(rls_normal_t op, int32_t which, float*
 int32_t rls_normal_apply_deferred_raw(rls_normal_t op, const void* x, const float* xold, const float* th_old, const float* th,
                                       const int* gate, NormalPartials* np) {
   np->gpart = nullptr; np->gstride = 0; np->ncl = 0;
-  const char* off = getenv("RLS_FUSE_ITERATION");
-  if ((off && atoi(off) == 0) || !op->row || op->form != RLS_NORMAL_ONEPASS || op->ctx->nranks > 1 || !op->A || op->A->m == 0 || op->A->n == 0)
+  if (!rls_env_flag("RLS_FUSE_ITERATION", true) || !op->row || op->form != RLS_NORMAL_ONEPASS || op->ctx->nranks > 1 || !op->A || op->A->m == 0 || op->A->n == 0)
     return RLS_OK;
   return rls_rowpass_normal_deferred(op->row, x, xold, th_old, th, gate, &np->gpart, &np->gstride, &np->ncl);
 }

@@ -161,8 +161,7 @@ void rls_ctx_peer_release(rls_ctx_s* c) {
 // 256 KB vector (NVLS, in-switch reduction) is ~1 % faster per iteration than this one-shot kernel, so NCCL stays
 // the default exchange.
 bool rls_p2p_available(const rls_ctx_s* c, int64_t nfloats) {
-  const char* on = getenv("RLS_P2P");
-  return c->peer_ready && c->nranks > 1 && nfloats <= c->peer_cap && on && atoi(on) != 0;
+  return c->peer_ready && c->nranks > 1 && nfloats <= c->peer_cap && rls_env_flag("RLS_P2P", false);
 }
 
 // res = sum over ranks of (sum over the nsrc partial vectors src + k*sstride); float counts, nf <= peer_cap

@@ -1210,8 +1210,7 @@ extern "C" int32_t rls_solver_vec(rls_solver_t s, const char* name, rls_vec_t* o
 // FISTA with an elementwise prox: the K momentum kernels and the K epilogues of a batched iteration are one launch
 // each (fista_*_batch_kernel); everything else keeps the per-column kernels
 static bool fista_batched_kernels(rls_solver_s* s, int K) {
-  const char* off = getenv("RLS_BATCH_LANE_KERNELS");
-  if (off && atoi(off) == 0) return false;
+  if (!rls_env_flag("RLS_BATCH_LANE_KERNELS", true)) return false;
   if (s->desc.kind != RLS_FISTA || !rls_reg_is_elementwise(s->desc.reg[0].kind) || K > BATCH_MAXK || K > 4096) return false;
   const int g = ew_grid(s->ctx, s->n);
   return (int64_t)K * g * 2 <= (int64_t)RLS_MAX_RED_BLOCKS * RLS_MAX_ACC;
