@@ -248,11 +248,13 @@ def run_b200(args):
                        "in_step_gbs": alg_bytes * ITERS * args.steps / (ms * 1e-3) / 1e9},
             "e2e": {"value": e2e_its * world, "unit": "iterations/s", "h2d_bytes_per_step": int(b_host.nbytes),
                     "d2h_bytes_per_step": int(x_host.nbytes)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
                          "traffic": traffic, "kernel": f"normal operator A'(A x) [{AHA.describe()}]",
                          "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "matrix_layout": A.layout,
-                         "note": "one launch = one normal-operator apply, scored against a single read of A (m*n*4 B); "
+                         "ms_per_iteration_in_solve": ms / args.steps / ITERS,
+                         "note": "one launch = one normal-operator apply, scored against a single read of A (m*n*4 B); timed right "
+                                 "after the solves, i.e. at the clocks the power cap allows under sustained load (cold: 0.59 ms); "
                                  "onepass/rowmajor = cluster kernel that sweeps A once (+ a tiny partial-sum kernel); "
                                  "twopass = gemv_n + gemv_c, two sweeps"},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -391,7 +391,10 @@ rowpass_fn pick_v(int V, int R, int mode, bool full) {
     case 4: return pick_r<FPE, 4>(R, mode, full);
     // wide slices (cluster sizes that are not powers of two, e.g. 6 CTAs x 10924 floats): two rows per round
     case 5: return pick_mode<FPE, 5, 2, false>(mode);
-    default: return pick_mode<FPE, 6, 2, false>(mode);
+    case 6: return pick_mode<FPE, 6, 2, false>(mode);
+    // 16384-float slices: one row per round (a, x and g at 32 registers each), half the cluster size
+    case 7: return pick_mode<FPE, 7, 1, false>(mode);
+    default: return full ? pick_mode<FPE, 8, 1, true>(mode) : pick_mode<FPE, 8, 1, false>(mode);
   }
 }
 
@@ -447,17 +450,18 @@ int32_t rls_rowpass_plan_create(rls_ctx_s* c, rls_mat_s* A, RowPlan** out) {
     // cluster sizes need not be powers of two: what counts is how many SMs the co-resident clusters cover
     // (GPCs of 20/18/14 SMs: 8 -> 120 SMs, 6 -> 138, 4 -> 132, 2 and 1 -> 148) against the slice width
     const int g_env = env_int("RLS_ROWPASS_G", 0);
-    if (g_env > 0 && (int64_t)g_env * 6 * 2048 >= nf_pad) G = g_env;
+    if (g_env > 0 && (int64_t)g_env * 8 * 2048 >= nf_pad) G = g_env;
   }
   if (G > RP_MAXG) G = RP_MAXG;
   int W = (int)(((nf_pad + G - 1) / G + 3) & ~(int64_t)3);
   if (W < 4) W = 4;
   int V = (W + 2047) / 2048;
-  if (V > 6) { rls_set_error("rowpass: slice of %d floats too wide", W); rls_rowpass_plan_destroy(p); return RLS_ERR_UNSUPPORTED; }
+  if (V > 8) { rls_set_error("rowpass: slice of %d floats too wide", W); rls_rowpass_plan_destroy(p); return RLS_ERR_UNSUPPORTED; }
   int R = env_int("RLS_ROWPASS_R", fpe == 2 ? 3 : 4);  // measured on B200 (profiles/r01_rowpass_sweep.txt)
-  if (R < 2) R = 2;
+  if (R < 1) R = 1;
   if (R > RP_MAXR) R = RP_MAXR;
   if (V > 4) R = 2;
+  if (V > 6) R = 1;
   p->G = G; p->W = W; p->V = V; p->R = R;
   // every CTA's slice is exactly V*2048 floats: no column predicates in the kernel
   const bool full = (W == V * 4 * RP_CT) && ((int64_t)G * W == nf_pad);

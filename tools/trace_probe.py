@@ -3,7 +3,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rls_b200 as rls
 capi = rls._capi
-m, n = 16384, 65536
+m, n = int(os.environ.get("M", "16384")), int(os.environ.get("N", "65536"))
 ctx = rls.B200Context.default(0)
 A = rls.B200Matrix.philox(np.float32, m, n, seed=1, scale=1.0 / np.sqrt(m), ctx=ctx, layout="row")
 b = rls.B200Vector(ctx, np.float32, m).fill_philox(3, stream=1, dist=1)
