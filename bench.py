@@ -254,7 +254,8 @@ def run_b200(args):
                          "matrix_layout": A.layout,
                          "ms_per_iteration_in_solve": ms / args.steps / ITERS,
                          "note": "one launch = one normal-operator apply, scored against a single read of A (m*n*4 B); timed right "
-                                 "after the solves, i.e. at the clocks the power cap allows under sustained load (cold: 0.59 ms); "
+                                 "after the solves, i.e. at the clocks the power cap allows under sustained load (the cluster kernel on 120 "
+                                 "SMs is clock-sensitive: 0.58-0.60 ms at 1.9 GHz, up to 0.68 ms at 1.7 GHz); "
                                  "onepass/rowmajor = cluster kernel that sweeps A once (+ a tiny partial-sum kernel); "
                                  "twopass = gemv_n + gemv_c, two sweeps"},
             "gpu_launches": int(launches), "clocks": clocks,
