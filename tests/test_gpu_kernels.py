@@ -252,3 +252,27 @@ def test_gram_on_tensor_cores(rls, ctx, dtype, shape, monkeypatch):
     op2 = rls.B200NormalOp(Ad, form="gram")
     assert "tensor cores" not in op2.describe()
     assert rel(op2.apply(rls.B200Vector.from_numpy(x, ctx)).to_numpy(), g) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("shape", [(0, 5), (5, 0), (0, 0), (1, 1), (2, 3)])
+def test_degenerate_shapes(rls, ctx, dtype, layout, shape):
+    """empty and tiny systems: A x of an m = 0 system is empty, A'(A x) is the zero vector, nothing hangs"""
+    m, n = shape
+    A = np.zeros((m, n), dtype)
+    if m and n:
+        A, _ = rand_matrix(dtype, m, n, 5)
+    Ad = rls.B200Matrix.from_numpy(A, ctx, layout=layout)
+    assert Ad.to_numpy().shape == (m, n)
+    x = rand_vector(dtype, n, 6) if n else np.zeros(0, dtype)
+    y = rand_vector(dtype, m, 7) if m else np.zeros(0, dtype)
+    xd, yd = rls.B200Vector.from_numpy(x, ctx), rls.B200Vector.from_numpy(y, ctx)
+    A64 = A.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
+    assert np.allclose(Ad.mul(xd).to_numpy(), A64 @ x, atol=1e-5)
+    assert np.allclose(Ad.adjoint_mul(yd).to_numpy(), A64.conj().T @ y, atol=1e-5)
+    for form in ("twopass", "onepass"):
+        if n == 0:
+            continue
+        g = rls.B200NormalOp(Ad, form=form).apply(xd).to_numpy()
+        assert np.allclose(g, A64.conj().T @ (A64 @ x), atol=1e-5), form
