@@ -26,7 +26,7 @@ __all__ = [
     "PositiveRegularization", "RealRegularization", "NormalizedRegularization",
     "NoNormalization", "MeasurementBasedNormalization", "SystemMatrixBasedNormalization",
     "prox_", "reg_norm", "lam_of", "grad_op", "grad_op_t", "grad_t_axpy", "grad_rows", "cg", "power_iterations",
-    "NormalOp", "FISTA", "CGNR", "POGM", "OptISTA", "ADMM", "GradientOp",
+    "NormalOp", "FISTA", "CGNR", "POGM", "OptISTA", "ADMM", "SplitBregman", "GradientOp",
     "createLinearSolver", "solve_", "normalize_factor", "enf_real", "enf_pos",
 ]
 
@@ -935,6 +935,133 @@ class ADMM(_Base):
                     self.rho_state[i] /= 2
                     self.u[i] *= 2
         self.iteration += 1
+        return True
+
+    def convergence(self):
+        return {"primal": self.rk.copy(), "dual": self.sk.copy()}
+
+
+class SplitBregman(_Base):
+    """src/SplitBregman.jl:80-290 (precon = Identity only).  Constrained split Bregman: `iterations` outer
+    (Bregman) iterations of at most `iterationsInner` ADMM-like inner iterations each; `state.iteration` counts
+    inner iterations from 1 and is reset at every outer update (:258-268)."""
+    def __init__(self, A, *, AHA=None, reg=None, regTrafo=None, normalizeReg=None, rho=1e-1, iterations=10,
+                 iterationsInner=10, iterationsCG=10, absTol=None, relTol=None, tolInner=1e-5, verbose=False,
+                 normal="lazy"):
+        self.A = A
+        self.AHA = _make_normal(A, AHA, normal)
+        self.T = np.dtype(self.AHA.dtype)
+        rT = self.rT = real_type(self.T)
+        self.normalizeReg = NoNormalization() if normalizeReg is None else normalizeReg
+        if reg is None:
+            reg = L1Regularization(rT(0))
+        regs, self.proj = _split_regs(reg, "SplitBregman", exactly_one=False)
+        n = self.AHA.n
+        if regTrafo is None:
+            trafo = [_Eye(n) for _ in regs]
+        else:
+            trafo = list(regTrafo) if isinstance(regTrafo, (list, tuple)) else [regTrafo]
+            trafo = [_Eye(n) if t is None else t for t in trafo]
+        assert len(regs) == len(trafo), "reg and regTrafo must have the same length"   # :108
+        self.regTrafo = trafo
+        if np.isscalar(rho):
+            self.rho = np.array([rT(rho) for _ in regs], dtype=rT)                    # :110-114
+        else:
+            self.rho = np.asarray(rho, dtype=rT).copy()
+        f = normalize_factor(self.normalizeReg, A, None)                               # :140
+        self.reg = [_normalize_reg(r, f) for r in regs]
+        self.iterations = int(iterations); self.iterationsInner = int(iterationsInner); self.iterationsCG = int(iterationsCG)
+        eps = np.finfo(rT).eps
+        self.absTol = rT(eps if absTol is None else absTol)
+        self.relTol = rT(eps if relTol is None else relTol)
+        self.tolInner = rT(tolInner)
+        self.verbose = verbose
+        self.x = np.zeros(n, self.T)
+        self.iteration = 1; self.iter_cnt = 1
+        self.total_iterations = 0
+        self.cg_iters = []
+
+    def init(self, b, x0=0):
+        rT = self.rT; n = self.AHA.n; k = len(self.reg)
+        self.x = np.zeros(n, self.T); self.x[...] = x0                      # :171
+        self.beta_y = self._adjoint_b(b)                                   # :174-178
+        self.y = self.beta_y.copy()                                        # :179
+        self.z = [np.asarray(self.regTrafo[i].mul(self.x), dtype=self.T) for i in range(k)]   # :183
+        self.u = [np.zeros_like(self.z[i]) for i in range(k)]
+        self.zold = [np.zeros_like(self.z[i]) for i in range(k)]
+        self.rk = np.full(k, np.inf, rT); self.sk = np.full(k, np.inf, rT)
+        self.eps_pri = np.zeros(k, rT); self.eps_dua = np.zeros(k, rT)
+        self.sigma_abs = rT(np.sqrt(rT(len(b))) * self.absTol)              # :192
+        if isinstance(self.normalizeReg, MeasurementBasedNormalization):   # :195
+            f = normalize_factor(self.normalizeReg, self.A, b)
+            self.reg = [_normalize_reg(r, f) for r in self.reg]
+        self.iter_cnt = 1                                                  # :198-199
+        self.iteration = 1
+        self.total_iterations = 0
+        self.cg_iters = []
+
+    def converged(self):                                                   # :281-287
+        for i in range(len(self.reg)):
+            if self.rk[i] >= self.sigma_abs + self.relTol * self.eps_pri[i]:
+                return False
+            if self.sk[i] >= self.sigma_abs + self.relTol * self.eps_dua[i]:
+                return False
+        return True
+
+    def done(self):                                                        # :289
+        return self.converged() or (self.iteration == 1 and self.iter_cnt > self.iterations)
+
+    def _composite(self, v):
+        res = self.AHA.apply(v).astype(self.T, copy=False)
+        for i, t in enumerate(self.regTrafo):
+            if isinstance(t, _Eye):
+                res = self.rho[i] * v + res
+            else:
+                res = grad_t_axpy(self.rho[i], t.mul(v), t.shape, t.dims, res)
+        return res
+
+    def iterate(self):
+        rT = self.rT
+        if self.done():
+            return False
+        k = len(self.reg)
+        # x update (:209-218)
+        self.beta = self.beta_y.copy()
+        for i in range(k):
+            t = self.regTrafo[i]
+            if isinstance(t, _Eye):
+                self.beta = self.rho[i] * self.z[i] + self.beta
+                self.beta = (-self.rho[i]) * self.u[i] + self.beta
+            else:
+                self.beta = grad_t_axpy(self.rho[i], self.z[i], t.shape, t.dims, self.beta)
+                self.beta = grad_t_axpy(-self.rho[i], self.u[i], t.shape, t.dims, self.beta)
+        self.cg_iters.append(cg(self.x, self._composite, self.beta, self.iterationsCG, self.tolInner))
+        for p in self.proj:                                                # :220-222
+            prox_(p, self.x)
+        for i in range(k):                                                 # :225-254
+            t = self.regTrafo[i]
+            self.zold[i], self.z[i] = self.z[i], self.zold[i]
+            self.z[i][...] = t.mul(self.x)
+            self.z[i] += self.u[i]
+            if self.rho[i] != 0:
+                prox_(self.reg[i], self.z[i], lam_of(self.reg[i]) / self.rho[i])
+            self.u[i][...] = t.mul(self.x) + self.u[i]                     # mul!(u, Φ, x, 1, 1)
+            self.u[i] -= self.z[i]
+            phix = np.asarray(t.mul(self.x), dtype=self.T)
+            self.rk[i] = rT(_norm2(phix - self.z[i]))
+            self.sk[i] = rT(_norm2(self.rho[i] * np.asarray(t.tmul(self.z[i] - self.zold[i]), dtype=self.T)))
+            self.eps_pri[i] = max(rT(_norm2(phix)), rT(_norm2(self.z[i])))
+            self.eps_dua[i] = rT(_norm2(self.rho[i] * np.asarray(t.tmul(self.u[i]), dtype=self.T)))
+        if self.converged() or self.iteration >= self.iterationsInner:     # :257-268
+            self.beta_y += self.y
+            self.beta_y[...] = -self.AHA.apply(self.x).astype(self.T, copy=False) + self.beta_y   # mul!(β_y, AHA, x, -1, 1)
+            for i in range(k):
+                self.z[i][...] = self.regTrafo[i].mul(self.x)
+                self.u[i][...] = 0
+            self.iter_cnt += 1
+            self.iteration = 0
+        self.iteration += 1
+        self.total_iterations += 1
         return True
 
     def convergence(self):

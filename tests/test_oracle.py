@@ -223,3 +223,68 @@ def test_float32_scalar_recurrences_stay_float32():
     S = O.CGNR(A.astype(np.complex64), iterations=3)
     S.solve(np.ones(4, np.complex64))
     assert type(S.alpha) is np.complex64
+
+
+# ---------------------------------------------------------------- SplitBregman
+def _dft_cs_problem(seed=1):
+    rng = np.random.default_rng(seed)
+    N = 256
+    F = (np.exp(-2j * np.pi * np.outer(np.arange(N), np.arange(N)) / N) / np.sqrt(N))
+    x = np.zeros(N)
+    for _ in range(3):
+        x[rng.integers(0, N)] = rng.random()
+    b = F @ x
+    idx = np.sort(np.unique(rng.integers(0, N, N // 2)))
+    return F[idx, :].astype(np.complex128), b[idx].astype(np.complex128), x
+
+
+@pytest.mark.parametrize("elType", [np.float32, np.float64])
+def test_split_bregman_dft_compressed_sensing(elType):
+    """test/testSolvers.jl:174-201: SplitBregman, L1Regularization(2e-3), iterations=5, iterationsInner=40, rho=1.0,
+    plain and with MeasurementBasedNormalization on a rescaled system, rtol 0.1."""
+    F, b, x = _dft_cs_problem()
+    reg = O.L1Regularization(elType(2e-3))
+    S = O.createLinearSolver(O.SplitBregman, F, reg=reg, iterations=5, iterationsInner=40, rho=1.0,
+                             normalizeReg=O.NoNormalization())
+    xa = O.solve_(S, b)
+    assert np.linalg.norm(x - xa) <= 0.1 * np.linalg.norm(x)
+    assert S.iter_cnt <= 6 and S.total_iterations <= 5 * 40
+    reg2 = O.L1Regularization(elType(reg.lam * len(b) / np.sum(np.abs(b))))
+    S = O.createLinearSolver(O.SplitBregman, F, reg=reg2, iterations=5, iterationsInner=40, rho=1.0,
+                             normalizeReg=O.MeasurementBasedNormalization())
+    xa = O.solve_(S, b)
+    assert np.linalg.norm(x - xa) <= 0.1 * np.linalg.norm(x)
+
+
+def test_split_bregman_one_outer_iteration_is_admm():
+    """SplitBregman.jl docstring: `iterations = 1` is the unconstrained problem ADMM solves; the inner iteration
+    is ADMM's with the threshold λ/ρ instead of ADMM's λ/(2ρ) (ADMM.jl:262), so SplitBregman(λ) ≡ ADMM(2λ)
+    iterate by iterate as long as neither has stopped."""
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((40, 24)); xt = np.zeros(24); xt[[3, 11, 17]] = [1.0, -0.5, 0.7]
+    b = A @ xt
+    lam, rho, inner = 1e-2, 0.5, 15
+    S = O.SplitBregman(A, reg=O.L1Regularization(lam), rho=rho, iterations=1, iterationsInner=inner, absTol=0.0, relTol=0.0)
+    R = O.ADMM(A, reg=O.L1Regularization(2 * lam), rho=rho, iterations=inner, absTol=0.0, relTol=0.0)
+    S.init(b); R.init(b)
+    for k in range(inner):
+        assert S.iterate() and R.iterate()
+        if k < inner - 1:        # after the last inner iteration SplitBregman performs its Bregman update of β_y only
+            assert np.allclose(S.x, R.x, rtol=1e-12, atol=1e-14), k
+            assert np.allclose(S.z[0], R.z[0], rtol=1e-12, atol=1e-14)
+    assert np.allclose(S.x, R.x, rtol=1e-12, atol=1e-14)
+    assert not S.iterate()       # iteration == 1 and iter_cnt (2) > iterations (1)   (:289)
+    assert S.iter_cnt == 2 and S.total_iterations == inner
+
+
+def test_split_bregman_constraint_is_enforced():
+    """More outer (Bregman) iterations drive ||A x - b|| down at fixed λ (Goldstein & Osher eq. 4.7)."""
+    rng = np.random.default_rng(6)
+    A = rng.standard_normal((60, 30)); xt = np.zeros(30); xt[[2, 9, 21]] = [1.0, 0.8, -0.6]
+    b = A @ xt
+    res = []
+    for outer in (1, 4):
+        S = O.SplitBregman(A, reg=O.L1Regularization(0.5), rho=1.0, iterations=outer, iterationsInner=20, absTol=0.0, relTol=0.0)
+        xa = O.solve_(S, b)
+        res.append(np.linalg.norm(A @ xa - b))
+    assert res[1] < 0.5 * res[0]
