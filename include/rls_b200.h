@@ -45,8 +45,8 @@ enum {
 /* ---- element types: eltype(A) on the hot path (SURVEY 8b "Types") ------------ */
 enum { RLS_F32 = 0, RLS_C32 = 1 };
 
-/* ---- solver kinds: src/{FISTA,POGM,OptISTA,CGNR,ADMM}.jl --------------------- */
-enum { RLS_FISTA = 0, RLS_POGM = 1, RLS_OPTISTA = 2, RLS_CGNR = 3, RLS_ADMM = 4 };
+/* ---- solver kinds: src/{FISTA,POGM,OptISTA,CGNR,ADMM,SplitBregman}.jl -------- */
+enum { RLS_FISTA = 0, RLS_POGM = 1, RLS_OPTISTA = 2, RLS_CGNR = 3, RLS_ADMM = 4, RLS_SPLITBREGMAN = 5 };
 
 /* ---- regularisation sinks: src/proximalMaps/Prox{L1,L2,L21,TV}.jl ------------ */
 enum { RLS_REG_NONE = 0, RLS_REG_L1 = 1, RLS_REG_L2 = 2, RLS_REG_L21 = 3, RLS_REG_TV = 4 };
@@ -239,8 +239,8 @@ typedef struct {
   float tol_inner;           /* ADMM cg! reltol                                    */
   int32_t iterations_cg;     /* ADMM                                               */
   int32_t vary_rho;          /* ADMM RLS_VARY_RHO_*                                */
-  int32_t n_reg;             /* 1 (ADMM: 1..4)                                     */
-  int32_t _pad;
+  int32_t n_reg;             /* 1 (ADMM / SplitBregman: 1..4)                      */
+  int32_t iterations_inner;  /* SplitBregman: inner iterations per Bregman update; `iterations` counts the outer ones */
   rls_reg_desc reg[4];
 } rls_solver_desc;
 
@@ -258,7 +258,7 @@ typedef struct {
   float admm_sigma_abs;
   int32_t cg_iterations_last;                     /* ADMM: inner CG steps of the last outer iteration */
   int32_t cg_iterations_total;
-  int32_t _pad;
+  int32_t outer_iteration;                        /* SplitBregman: iter_cnt (SplitBregman.jl:35) */
 } rls_solver_scalars;
 
 /* createLinearSolver(S, A; AHA=op, kwargs...) RegularizedLeastSquares.jl:288-294.
@@ -271,7 +271,7 @@ int32_t rls_solver_set_reg(rls_solver_t s, int32_t idx, const rls_reg_desc* reg)
  * CGNR.jl:107-130, ADMM.jl:191-220.  b and x0 are device vectors (x0 may be NULL = 0). */
 int32_t rls_solver_init(rls_solver_t s, rls_vec_t b, rls_vec_t x0);
 /* iterate(solver, state): FISTA.jl:139-185, POGM.jl:173-237, OptISTA.jl:164-204,
- * CGNR.jl:143-178, ADMM.jl:230-322.  *advanced = 0 when done() was already true
+ * CGNR.jl:143-178, ADMM.jl:230-322, SplitBregman.jl:203-272.  *advanced = 0 when done() was already true
  * (Julia `nothing`).  Synchronises to return the scalars. */
 int32_t rls_solver_iterate(rls_solver_t s, int32_t* advanced, rls_solver_scalars* scalars);
 /* the `for _ in enumerate(solver)` loop of solve! for an initialised solver: enqueue the

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librls_b200.so")
 
 RLS_OK = 0
 RLS_F32, RLS_C32 = 0, 1
-RLS_FISTA, RLS_POGM, RLS_OPTISTA, RLS_CGNR, RLS_ADMM = 0, 1, 2, 3, 4
+RLS_FISTA, RLS_POGM, RLS_OPTISTA, RLS_CGNR, RLS_ADMM, RLS_SPLITBREGMAN = 0, 1, 2, 3, 4, 5
 RLS_REG_NONE, RLS_REG_L1, RLS_REG_L2, RLS_REG_L21, RLS_REG_TV = 0, 1, 2, 3, 4
 RLS_PROJ_REAL, RLS_PROJ_POSITIVE = 1, 2
 RLS_NORMAL_TWOPASS, RLS_NORMAL_ONEPASS, RLS_NORMAL_GRAM, RLS_NORMAL_AUTO = 0, 1, 2, 3
@@ -45,7 +45,7 @@ class SolverDesc(C.Structure):
         ("kind", C.c_int32), ("iterations", C.c_int32), ("restart", C.c_int32), ("proj_mask", C.c_int32),
         ("rho", C.c_float), ("theta", C.c_float), ("sigma_fac", C.c_float), ("rel_tol", C.c_float),
         ("abs_tol", C.c_float), ("tol_inner", C.c_float), ("iterations_cg", C.c_int32), ("vary_rho", C.c_int32),
-        ("n_reg", C.c_int32), ("_pad", C.c_int32), ("reg", RegDesc * 4),
+        ("n_reg", C.c_int32), ("iterations_inner", C.c_int32), ("reg", RegDesc * 4),
     ]
 
 
@@ -59,7 +59,7 @@ class SolverScalars(C.Structure):
         ("admm_rk", C.c_float * 4), ("admm_sk", C.c_float * 4), ("admm_eps_pri", C.c_float * 4),
         ("admm_eps_dua", C.c_float * 4), ("admm_delta", C.c_float * 4), ("admm_rho", C.c_float * 4),
         ("admm_sigma_abs", C.c_float), ("cg_iterations_last", C.c_int32), ("cg_iterations_total", C.c_int32),
-        ("_pad", C.c_int32),
+        ("outer_iteration", C.c_int32),
     ]
 
 

@@ -29,6 +29,8 @@ struct DevState {
   float cgi_res, cgi_prev, cgi_tol, cgi_beta;
   float2 cgi_alpha;
   int cgi_k, cgi_gate, cgi_last, cgi_total;
+  // SplitBregman (ADMM-like inner iteration + Bregman update of β_y): SplitBregman.jl:19-46
+  int sb, iterations_inner, sb_iter_cnt, sb_outer_gate, sb_total;
 };
 
 enum {
@@ -54,7 +56,8 @@ enum {
   STEP_ADMM_CG_POST,   // t[0] = |r|^2
   STEP_ADMM_TERM_SAVE, // gradient trafo: dual-domain sums parked in save[] until the pixel pass
   STEP_ADMM_TERM,      // residual bookkeeping of one term (index in `arg`; arg >= 16: merge save[])
-  STEP_ADMM_ITER_END
+  STEP_ADMM_ITER_END,
+  STEP_SB_FINISH       // SplitBregman: counters after the (gated) Bregman update  SplitBregman.jl:264-271
 };
 
 #ifdef __CUDACC__
@@ -77,6 +80,18 @@ __device__ inline void admm_update_done(DevState* S) {
     if (S->a_sk[i] >= fadd(S->sigma_abs, fmul(S->rel_tol, S->a_eps_dua[i]))) conv = false;
   }
   S->done = (conv || S->iteration >= S->iterations) ? 1 : 0;
+}
+
+__device__ inline bool admm_converged(const DevState* S) {
+  for (int i = 0; i < S->n_reg; ++i) {
+    if (S->a_rk[i] >= fadd(S->sigma_abs, fmul(S->rel_tol, S->a_eps_pri[i]))) return false;
+    if (S->a_sk[i] >= fadd(S->sigma_abs, fmul(S->rel_tol, S->a_eps_dua[i]))) return false;
+  }
+  return true;
+}
+// done(::SplitBregman) = converged || (iteration == 1 && iter_cnt > iterations)   SplitBregman.jl:289
+__device__ inline void sb_update_done(DevState* S) {
+  S->done = (admm_converged(S) || (S->iteration == 1 && S->sb_iter_cnt > S->iterations)) ? 1 : 0;
 }
 
 // The scalar part of every solver step.  `t` are the fixed-order reduction totals.
@@ -219,13 +234,19 @@ __device__ inline void scalar_step(DevState* S, int step, int arg, const double*
       S->sigma_abs = (float)(sqrt((double)S->b_len) * (double)S->abs_tol);
       S->iteration = 0;
       S->cgi_k = 0; S->cgi_last = 0; S->cgi_total = 0;
-      admm_update_done(S);
+      S->sb_outer_gate = 1; S->sb_total = 0;
+      if (S->sb) {                                                           // SplitBregman.jl:198-199
+        S->iteration = 1; S->sb_iter_cnt = 1;
+        sb_update_done(S);
+      } else {
+        admm_update_done(S);
+      }
       S->cgi_gate = 1;
       break;
     }
     case STEP_ADMM_ITER_BEGIN: {
-      for (int i = 0; i < S->n_reg; ++i) {                                   // λ/(2ρ)  ADMM.jl:261
-        const float two_rho = fmul(2.f, S->a_rho[i]);
+      for (int i = 0; i < S->n_reg; ++i) {                                   // λ/(2ρ)  ADMM.jl:261 ; λ/ρ  SplitBregman.jl:236
+        const float two_rho = S->sb ? S->a_rho[i] : fmul(2.f, S->a_rho[i]);
         S->a_thr[i] = S->lam_is_f64[i] ? (float)(S->lam64[i] / (double)two_rho) : fdiv(S->lam[i], two_rho);
       }
       S->cgi_gate = S->done;
@@ -275,11 +296,13 @@ __device__ inline void scalar_step(DevState* S, int step, int arg, const double*
       const float rho = S->a_rho[i];
       const float delta_old = S->a_delta[i];
       S->a_delta[i] = fadd(fadd((float)sqrt(t[0]), (float)sqrt(t[1])), (float)sqrt(t[2]));
-      S->a_sk[i] = fmul(rho, (float)sqrt(t[3]));
+      // ADMM: ρ‖Φ'(z-zᵒˡᵈ)‖, ρ‖Φ'u‖ (ADMM.jl:290,299); SplitBregman: ‖ρΦ'(z-zᵒˡᵈ)‖, ‖ρΦ'u‖ — ρ already inside the sums
+      S->a_sk[i] = S->sb ? (float)sqrt(t[3]) : fmul(rho, (float)sqrt(t[3]));
       S->a_eps_pri[i] = fmaxf((float)sqrt(t[4]), (float)sqrt(t[5]));
       S->a_rk[i] = (float)sqrt(t[6]);
-      S->a_eps_dua[i] = fmul(rho, (float)sqrt(t[7]));
+      S->a_eps_dua[i] = S->sb ? (float)sqrt(t[7]) : fmul(rho, (float)sqrt(t[7]));
       S->a_uscale[i] = 1.f;
+      if (S->sb) break;
       // rᵏ/ɛᵖʳⁱ > 10sᵏ/ɛᵈᵘᵃ parses as (10*sᵏ)/ɛᵈᵘᵃ ; Δ/Δᵒˡᵈ > 0.9 compares against the Float64 literal
       const float rp = fdiv(S->a_rk[i], S->a_eps_pri[i]), sd = fdiv(S->a_sk[i], S->a_eps_dua[i]);
       const float rp10 = fdiv(fmul(10.f, S->a_rk[i]), S->a_eps_pri[i]), sd10 = fdiv(fmul(10.f, S->a_sk[i]), S->a_eps_dua[i]);
@@ -296,9 +319,22 @@ __device__ inline void scalar_step(DevState* S, int step, int arg, const double*
     case STEP_ADMM_ITER_END: {
       S->cgi_last = S->cgi_k;
       S->cgi_total += S->cgi_k;
+      S->cgi_gate = 1;
+      if (S->sb) {
+        // Bregman update next iff converged || iteration >= iterationsInner   SplitBregman.jl:257
+        S->sb_outer_gate = (admm_converged(S) || S->iteration >= S->iterations_inner) ? 0 : 1;
+        break;
+      }
       S->iteration += 1;
       admm_update_done(S);
-      S->cgi_gate = 1;
+      break;
+    }
+    case STEP_SB_FINISH: {                                                   // SplitBregman.jl:264-271
+      if (S->sb_outer_gate == 0) { S->sb_iter_cnt += 1; S->iteration = 0; }
+      S->iteration += 1;
+      S->sb_total += 1;
+      S->sb_outer_gate = 1;
+      sb_update_done(S);
       break;
     }
     default:

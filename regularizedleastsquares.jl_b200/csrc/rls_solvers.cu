@@ -185,6 +185,23 @@ __global__ void __launch_bounds__(EB) fista_main_batch_kernel(const __grid_const
   grid_reduce_finalize<2, EB>(acc, partials + (size_t)k * pstride, tickets + k, [=](double* t) { scalar_step(S, STEP_FISTA_POST, 0, t); });
 }
 
+// ================================ SplitBregman =======================================
+// Bregman update (SplitBregman.jl:258-263), executed only when the device-side flag says so:
+//   β_y .+= y ; mul!(β_y, AHA, x, -1, 1)        (ahax = AHA x from the gated operator apply)
+template <typename T>
+__global__ void __launch_bounds__(EB) sb_outer_kernel(T* __restrict__ beta_y, const T* __restrict__ y, const T* __restrict__ ahax,
+                                                       int64_t n, const DevState* __restrict__ S) {
+  if (S->done || S->sb_outer_gate) return;
+  EW_LOOP(i, n) beta_y[i] = Elem<T>::sub(Elem<T>::add(beta_y[i], y[i]), ahax[i]);
+}
+//   z[i] = Φ_i x (identity regTrafo) ; u[i] .= 0
+template <typename T>
+__global__ void __launch_bounds__(EB) sb_reset_term_kernel(T* __restrict__ z, T* __restrict__ u, const T* __restrict__ x, int64_t n,
+                                                            const DevState* __restrict__ S) {
+  if (S->done || S->sb_outer_gate) return;
+  EW_LOOP(i, n) { z[i] = x[i]; u[i] = Elem<T>::zero(); }
+}
+
 // ================================ POGM ===============================================
 // bufX holds x on entry and y on exit; bufY holds y on entry and x on exit (the host swaps roles).
 template <typename T, int PART>
@@ -429,6 +446,8 @@ __global__ void __launch_bounds__(EB) admm_term_identity_kernel(const T* __restr
   if (S->done) return;
   const float thr = S->a_thr[term];
   const bool do_prox = S->a_rho[term] != 0.f;
+  const bool sb = S->sb != 0;                       // SplitBregman: ‖ρΦ'(z-zᵒˡᵈ)‖, ‖ρΦ'u‖ with ρ inside (SplitBregman.jl:244,247)
+  const float rho_in = sb ? S->a_rho[term] : 1.f;
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   EW_LOOP(i, n) {
     const T xv = x[i], uv = u[i];
@@ -446,10 +465,10 @@ __global__ void __launch_bounds__(EB) admm_term_identity_kernel(const T* __restr
     const T du = Elem<T>::sub(un, uv);
     const T xz = Elem<T>::sub(xv, zn);
     acc[0] += Elem<T>::abs2(dx); acc[1] += Elem<T>::abs2(dz); acc[2] += Elem<T>::abs2(du);
-    acc[3] += Elem<T>::abs2(dz);                                         // Φ'(z - zᵒˡᵈ)          :289-290
+    acc[3] += Elem<T>::abs2(sb ? Elem<T>::scale(dz, rho_in) : dz);       // Φ'(z - zᵒˡᵈ)          :289-290
     acc[4] += Elem<T>::abs2(xv); acc[5] += Elem<T>::abs2(zn);            // :292-293
     acc[6] += Elem<T>::abs2(xz);                                         // :295-296
-    acc[7] += Elem<T>::abs2(un);                                         // :298-299
+    acc[7] += Elem<T>::abs2(sb ? Elem<T>::scale(un, rho_in) : un);       // :298-299
     z[i] = zn; u[i] = un; uold[i] = du; zold[i] = xz; xold[i] = un;
   }
   if (PART == 1) return;
@@ -576,6 +595,16 @@ struct rls_solver_s {
 
 namespace {
 
+// upper bound on the iterations a callback-free solve! has to enqueue (done() gates the rest on the device)
+static inline int iteration_cap(const rls_solver_desc& d, int64_t n) {
+  if (d.kind == RLS_CGNR) return (int)std::min<int64_t>(d.iterations, n);
+  if (d.kind == RLS_SPLITBREGMAN) return (int)std::min<int64_t>((int64_t)d.iterations * d.iterations_inner, 1 << 20);
+  return d.iterations;
+}
+
+// SplitBregman shares ADMM's state layout, x update (β build + warm-started cg!) and term update kernels
+static inline bool admm_like(int kind) { return kind == RLS_ADMM || kind == RLS_SPLITBREGMAN; }
+
 static void free_lane(Lane& L) {
   for (int k = 0; k < V_COUNT; ++k)
     if (L.v[k]) { rls_vec_destroy(L.v[k]); L.v[k] = nullptr; }
@@ -598,11 +627,12 @@ static int32_t alloc_lane(rls_solver_s* s, Lane& L) {
   RLS_TRY(need_vec(s, L, V_X, n));
   RLS_TRY(need_vec(s, L, V_X0, n));
   if (kind == RLS_FISTA || kind == RLS_POGM || kind == RLS_OPTISTA) RLS_TRY(need_vec(s, L, V_RES, n));
-  if (kind == RLS_FISTA || kind == RLS_POGM || kind == RLS_ADMM) RLS_TRY(need_vec(s, L, V_XOLD, n));
+  if (kind == RLS_FISTA || kind == RLS_POGM || admm_like(kind)) RLS_TRY(need_vec(s, L, V_XOLD, n));
   if (kind == RLS_POGM) { RLS_TRY(need_vec(s, L, V_Y, n)); RLS_TRY(need_vec(s, L, V_Z, n)); RLS_TRY(need_vec(s, L, V_W, n)); }
   if (kind == RLS_OPTISTA) { RLS_TRY(need_vec(s, L, V_Y, n)); RLS_TRY(need_vec(s, L, V_Z, n)); RLS_TRY(need_vec(s, L, V_ZOLD, n)); }
   if (kind == RLS_CGNR) { RLS_TRY(need_vec(s, L, V_P, n)); RLS_TRY(need_vec(s, L, V_V, n)); }
-  if (kind == RLS_ADMM) {
+  if (kind == RLS_SPLITBREGMAN) RLS_TRY(need_vec(s, L, V_Y, n));     // y = A'b, kept for the Bregman updates
+  if (admm_like(kind)) {
     RLS_TRY(need_vec(s, L, V_BETA, n)); RLS_TRY(need_vec(s, L, V_BETAY, n));
     RLS_TRY(need_vec(s, L, V_CGU, n)); RLS_TRY(need_vec(s, L, V_CGR, n)); RLS_TRY(need_vec(s, L, V_CGC, n));
     for (int i = 0; i < s->desc.n_reg; ++i) {
@@ -629,6 +659,8 @@ static int32_t push_config(rls_solver_s* s, Lane& L) {
   h->iterations_cg = d.iterations_cg; h->vary_rho = d.vary_rho; h->n_reg = d.n_reg; h->proj_mask = d.proj_mask;
   h->rho = d.rho; h->theta0 = d.theta; h->sigma_fac = d.sigma_fac; h->rel_tol = d.rel_tol; h->abs_tol = d.abs_tol;
   h->tol_inner = d.tol_inner;
+  h->sb = d.kind == RLS_SPLITBREGMAN ? 1 : 0;
+  h->iterations_inner = d.iterations_inner;
   for (int i = 0; i < 4; ++i) {
     h->lam[i] = (float)d.reg[i].lambda; h->lam64[i] = d.reg[i].lambda; h->lam_is_f64[i] = d.reg[i].lambda_is_f64;
     h->rho0[i] = d.reg[i].rho;
@@ -651,6 +683,7 @@ static void swap_roles(rls_solver_s* s, Lane& L) {
   switch (s->desc.kind) {
     case RLS_FISTA: std::swap(L.v[V_X], L.v[V_XOLD]); break;
     case RLS_POGM: std::swap(L.v[V_X], L.v[V_Y]); break;
+    case RLS_SPLITBREGMAN:
     case RLS_ADMM:
       for (int i = 0; i < s->desc.n_reg; ++i) std::swap(L.v[V_TZ0 + i], L.v[V_TZOLD0 + i]);
       break;
@@ -660,10 +693,12 @@ static void swap_roles(rls_solver_s* s, Lane& L) {
 
 // after a synchronisation: iterations that were enqueued but gated off must not count as swaps
 static void reconcile_roles(rls_solver_s* s, Lane& L) {
-  const int executed = L.hS->iteration - L.base_iter;
+  // SplitBregman's `iteration` restarts at every Bregman update: it counts executed iterations in sb_total
+  const int count = s->desc.kind == RLS_SPLITBREGMAN ? L.hS->sb_total : L.hS->iteration;
+  const int executed = count - L.base_iter;
   if (((L.enq_swaps - executed) & 1) != 0) swap_roles(s, L);
   L.enq_swaps = 0;
-  L.base_iter = L.hS->iteration;
+  L.base_iter = count;
 }
 
 template <typename T> static T* P(rls_vec_s* v) { return v ? (T*)v->d : nullptr; }
@@ -682,7 +717,7 @@ static int32_t init_lane_t(rls_solver_s* s, Lane& L, const void* b_dev, int64_t 
   L.enq_swaps = 0;
   L.base_iter = 0;
   // x₀ / β_y = A' b   (or b itself when only AHA was given)
-  T* x0v = P<T>(kind == RLS_ADMM ? L.v[V_BETAY] : L.v[V_X0]);
+  T* x0v = P<T>(admm_like(kind) ? L.v[V_BETAY] : L.v[V_X0]);
   if (s->A && have_atb) {
     // the multi-RHS driver already formed A'b for all columns with one GEMM (and all-reduced it)
   } else if (s->A) {
@@ -718,6 +753,9 @@ static int32_t init_lane_t(rls_solver_s* s, Lane& L, const void* b_dev, int64_t 
       RLS_CUDA(cudaMemsetAsync(L.v[V_V]->d, 0, nb, st));
       RLS_CUDA(cudaMemcpyAsync(L.v[V_P]->d, L.v[V_X0]->d, nb, cudaMemcpyDeviceToDevice, st));
       break;
+    case RLS_SPLITBREGMAN:
+      RLS_CUDA(cudaMemcpyAsync(L.v[V_Y]->d, L.v[V_BETAY]->d, nb, cudaMemcpyDeviceToDevice, st));   // y .= β_y  :179
+      // fall through
     case RLS_ADMM:
       RLS_CUDA(cudaMemsetAsync(L.v[V_XOLD]->d, 0, nb, st));
       for (int i = 0; i < s->desc.n_reg; ++i) {
@@ -731,7 +769,7 @@ static int32_t init_lane_t(rls_solver_s* s, Lane& L, const void* b_dev, int64_t 
       break;
   }
   c->launches++;
-  if (kind == RLS_ADMM) {
+  if (admm_like(kind)) {
     scalar_kernel<<<1, 32, 0, st>>>(L.dS, STEP_ADMM_INIT, 0, nullptr);
   } else {
     norm_step_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_X0]), n, L.dS, STEP_INIT, 0, c->red_partials, c->red_ticket, nullptr);
@@ -854,6 +892,7 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L, int phase = IT_ALL)
       c->launches += 3;
       break;
     }
+    case RLS_SPLITBREGMAN:
     case RLS_ADMM: {
       const int k = s->desc.n_reg;
       bool all_identity = true;
@@ -914,6 +953,16 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L, int phase = IT_ALL)
       }
       scalar_kernel<<<1, 32, 0, st>>>(S, STEP_ADMM_ITER_END, 0, gate);
       c->launches++;
+      if (s->desc.kind == RLS_SPLITBREGMAN) {
+        // Bregman update, gated on the device flag set by ITER_END (converged || iteration >= iterationsInner)
+        const int* ogate = &S->sb_outer_gate;
+        RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_CGC]->d, ogate));
+        sb_outer_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_BETAY]), P<T>(L.v[V_Y]), P<T>(L.v[V_CGC]), n, S);
+        for (int i = 0; i < k; ++i)
+          sb_reset_term_kernel<T><<<ew_grid(c, s->rows[i]), EB, 0, st>>>(P<T>(L.v[V_TZ0 + i]), P<T>(L.v[V_TU0 + i]), P<T>(L.v[V_X]), s->rows[i], S);
+        scalar_kernel<<<1, 32, 0, st>>>(S, STEP_SB_FINISH, 0, gate);
+        c->launches += 2 + k;
+      }
       break;
     }
     default:
@@ -949,14 +998,19 @@ static void fill_scalars(const DevState* h, rls_solver_scalars* o) {
   o->admm_sigma_abs = h->sigma_abs;
   o->cg_iterations_last = h->cgi_last;
   o->cg_iterations_total = h->cgi_total;
+  o->outer_iteration = h->sb_iter_cnt;
 }
 
 static int32_t validate_desc(const rls_solver_desc* d) {
-  RLS_CHECK_ARG(d->kind >= RLS_FISTA && d->kind <= RLS_ADMM, "unknown solver kind %d", d->kind);
+  RLS_CHECK_ARG(d->kind >= RLS_FISTA && d->kind <= RLS_SPLITBREGMAN, "unknown solver kind %d", d->kind);
   RLS_CHECK_ARG(d->iterations >= 0, "iterations must be >= 0");
-  if (d->kind == RLS_ADMM) {
-    RLS_CHECK_ARG(d->n_reg >= 1 && d->n_reg <= 4, "ADMM supports 1..4 regularization terms, got %d", d->n_reg);
+  if (admm_like(d->kind)) {
+    RLS_CHECK_ARG(d->n_reg >= 1 && d->n_reg <= 4, "ADMM / SplitBregman support 1..4 regularization terms, got %d", d->n_reg);
     RLS_CHECK_ARG(d->iterations_cg >= 0, "iterationsCG must be >= 0");
+    if (d->kind == RLS_SPLITBREGMAN) {
+      RLS_CHECK_ARG(d->iterations_inner >= 1, "iterationsInner must be >= 1");
+      RLS_CHECK_ARG(d->vary_rho == RLS_VARY_RHO_NONE, "SplitBregman has no vary_rho keyword");
+    }
   } else if (d->kind == RLS_CGNR) {
     RLS_CHECK_ARG(d->n_reg <= 1, "CGNR does not allow for more additional regularization terms, found %d", d->n_reg);
     RLS_CHECK_ARG(d->n_reg == 0 || d->reg[0].kind == RLS_REG_L2 || d->reg[0].kind == RLS_REG_NONE,
@@ -970,6 +1024,10 @@ static int32_t validate_desc(const rls_solver_desc* d) {
     const rls_reg_desc& r = d->reg[i];
     RLS_CHECK_ARG(r.kind >= RLS_REG_NONE && r.kind <= RLS_REG_TV, "unknown regularization kind %d", r.kind);
     RLS_CHECK_ARG(r.trafo == RLS_TRAFO_IDENTITY || r.trafo == RLS_TRAFO_GRADIENT, "unknown regTrafo %d", r.trafo);
+    if (r.trafo == RLS_TRAFO_GRADIENT && d->kind == RLS_SPLITBREGMAN) {
+      rls_set_error("SplitBregman with a GradientOp regTrafo is not on the accelerated path yet (identity regTrafo only)");
+      return RLS_ERR_UNSUPPORTED;
+    }
     if (r.trafo == RLS_TRAFO_GRADIENT) {
       RLS_CHECK_ARG(d->kind == RLS_ADMM, "regTrafo is an ADMM keyword");
       if (!rls_reg_is_elementwise(r.kind)) {
@@ -1106,7 +1164,7 @@ extern "C" int32_t rls_solver_iterate(rls_solver_t s, int32_t* advanced, rls_sol
 }
 
 static int32_t run_lane_async(rls_solver_s* s, Lane& L, int already_done) {
-  const int cap = s->desc.kind == RLS_CGNR ? (int)std::min<int64_t>(s->desc.iterations, s->n) : s->desc.iterations;
+  const int cap = iteration_cap(s->desc, s->n);
   for (int it = already_done; it < cap; ++it) RLS_TRY(enqueue_iteration(s, L));
   if (s->desc.kind == RLS_CGNR && s->desc.proj_mask)
     RLS_TRY(rls_proj_launch(s->ctx, s->dtype, L.v[V_X]->d, s->n, s->desc.proj_mask, nullptr));
@@ -1124,7 +1182,7 @@ extern "C" int32_t rls_solver_run(rls_solver_t s, int32_t* iterations_done, rls_
   RLS_CHECK_ARG(s, "NULL argument");
   RlsDeviceGuard g(s->ctx->device);
   Lane& L = s->lanes[0];
-  if (!L.hS->done) RLS_TRY(run_lane_async(s, L, L.hS->iteration));
+  if (!L.hS->done) RLS_TRY(run_lane_async(s, L, s->desc.kind == RLS_SPLITBREGMAN ? L.hS->sb_total : L.hS->iteration));
   else if (s->desc.kind == RLS_CGNR && s->desc.proj_mask)
     RLS_TRY(rls_proj_launch(s->ctx, s->dtype, L.v[V_X]->d, s->n, s->desc.proj_mask, nullptr));
   RLS_TRY(pull_state(s, L));
@@ -1272,7 +1330,7 @@ extern "C" int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_hos
       std::vector<void*> xp(K);
       for (int k = 0; k < K; ++k) {
         bp[k] = (const char*)Bd->d + (size_t)k * bstride * es;
-        xp[k] = s->lanes[k].v[s->desc.kind == RLS_ADMM ? V_BETAY : V_X0]->d;
+        xp[k] = s->lanes[k].v[admm_like(s->desc.kind) ? V_BETAY : V_X0]->d;
       }
       status = rls_normal_adjoint_batch_raw(s->AHA, K, bp.data(), xp.data(), &have_atb);
       if (status != RLS_OK) break;
@@ -1281,11 +1339,11 @@ extern "C" int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_hos
       status = init_lane(s, s->lanes[k], (const char*)Bd->d + (size_t)k * bstride * es, blen, nullptr, have_atb);
     if (status != RLS_OK) break;
     const auto t2 = now();
-    const int cap = s->desc.kind == RLS_CGNR ? (int)std::min<int64_t>(s->desc.iterations, s->n) : s->desc.iterations;
+    const int cap = iteration_cap(s->desc, s->n);
     // one apply per iteration (FISTA / POGM / OptISTA / CGNR): the K applies of a batched iteration go through
     // rls_normal_apply_batch_raw — two tensor-core GEMMs reading A once each when A is row-major — between the
     // per-column pre and post kernels.  ADMM (1 + n_cg applies with data-dependent gates) keeps the per-column loop.
-    const bool split = K > 1 && s->desc.kind != RLS_ADMM;
+    const bool split = K > 1 && !admm_like(s->desc.kind);
     for (int it = 0; it < cap && status == RLS_OK; ++it) {
       if (!split) {
         for (int k = 0; k < K && status == RLS_OK; ++k) status = enqueue_iteration(s, s->lanes[k]);

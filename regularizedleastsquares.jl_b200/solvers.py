@@ -405,9 +405,64 @@ class ADMM(AbstractLinearSolver):
         return {"primal": list(self._scalars.admm_rk)[:k], "dual": list(self._scalars.admm_sk)[:k]}
 
 
+class SplitBregman(ADMM):
+    """SplitBregman(A; AHA, precon, reg, regTrafo, normalizeReg, rho, iterations, iterationsInner, iterationsCG,
+    absTol, relTol, tolInner, verbose)  SplitBregman.jl:80-146 (precon = Identity and identity regTrafo only on the
+    accelerated path).  `iterations` counts the outer (Bregman) iterations, `iterationsInner` the ADMM-like inner
+    ones; `state.iteration` restarts at every Bregman update, `iter_cnt` is `outer_iteration`."""
+    name = "SplitBregman"
+    _norm_after_init = False
+
+    def __init__(self, A, *, AHA=None, precon=None, reg=None, regTrafo=None, normalizeReg=None, rho=1e-1,
+                 iterations=10, iterationsInner=10, iterationsCG=10, absTol=None, relTol=None, tolInner=1e-5,
+                 verbose=False, normal="auto", ctx=None):
+        if precon is not None:
+            raise NotImplementedError("SplitBregman: only the Identity() preconditioner is on the accelerated path")
+        self._setup(A, AHA, normal, ctx)
+        self.normalizeReg = NoNormalization() if normalizeReg is None else normalizeReg
+        if reg is None:
+            reg = L1Regularization(np.float32(0))
+        regs = list(reg) if isinstance(reg, (list, tuple)) else [reg]
+        idx = findsinks(AbstractProjectionRegularization, regs)
+        self.proj = [regs[i] for i in idx]
+        regs = [r for i, r in enumerate(regs) if i not in idx]
+        if regTrafo is None:
+            trafo = [None] * len(regs)
+        else:
+            trafo = list(regTrafo) if isinstance(regTrafo, (list, tuple)) else [regTrafo]
+        assert len(regs) == len(trafo), "reg and regTrafo must have the same length"      # SplitBregman.jl:108
+        if any(t is not None for t in trafo):
+            raise NotImplementedError("SplitBregman: a regTrafo other than the identity is not on the accelerated path yet")
+        if not 1 <= len(regs) <= 4:
+            raise ValueError("SplitBregman on this path takes 1..4 regularization terms")
+        self.regTrafo = trafo
+        self.rho = [np.float32(rho)] * len(regs) if np.isscalar(rho) else [np.float32(r) for r in rho]
+        self.reg = self._normalize_ctor(regs)
+        eps = np.finfo(np.float32).eps
+        self.iterations, self.iterationsInner, self.iterationsCG = int(iterations), int(iterationsInner), int(iterationsCG)
+        d = capi.SolverDesc()
+        d.kind = capi.RLS_SPLITBREGMAN
+        d.iterations = self.iterations
+        d.iterations_inner = self.iterationsInner
+        d.iterations_cg = self.iterationsCG
+        d.abs_tol = np.float32(eps if absTol is None else absTol)
+        d.rel_tol = np.float32(eps if relTol is None else relTol)
+        d.tol_inner = np.float32(tolInner)
+        for p in self.proj:
+            d.proj_mask |= sink(p).mask
+        d.n_reg = len(regs)
+        for i, r in enumerate(self.reg):
+            d.reg[i] = self._reg_desc(i, r)
+        self._create(d)
+
+    @property
+    def iter_cnt(self):
+        return self._scalars.outer_iteration
+
+
 def linearSolverList():
     """the solvers on the accelerated path (RegularizedLeastSquares.jl:213-220 lists all of upstream's)"""
-    return [CGNR, FISTA, OptISTA, POGM, ADMM]
+    return [CGNR, FISTA, OptISTA, POGM, ADMM, SplitBregman]
 
 
 def createLinearSolver(solver, A=None, *, AHA=None, kwargWarning=True, **kwargs):

@@ -372,3 +372,61 @@ def test_row_major_fista_split_epilogue_and_projections(rls, ctx, regname, monke
     monkeypatch.setenv("RLS_FUSE_ITERATION", "0")
     x_chain = rls.solve_(S, b)
     assert np.array_equal(x_fused, x_chain)
+
+
+# ---------------------------------------------------------------- SplitBregman
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", ["l1", "l1_stops_early", "two_terms", "l21_split_prox"])
+def test_split_bregman(rls, ctx, dtype, case):
+    """SplitBregman.jl:203-289 against the oracle, iterate by iterate: inner ADMM-like iterations, the Bregman update
+    of β_y every `iterationsInner` inner iterations (or at convergence), `iter_cnt`, stopping decisions and the
+    inner-CG counts."""
+    A, xt, b = problem(dtype, 160, 96, seed=700)
+    kw = dict(rho=0.5, iterations=3, iterationsInner=6, iterationsCG=8, absTol=0.0, relTol=0.0)
+    if case == "l1":
+        mk = lambda M: dict(reg=M.L1Regularization(np.float32(2e-2)))
+    elif case == "l1_stops_early":
+        mk = lambda M: dict(reg=M.L1Regularization(np.float32(2e-2)))
+        kw.update(relTol=np.float32(3e-2), iterations=4, iterationsInner=25)
+    elif case == "two_terms":
+        mk = lambda M: dict(reg=[M.L1Regularization(np.float32(1e-2)), M.L2Regularization(np.float32(5e-2)), M.RealRegularization()],
+                            regTrafo=[None, None])
+        kw.update(rho=[0.5, 0.25])
+    else:
+        mk = lambda M: dict(reg=M.L21Regularization(np.float32(5e-3), slices=8))
+    S = rls.SplitBregman(A, **mk(rls), **kw)
+    R = O.SplitBregman(A, **mk(O), **kw)
+    S.init_(b); R.init(b)
+    steps = 0
+    while True:
+        a1, a2 = S.iterate(), R.iterate()
+        assert a1 == a2, f"stopping decision differs after {steps} iterations: gpu={a1} oracle={a2}"
+        if not a1:
+            break
+        steps += 1
+        assert S.iteration == R.iteration and S.iter_cnt == R.iter_cnt, (steps, S.iteration, R.iteration, S.iter_cnt, R.iter_cnt)
+        assert rel(S.x, R.x) < 5e-5, f"iteration {steps}: rel-L2 {rel(S.x, R.x):.3e}"
+        assert S._scalars.cg_iterations_last == R.cg_iters[-1]
+    assert steps == R.total_iterations and steps > 0
+    if case == "l1_stops_early":
+        assert steps < 4 * 25
+    # whole-solve fast path (iterations enqueued back to back, device-side gating of the Bregman updates)
+    x = rls.solve_(S, b)
+    assert rel(x, O.solve_(R, b)) < 5e-5
+    assert S.iter_cnt == R.iter_cnt
+
+
+def test_split_bregman_reference_acceptance(rls, ctx):
+    """test/testSolvers.jl:174-201 on the accelerated path (ComplexF32 instance of the 256-point DFT problem)."""
+    rng = np.random.default_rng(1)
+    N = 256
+    F = (np.exp(-2j * np.pi * np.outer(np.arange(N), np.arange(N)) / N) / np.sqrt(N))
+    x = np.zeros(N)
+    for _ in range(3):
+        x[rng.integers(0, N)] = rng.random()
+    idx = np.sort(np.unique(rng.integers(0, N, N // 2)))
+    F = F[idx, :].astype(np.complex64); b = (F @ x).astype(np.complex64)
+    S = rls.createLinearSolver(rls.SplitBregman, F, reg=rls.L1Regularization(np.float32(2e-3)), iterations=5, iterationsInner=40,
+                               rho=1.0, normalizeReg=rls.NoNormalization())
+    xa = rls.solve_(S, b)
+    assert np.linalg.norm(x - xa) <= 0.1 * np.linalg.norm(x)
