@@ -14,7 +14,7 @@ using RegularizedLeastSquares
 using LinearAlgebra
 import RegularizedLeastSquares: init!, iterate, solve!, prox!, solversolution, solverconvergence,
        L1Regularization, L2Regularization, L21Regularization, TVRegularization, PositiveRegularization,
-       RealRegularization, FISTA, POGM, OptISTA, CGNR, ADMM, λ, sink
+       RealRegularization, FISTA, POGM, OptISTA, CGNR, ADMM, SplitBregman, λ, sink
 
 const LIB = get(ENV, "RLS_B200_LIB", "librls_b200.so")
 
@@ -30,7 +30,7 @@ end
 
 # ---- enums of include/rls_b200.h ----------------------------------------------------------------
 const RLS_F32, RLS_C32 = Int32(0), Int32(1)
-const RLS_FISTA, RLS_POGM, RLS_OPTISTA, RLS_CGNR, RLS_ADMM = Int32.(0:4)
+const RLS_FISTA, RLS_POGM, RLS_OPTISTA, RLS_CGNR, RLS_ADMM, RLS_SPLITBREGMAN = Int32.(0:5)
 const RLS_REG_NONE, RLS_REG_L1, RLS_REG_L2, RLS_REG_L21, RLS_REG_TV = Int32.(0:4)
 const RLS_PROJ_REAL, RLS_PROJ_POSITIVE = Int32(1), Int32(2)
 const RLS_NORMAL_AUTO = Int32(3)
@@ -47,7 +47,7 @@ end
 struct SolverDesc
   kind::Int32; iterations::Int32; restart::Int32; proj_mask::Int32
   rho::Float32; theta::Float32; sigma_fac::Float32; rel_tol::Float32; abs_tol::Float32; tol_inner::Float32
-  iterations_cg::Int32; vary_rho::Int32; n_reg::Int32; _pad::Int32
+  iterations_cg::Int32; vary_rho::Int32; n_reg::Int32; iterations_inner::Int32   # iterations_inner: SplitBregman
   reg::NTuple{4,RegDesc}
 end
 struct SolverScalars
@@ -57,7 +57,7 @@ struct SolverScalars
   cg_alpha::NTuple{2,Float32}; cg_beta::NTuple{2,Float32}; cg_zeta::NTuple{2,Float32}
   admm_rk::NTuple{4,Float32}; admm_sk::NTuple{4,Float32}; admm_eps_pri::NTuple{4,Float32}
   admm_eps_dua::NTuple{4,Float32}; admm_delta::NTuple{4,Float32}; admm_rho::NTuple{4,Float32}
-  admm_sigma_abs::Float32; cg_iterations_last::Int32; cg_iterations_total::Int32; _pad::Int32
+  admm_sigma_abs::Float32; cg_iterations_last::Int32; cg_iterations_total::Int32; outer_iteration::Int32   # SplitBregman iter_cnt
 end
 
 # ---- context (one per device) -------------------------------------------------------------------
@@ -175,7 +175,7 @@ projmask(proj) = reduce(|, (p isa PositiveRegularization ? RLS_PROJ_POSITIVE : R
 const EMPTYREG = RegDesc(0, 0, 0.0, 1, 0, 0, ntuple(_ -> Int64(0), 4), ntuple(_ -> Int32(0), 4), 0, 0, 0f0, 0)
 
 const HANDLES = IdDict{Any,Ptr{Cvoid}}()
-function handle!(solver::FISTA, state)        # POGM / OptISTA / CGNR / ADMM are built the same way
+function handle!(solver::FISTA, state)        # POGM / OptISTA / CGNR / ADMM / SplitBregman are built the same way
   get!(HANDLES, solver) do
     d = SolverDesc(RLS_FISTA, solver.iterations, solver.restart == :gradient ? 1 : 0, projmask(solver.proj),
                    state.ρ, state.theta, 1f0, state.relTol, 0f0, 0f0, 0, 0, 1, 0,
