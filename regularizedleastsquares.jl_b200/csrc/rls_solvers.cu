@@ -521,6 +521,8 @@ __global__ void __launch_bounds__(EB) admm_term_grad_pix_kernel(const T* __restr
                                                                  const T* __restrict__ dz, const T* __restrict__ u, GradGeom G,
                                                                  DevState* S, int term, double* partials, unsigned* ticket) {
   if (S->done) return;
+  const bool sb = S->sb != 0;          // SplitBregman: ‖ρ Φ'(z - zᵒˡᵈ)‖ and ‖ρ Φ'u‖ with ρ inside the norm
+  const float rho_in = sb ? S->a_rho[term] : 1.f;
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   EW_LOOP(p, G.npix) {
     const T dx = Elem<T>::sub(x[p], xold[p]);
@@ -529,7 +531,9 @@ __global__ void __launch_bounds__(EB) admm_term_grad_pix_kernel(const T* __restr
       t1 = Elem<T>::add(grad_t_block(dz, G, k, p), t1);                  // Φ'(z - zᵒˡᵈ)
       t2 = Elem<T>::add(grad_t_block(u, G, k, p), t2);                   // Φ'u
     }
-    acc[0] += Elem<T>::abs2(dx); acc[3] += Elem<T>::abs2(t1); acc[7] += Elem<T>::abs2(t2);
+    acc[0] += Elem<T>::abs2(dx);
+    acc[3] += Elem<T>::abs2(sb ? Elem<T>::scale(t1, rho_in) : t1);
+    acc[7] += Elem<T>::abs2(sb ? Elem<T>::scale(t2, rho_in) : t2);
     xold[p] = t2;
   }
   grid_reduce_finalize<8, EB>(acc, partials, ticket, [=](double* t) { scalar_step(S, STEP_ADMM_TERM, term + 16, t); });
@@ -958,8 +962,14 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L, int phase = IT_ALL)
         const int* ogate = &S->sb_outer_gate;
         RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_CGC]->d, ogate));
         sb_outer_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_BETAY]), P<T>(L.v[V_Y]), P<T>(L.v[V_CGC]), n, S);
-        for (int i = 0; i < k; ++i)
-          sb_reset_term_kernel<T><<<ew_grid(c, s->rows[i]), EB, 0, st>>>(P<T>(L.v[V_TZ0 + i]), P<T>(L.v[V_TU0 + i]), P<T>(L.v[V_X]), s->rows[i], S);
+        for (int i = 0; i < k; ++i) {
+          if (s->desc.reg[i].trafo == RLS_TRAFO_GRADIENT) {                 // z = Φx ; u = 0   :261-262
+            RLS_TRY(rls_grad_fwd_launch(c, s->dtype, L.v[V_X]->d, L.v[V_TZ0 + i]->d, s->geom[i], ogate));
+            fill_gated_kernel<T><<<ew_grid(c, s->rows[i]), EB, 0, st>>>(P<T>(L.v[V_TU0 + i]), T{}, s->rows[i], ogate);
+          } else {
+            sb_reset_term_kernel<T><<<ew_grid(c, s->rows[i]), EB, 0, st>>>(P<T>(L.v[V_TZ0 + i]), P<T>(L.v[V_TU0 + i]), P<T>(L.v[V_X]), s->rows[i], S);
+          }
+        }
         scalar_kernel<<<1, 32, 0, st>>>(S, STEP_SB_FINISH, 0, gate);
         c->launches += 2 + k;
       }
@@ -1024,14 +1034,10 @@ static int32_t validate_desc(const rls_solver_desc* d) {
     const rls_reg_desc& r = d->reg[i];
     RLS_CHECK_ARG(r.kind >= RLS_REG_NONE && r.kind <= RLS_REG_TV, "unknown regularization kind %d", r.kind);
     RLS_CHECK_ARG(r.trafo == RLS_TRAFO_IDENTITY || r.trafo == RLS_TRAFO_GRADIENT, "unknown regTrafo %d", r.trafo);
-    if (r.trafo == RLS_TRAFO_GRADIENT && d->kind == RLS_SPLITBREGMAN) {
-      rls_set_error("SplitBregman with a GradientOp regTrafo is not on the accelerated path yet (identity regTrafo only)");
-      return RLS_ERR_UNSUPPORTED;
-    }
     if (r.trafo == RLS_TRAFO_GRADIENT) {
-      RLS_CHECK_ARG(d->kind == RLS_ADMM, "regTrafo is an ADMM keyword");
+      RLS_CHECK_ARG(admm_like(d->kind), "regTrafo is an ADMM / SplitBregman keyword");
       if (!rls_reg_is_elementwise(r.kind)) {
-        rls_set_error("ADMM with a GradientOp regTrafo supports elementwise prox (L1/L2) only");
+        rls_set_error("ADMM / SplitBregman with a GradientOp regTrafo support elementwise prox (L1/L2) only");
         return RLS_ERR_UNSUPPORTED;
       }
     }

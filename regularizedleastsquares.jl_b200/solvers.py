@@ -407,8 +407,8 @@ class ADMM(AbstractLinearSolver):
 
 class SplitBregman(ADMM):
     """SplitBregman(A; AHA, precon, reg, regTrafo, normalizeReg, rho, iterations, iterationsInner, iterationsCG,
-    absTol, relTol, tolInner, verbose)  SplitBregman.jl:80-146 (precon = Identity and identity regTrafo only on the
-    accelerated path).  `iterations` counts the outer (Bregman) iterations, `iterationsInner` the ADMM-like inner
+    absTol, relTol, tolInner, verbose)  SplitBregman.jl:80-146 (precon = Identity only; regTrafo = identity or
+    GradientOp, as for ADMM).  `iterations` counts the outer (Bregman) iterations, `iterationsInner` the ADMM-like inner
     ones; `state.iteration` restarts at every Bregman update, `iter_cnt` is `outer_iteration`."""
     name = "SplitBregman"
     _norm_after_init = False
@@ -431,8 +431,6 @@ class SplitBregman(ADMM):
         else:
             trafo = list(regTrafo) if isinstance(regTrafo, (list, tuple)) else [regTrafo]
         assert len(regs) == len(trafo), "reg and regTrafo must have the same length"      # SplitBregman.jl:108
-        if any(t is not None for t in trafo):
-            raise NotImplementedError("SplitBregman: a regTrafo other than the identity is not on the accelerated path yet")
         if not 1 <= len(regs) <= 4:
             raise ValueError("SplitBregman on this path takes 1..4 regularization terms")
         self.regTrafo = trafo

@@ -376,7 +376,7 @@ def test_row_major_fista_split_epilogue_and_projections(rls, ctx, regname, monke
 
 # ---------------------------------------------------------------- SplitBregman
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("case", ["l1", "l1_stops_early", "two_terms", "l21_split_prox"])
+@pytest.mark.parametrize("case", ["l1", "l1_stops_early", "two_terms", "l21_split_prox", "l1_gradient"])
 def test_split_bregman(rls, ctx, dtype, case):
     """SplitBregman.jl:203-289 against the oracle, iterate by iterate: inner ADMM-like iterations, the Bregman update
     of β_y every `iterationsInner` inner iterations (or at convergence), `iter_cnt`, stopping decisions and the
@@ -392,6 +392,9 @@ def test_split_bregman(rls, ctx, dtype, case):
         mk = lambda M: dict(reg=[M.L1Regularization(np.float32(1e-2)), M.L2Regularization(np.float32(5e-2)), M.RealRegularization()],
                             regTrafo=[None, None])
         kw.update(rho=[0.5, 0.25])
+    elif case == "l1_gradient":
+        # the formulation the docstring recommends for TV (SplitBregman.jl:74): L1 on the finite differences
+        mk = lambda M: dict(reg=M.L1Regularization(np.float32(1e-2)), regTrafo=M.GradientOp(dtype, shape=(12, 8)))
     else:
         mk = lambda M: dict(reg=M.L21Regularization(np.float32(5e-3), slices=8))
     S = rls.SplitBregman(A, **mk(rls), **kw)
