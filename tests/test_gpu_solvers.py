@@ -433,3 +433,29 @@ def test_split_bregman_reference_acceptance(rls, ctx):
                                rho=1.0, normalizeReg=rls.NoNormalization())
     xa = rls.solve_(S, b)
     assert np.linalg.norm(x - xa) <= 0.1 * np.linalg.norm(x)
+
+
+def test_callbacks_like_the_reference(rls, ctx):
+    """test/testCallbacks.jl:1-57 on the accelerated path: every callback fires iterations + 1 times, the last stored
+    solution is the returned one, the comparison improves, several callbacks can be combined."""
+    rng = np.random.default_rng(3)
+    A = rng.random((32, 32)).astype(np.float32); x = rng.random(32).astype(np.float32); b = A @ x
+    its = 10
+    S = rls.createLinearSolver(rls.CGNR, A, iterations=its, relTol=0.0)
+    cbk = rls.StoreSolutionCallback()
+    xa = rls.solve_(S, b, callbacks=cbk)
+    assert len(cbk.solutions) == its + 1 and np.array_equal(cbk.solutions[-1], xa)
+    cmp = rls.CompareSolutionCallback(x)
+    rls.solve_(S, b, callbacks=cmp)
+    assert len(cmp.results) == its + 1 and cmp.results[0] > cmp.results[-1]
+    conv = rls.StoreConvergenceCallback()
+    rls.solve_(S, b, callbacks=conv)
+    key = next(iter(conv.convMeas))
+    assert len(conv.convMeas[key]) == its + 1 and conv.convMeas[key][-1] == rls.solverconvergence(S)[key]
+    counter = []
+    rls.solve_(S, b, callbacks=lambda s, it: counter.append(it))
+    assert len(counter) == its + 1
+    both = [rls.StoreSolutionCallback(), rls.StoreConvergenceCallback()]
+    xa = rls.solve_(S, b, callbacks=both)
+    assert len(both[0].solutions) == its + 1 and np.array_equal(both[0].solutions[-1], xa)
+    assert len(both[1].convMeas[key]) == its + 1
