@@ -70,7 +70,7 @@ def c3():
         img[i:, j:] += np.float32(rng.standard_normal())
     xt = rls.B200Vector.from_numpy(img.ravel(order="F"), ctx)
     b = A.mul(xt)
-    outer = 10
+    outer = int(os.environ.get("C3_OUTER", "10"))
     S = rls.ADMM(A, reg=rls.TVRegularization(np.float32(1e-2), shape=(256, 256)), rho=0.1, iterations=outer, iterationsCG=10,
                  absTol=0.0, relTol=0.0)
     ms, done = timed_solve(S, b, 1)
