@@ -216,7 +216,7 @@ def test_admm_docstring_kat_float32(rls, ctx):
     assert rel(xg, R.solve(b.astype(np.float32))) < 1e-5
 
 
-@pytest.mark.parametrize("solver", ["FISTA", "CGNR", "ADMM", "POGM", "OptISTA"])
+@pytest.mark.parametrize("solver", ["FISTA", "CGNR", "ADMM", "POGM", "OptISTA", "SplitBregman"])
 @pytest.mark.parametrize("tensor_cores", [True, False])
 def test_multi_rhs(rls, ctx, solver, tensor_cores, monkeypatch):
     """test/testMultiThreading.jl: batched == sequential, and a vector solve still works afterwards.
@@ -232,10 +232,12 @@ def test_multi_rhs(rls, ctx, solver, tensor_cores, monkeypatch):
     kw = dict(iterations=30)
     if solver in ("FISTA", "POGM", "OptISTA"):
         kw.update(rho=rho_for(A), reg=rls.L1Regularization(np.float32(1e-4)))
+    if solver == "SplitBregman":
+        kw.update(iterations=3, iterationsInner=5)
     S = rls.createLinearSolver(getattr(rls, solver), A, **kw)
     Xb = rls.solve_(S, B)
     Xs = np.stack([rls.solve_(S, B[:, k].copy()) for k in range(5)], axis=1)
-    if tensor_cores and solver != "ADMM":
+    if tensor_cores and solver not in ("ADMM", "SplitBregman"):
         tol = 5e-5 if solver == "CGNR" else TOL
         assert max(rel(Xb[:, k], Xs[:, k]) for k in range(5)) < tol
         assert S.batch_iterations == [S.iteration] * 5 or solver == "CGNR"
