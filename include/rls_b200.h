@@ -45,7 +45,7 @@ enum {
 /* ---- element types: eltype(A) on the hot path (SURVEY 8b "Types") ------------ */
 enum { RLS_F32 = 0, RLS_C32 = 1 };
 
-/* ---- solver kinds: src/{FISTA,POGM,OptISTA,CGNR,ADMM,SplitBregman}.jl -------- */
+/* ---- solver kinds: src/{FISTA,POGM,OptISTA,CGNR,ADMM,SplitBregman}.jl (Kaczmarz: rls_kaczmarz_*) */
 enum { RLS_FISTA = 0, RLS_POGM = 1, RLS_OPTISTA = 2, RLS_CGNR = 3, RLS_ADMM = 4, RLS_SPLITBREGMAN = 5 };
 
 /* ---- regularisation sinks: src/proximalMaps/Prox{L1,L2,L21,TV}.jl ------------ */
@@ -86,6 +86,7 @@ typedef struct rls_mat_s* rls_mat_t;
 typedef struct rls_vec_s* rls_vec_t;
 typedef struct rls_normal_s* rls_normal_t;
 typedef struct rls_solver_s* rls_solver_t;
+typedef struct rls_kaczmarz_s* rls_kaczmarz_t;
 
 /* ============================ context ========================================= */
 int32_t rls_abi_version(void);
@@ -295,6 +296,30 @@ int32_t rls_solver_vec(rls_solver_t s, const char* name, rls_vec_t* out);
  * is active.  iterations_done[k] returns each column's count. */
 int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_host, int64_t ldb, int32_t K, void* X_host,
                                     int64_t ldx, int32_t* iterations_done);
+
+/* ---- Kaczmarz row-action solver (src/Kaczmarz.jl) ----------------- */
+/* The row loop of iterate(::Kaczmarz) (Kaczmarz.jl:270-273, row step :305-310) on a ROW-MAJOR device matrix, evaluated
+ * block-wise: for `block_rows` consecutive rows of the visiting order the projections are resolved exactly through the
+ * block Gram matrix A_blk A_blk^H (built once per order), so that one iteration is one HBM sweep over A instead of m
+ * dependent dot/axpy pairs.  The constructor logic (L2 / denom / rowindex / probabilities / row order, Kaczmarz.jl:73-159,
+ * :326-392) and the prox! calls after the sweep (:275-277, rls_prox_*) stay with the host, as in the reference.
+ * block_rows: 64, 128, 192, 256, or 0 = sized so that a block stays L2-resident. */
+int32_t rls_kaczmarz_create(rls_mat_t A, int32_t block_rows, rls_kaczmarz_t* out);
+int32_t rls_kaczmarz_destroy(rls_kaczmarz_t K);
+int32_t rls_kaczmarz_block_rows(rls_kaczmarz_t K, int32_t* block_rows);
+/* rownorm²(A, i) for all rows (Utils.jl:16-23; initkaczmarz Kaczmarz.jl:365-376, rowProbabilities :326-334) */
+int32_t rls_kaczmarz_rownorm2(rls_kaczmarz_t K, float* host, int64_t len);
+/* the visiting order of one iteration: rows[i] = rowindex[usedIndices[i]] (0-based, distinct), denom[i] as in
+ * Kaczmarz.jl:372.  Re-call after shuffle! (:201) or sample! (:268); rebuilds the block Gram matrices. */
+int32_t rls_kaczmarz_set_rows(rls_kaczmarz_t K, const int64_t* rows, const float* denom, int64_t count);
+/* init!(solver, state, b; x0): x = x0 (NULL = 0), vl = 0, u = b, eps_w = sqrt(λ) (Kaczmarz.jl:205-215) */
+int32_t rls_kaczmarz_init(rls_kaczmarz_t K, rls_vec_t b, rls_vec_t x0, float eps_w);
+/* `for i in usedIndices; iterate_row_index(...)` (Kaczmarz.jl:270-273); asynchronous on the context stream */
+int32_t rls_kaczmarz_sweep(rls_kaczmarz_t K);
+/* state vectors "x", "vl", "u" (borrowed handles) */
+int32_t rls_kaczmarz_vec(rls_kaczmarz_t K, const char* name, rls_vec_t* out);
+/* diagnostics: 0 = block Gram matrices, 1 = dot partials of the last block, 2 = alpha of the last block, 3 = denominators */
+int32_t rls_kaczmarz_debug(rls_kaczmarz_t K, int32_t which, float* host, int64_t nfloats);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ __all__ = [
     "PositiveRegularization", "RealRegularization", "NormalizedRegularization",
     "NoNormalization", "MeasurementBasedNormalization", "SystemMatrixBasedNormalization",
     "prox_", "reg_norm", "lam_of", "grad_op", "grad_op_t", "grad_t_axpy", "grad_rows", "cg", "power_iterations",
-    "NormalOp", "FISTA", "CGNR", "POGM", "OptISTA", "ADMM", "SplitBregman", "GradientOp",
+    "NormalOp", "FISTA", "CGNR", "POGM", "OptISTA", "ADMM", "SplitBregman", "Kaczmarz", "GradientOp",
     "createLinearSolver", "solve_", "normalize_factor", "enf_real", "enf_pos",
 ]
 
@@ -1066,6 +1066,144 @@ class SplitBregman(_Base):
 
     def convergence(self):
         return {"primal": self.rk.copy(), "dual": self.sk.copy()}
+
+
+class Kaczmarz(_Base):
+    """src/Kaczmarz.jl:73-317 (constructor :73-159, init! :178-216, iterate :264-283, row step :305-310,
+    initkaczmarz :365-392, rowProbabilities :326-334), src/Utils.jl:16-23 (rownorm²), :59-105 (dot_with_matrix_row),
+    Kaczmarz.jl:432-436 (kaczmarz_update!).  The greedy-randomised variant (:231-262, :394-428) is not restated
+    (the reference itself excludes it on GPU arrays, test/testKaczmarz.jl:114).
+
+    Row order: Julia's RNG stream cannot be reproduced, so ``shuffleRows`` / ``randomized`` draw from
+    ``numpy.random.default_rng(seed)`` — a permutation at init!, and per iteration a weighted sample without
+    replacement of ``subMatrixSize`` rows (StatsBase.sample! :267-269)."""
+    def __init__(self, A, *, reg=None, normalizeReg=None, randomized=False, subMatrixFraction=0.15, shuffleRows=False,
+                 seed=1234, iterations=10, greedy_randomized=False):
+        if greedy_randomized:
+            raise NotImplementedError("greedy randomised Kaczmarz is not restated")
+        A = np.asarray(A)
+        self.T = np.dtype(A.dtype)
+        rT = self.rT = real_type(self.T)
+        self.normalizeReg = NoNormalization() if normalizeReg is None else normalizeReg
+        regs = [L2Regularization(rT(0))] if reg is None else (list(reg) if isinstance(reg, (list, tuple)) else [reg])
+        f = normalize_factor(self.normalizeReg, A, None)                    # :82 (type-based: also SystemMatrixBased)
+        regs = [_normalize_reg(r, f) for r in regs]
+        l2 = [r for r in regs if isinstance(_sink(r), L2Regularization)]
+        if len(l2) > 1:
+            raise ValueError("Cannot unambigiously retrieve reg term of type L2Regularization")
+        self.L2 = l2[0] if l2 else L2Regularization(rT(0))                  # :83-89
+        rest = [r for r in regs if not isinstance(_sink(r), L2Regularization)]
+        lam = lam_of(self.L2)
+        if np.ndim(lam) > 0 and not isinstance(self.normalizeReg, (NoNormalization, SystemMatrixBasedNormalization)):
+            raise ValueError("Tikhonov matrix for Kaczmarz is only valid with no or system matrix based normalization")
+        other = [r for r in rest if _is_projection(_sink(r))]               # :95-97
+        rest = [r for r in rest if not _is_projection(_sink(r))]
+        if len(rest) == 1:
+            other.append(rest[0])
+        elif len(rest) > 1:
+            raise ValueError(f"Kaczmarz does not allow for more than one additional regularization term, found {len(rest)}")
+        self.reg = other
+        self.A, self.denom, self.rowindex = self._initkaczmarz(A, lam)      # :118
+        M, N = self.A.shape
+        self.randomized = bool(randomized); self.shuffleRows = bool(shuffleRows); self.seed = int(seed)
+        self.subMatrixSize = int(np.round(subMatrixFraction * M))           # :121 (round half to even, as Julia)
+        self.rowIndexCycle = np.arange(len(self.rowindex))
+        self.probabilities = self._row_probabilities() if self.randomized else None
+        self.usedIndices = np.zeros(self.subMatrixSize, np.int64) if self.randomized else self.rowIndexCycle
+        self.iterations = int(iterations)
+        self.u = np.zeros(M, self.T); self.x = np.zeros(N, self.T); self.vl = np.zeros(M, self.T)
+        self.eps_w = self.T.type(0); self.iteration = 0
+
+    # -- rownorm² (Utils.jl:16-23): sequential sum of abs2 in the real type
+    def _rownorm2(self, A):
+        rT = self.rT
+        a2 = (A.real.astype(rT) ** 2 + A.imag.astype(rT) ** 2) if np.iscomplexobj(A) else A.astype(rT) ** 2
+        return np.sum(a2, axis=1, dtype=rT)
+
+    def _initkaczmarz(self, A, lam):
+        """:365-392.  denom = T(1.0 / (s² + λ)): the quotient is formed in Float64 and stored in the real type."""
+        rT = self.rT
+        if np.ndim(lam) > 0:                                                # Tikhonov matrix :377-392
+            lam = np.asarray(lam).astype(rT)
+            A = (A * (rT(1) / np.sqrt(lam))[None, :]).astype(self.T)
+            lam = rT(1)
+        s2 = self._rownorm2(A)
+        keep = np.nonzero(s2 > 0)[0]
+        tot = s2[keep] + lam                                                # Float32 + Float32, or promoted by a Float64 λ
+        denom = (1.0 / tot.astype(np.float64)).astype(rT)
+        self._s2 = s2
+        return A, denom, keep
+
+    def _row_probabilities(self):
+        """:326-334 (Float64 accumulation vector, converted to T at :125)"""
+        s2 = self._s2
+        tot = self.rT(np.sum(s2, dtype=self.rT))
+        return (s2[self.rowindex].astype(np.float64) / np.float64(tot)).astype(self.rT)
+
+    def init(self, b, x0=0):
+        rT = self.rT
+        lam_prev = lam_of(self.L2)
+        if not isinstance(self.normalizeReg, SystemMatrixBasedNormalization):   # NormalizedRegularization.jl:84
+            f = normalize_factor(self.normalizeReg, self.A, b)
+            self.L2 = _normalize_reg(self.L2, f)
+            self.reg = [_normalize_reg(r, f) for r in self.reg]
+        lam = lam_of(self.L2)
+        if np.ndim(lam) == 0 and lam != lam_prev:                           # :186-193
+            _, self.denom, self.rowindex = self._initkaczmarz(self.A, lam)
+            self.rowIndexCycle = np.arange(len(self.rowindex))
+            if self.randomized:
+                self.probabilities = self._row_probabilities()
+        self._rng = np.random.default_rng(self.seed)                        # :195-197
+        if self.randomized:
+            self.usedIndices = np.zeros(self.subMatrixSize, np.int64)
+        elif self.shuffleRows:
+            self.rowIndexCycle = self._rng.permutation(self.rowIndexCycle)  # :201
+            self.usedIndices = self.rowIndexCycle
+        else:
+            self.usedIndices = self.rowIndexCycle
+        self.x = np.zeros(self.A.shape[1], self.T); self.x[...] = x0        # :206
+        self.vl = np.zeros(self.A.shape[0], self.T)
+        self.u = np.array(b, dtype=self.T, copy=True)
+        self.eps_w = self.T.type(1) if np.ndim(lam) > 0 else self.T.type(np.sqrt(lam))   # :210-214
+        self.iteration = 0
+
+    def done(self):
+        return self.iteration >= self.iterations                           # :315
+
+    def iterate(self):
+        if self.done():
+            return False
+        T = self.T.type
+        if self.randomized:                                                 # :267-269
+            p = self.probabilities.astype(np.float64)
+            self.usedIndices = self._rng.choice(len(self.rowIndexCycle), size=self.subMatrixSize, replace=False,
+                                                p=p / p.sum())
+        A = self.A
+        for i in self.usedIndices:                                          # :270-273
+            row = self.rowindex[i]
+            a = A[row]
+            tau = T(np.dot(a, self.x))                                      # dotu: no conjugation (Utils.jl:73-105)
+            alpha = T(self.denom[i] * (self.u[row] - tau - self.eps_w * self.vl[row]))   # :307
+            self.x += alpha * np.conj(a)                                    # :432-436
+            self.vl[row] += alpha * self.eps_w                              # :309
+        for r in self.reg:                                                  # :275-277
+            prox_(r, self.x)
+        self.iteration += 1
+        return True
+
+    def solution(self):
+        """solversolution :253-256: the Tikhonov-matrix form returns x ./ sqrt.(λ)"""
+        lam = lam_of(self.L2)
+        if np.ndim(lam) > 0:
+            return (self.x * (self.rT(1) / np.sqrt(np.asarray(lam).astype(self.rT)))).astype(self.T)
+        return self.x
+
+    def solve(self, b, callbacks=None, **kw):
+        super().solve(b, callbacks=callbacks, **kw)
+        return self.solution()
+
+    def convergence(self):
+        return {"residual": _norm2(self.A @ self.solution() - self.u)}
 
 
 def createLinearSolver(solver, A, **kw):

@@ -25,7 +25,7 @@ from .regularization import (AbstractParameterizedRegularization, AbstractProjec
                              NormalizedRegularization, PositiveRegularization, RealRegularization,
                              SystemMatrixBasedNormalization, TVRegularization, findsink, findsinks, lam, sink)
 from .prox import prox_  # noqa: E402
-from .solvers import (ADMM, CGNR, FISTA, POGM, OptISTA, SplitBregman, AbstractLinearSolver, createLinearSolver, init_, iterate,  # noqa: E402
+from .solvers import (ADMM, CGNR, FISTA, POGM, Kaczmarz, OptISTA, SplitBregman, AbstractLinearSolver, createLinearSolver, init_, iterate,  # noqa: E402
                       linearSolverList, solve_, solverconvergence, solversolution, solverstate)
 from .callbacks import CompareSolutionCallback, StoreConvergenceCallback, StoreSolutionCallback, nrmsd  # noqa: E402
 from . import dist  # noqa: E402

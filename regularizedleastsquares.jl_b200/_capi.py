@@ -138,6 +138,15 @@ SIGNATURES = {
     "rls_solver_scalars_get": [_P, C.POINTER(SolverScalars)],
     "rls_solver_vec": [_P, C.c_char_p, _PP],
     "rls_solver_solve_batch_host": [_P, _P, _I64, _I32, _P, _I64, _PI32],
+    "rls_kaczmarz_create": [_P, _I32, _PP],
+    "rls_kaczmarz_destroy": [_P],
+    "rls_kaczmarz_block_rows": [_P, _PI32],
+    "rls_kaczmarz_rownorm2": [_P, _P, _I64],
+    "rls_kaczmarz_set_rows": [_P, _P, _P, _I64],
+    "rls_kaczmarz_init": [_P, _P, _P, _F32],
+    "rls_kaczmarz_sweep": [_P],
+    "rls_kaczmarz_vec": [_P, C.c_char_p, _PP],
+    "rls_kaczmarz_debug": [_P, _I32, _P, _I64],
 }
 _SPECIAL = {"rls_abi_version": ([], _I32), "rls_last_error": ([], C.c_char_p)}
 

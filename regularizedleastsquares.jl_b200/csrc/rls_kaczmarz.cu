@@ -1,0 +1,629 @@
+// rls_kaczmarz.cu — the row loop of Kaczmarz (src/Kaczmarz.jl:264-283, row step :305-310) on a row-major system matrix.
+//
+// The reference visits the rows one after the other:
+//     tau   = dot_with_matrix_row(A, x, row)                    (Utils.jl:59-105, unconjugated)
+//     alpha = denom[i] * (u[row] - tau - eps_w * vl[row])       (Kaczmarz.jl:307)
+//     x    += alpha * conj(A[row, :])                           (Kaczmarz.jl:432-436)
+//     vl[row] += alpha * eps_w                                  (Kaczmarz.jl:309)
+// which on a GPU is one latency-bound dot + axpy per row.  The same recurrence in block form: for R consecutive
+// rows a_1..a_R (a block), with t = A_blk x taken BEFORE the block and the block Gram matrix G = A_blk A_blk^H,
+//     tau_j   = t_j + sum_{k<j} alpha_k G[j,k]
+//     alpha_j = denom_j * (u_j - tau_j - eps_w vl_j)
+//     x      += A_blk^H alpha
+// gives, in exact arithmetic, the very same iterates (G does not depend on x, so it is built once per row order).
+// Per block this is a whole-GPU streaming pass (t), a tiny triangular recurrence in one CTA, and a second pass over the
+// block that finds it in L2 (the block is sized for that): one HBM sweep over A per Kaczmarz iteration.
+//
+//   kz_dot_kernel     t partials: CTA = (column chunk, 8 rows), x chunk in registers, rows streamed with 128-bit loads
+//   kz_solve_kernel   one CTA of R threads: 32x32 diagonal blocks by warp shuffles, panels after one __syncthreads
+//   kz_update_kernel  x += sum_j alpha_j conj(a_j): thread = 4 floats of x, rows of the block from L2
+//   kz_gram_kernel    G = A_blk A_blk^H, 64x64 tiles on the FP32 pipes (lower triangle of tiles), once per row order
+//   kz_rownorm2_kernel  rownorm²(A, i) (Utils.jl:16-23) for denom / probabilities, which the host forms as the
+//                       reference does (initkaczmarz Kaczmarz.jl:365-376, rowProbabilities :326-334)
+#include "rls_common.cuh"
+
+#include <algorithm>
+#include <stdlib.h>
+
+struct rls_kaczmarz_s {
+  rls_ctx_s* ctx = nullptr;
+  rls_mat_s* A = nullptr;
+  int fpe = 1;
+  int R = 128;            // rows per block
+  int S = 1;              // column chunks of the dot kernel
+  bool vec4 = false;      // 128-bit loads possible
+  int64_t count = 0;      // rows in the current order
+  int64_t nblk = 0;
+  int32_t* d_rows = nullptr;   // [nblk * R], -1 = padding
+  float* d_denom = nullptr;    // [nblk * R]
+  float* d_G = nullptr;        // [nblk][R * R * fpe], element (k, j) at (j * R + k) * fpe
+  int64_t cap_blk = 0;
+  float* d_tpart = nullptr;    // [S][R][fpe]
+  float* d_alpha = nullptr;    // [R][fpe]
+  float* d_s2 = nullptr;       // [m]
+  rls_vec_s *x = nullptr, *vl = nullptr, *u = nullptr;
+  float eps_w = 0.f;
+  bool initialised = false;
+};
+
+namespace {
+
+constexpr int KZ_DOT_THREADS = 256;
+constexpr int KZ_DOT_LPT = 4;   // loads per thread and row
+constexpr int KZ_DOT_RG = 8;    // rows per CTA
+constexpr int KZ_UPD_THREADS = 64;
+constexpr int KZ_MAX_R = 256;
+
+template <int NF> struct PackT;
+template <> struct PackT<1> { using type = float; };
+template <> struct PackT<2> { using type = float2; };
+template <> struct PackT<4> { using type = float4; };
+
+template <int NF>
+__device__ __forceinline__ void ld_pack(const float* __restrict__ p, float (&v)[NF]) {
+  using P = typename PackT<NF>::type;
+  P q = __ldg(reinterpret_cast<const P*>(p));
+  const float* f = reinterpret_cast<const float*>(&q);
+#pragma unroll
+  for (int i = 0; i < NF; ++i) v[i] = f[i];
+}
+// L2-coherent load (data written by an earlier kernel of the same chain: x, partials, alpha)
+template <int NF>
+__device__ __forceinline__ void ld_pack_cg(const float* p, float (&v)[NF]) {
+  using P = typename PackT<NF>::type;
+  P q = __ldcg(reinterpret_cast<const P*>(p));
+  const float* f = reinterpret_cast<const float*>(&q);
+#pragma unroll
+  for (int i = 0; i < NF; ++i) v[i] = f[i];
+}
+template <int NF>
+__device__ __forceinline__ void ld_pack_stream(const float* __restrict__ p, float (&v)[NF]) {
+  using P = typename PackT<NF>::type;
+  P q = __ldcs(reinterpret_cast<const P*>(p));
+  const float* f = reinterpret_cast<const float*>(&q);
+#pragma unroll
+  for (int i = 0; i < NF; ++i) v[i] = f[i];
+}
+
+__device__ __forceinline__ void st_pack(float* p, const float (&v)[1]) { *p = v[0]; }
+__device__ __forceinline__ void st_pack(float* p, const float (&v)[2]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+__device__ __forceinline__ void st_pack(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// acc += a . x (unconjugated) over one pack
+template <int FPE, int NF>
+__device__ __forceinline__ void dot_acc(const float (&a)[NF], const float (&x)[NF], float (&acc)[FPE]) {
+  if constexpr (FPE == 1) {
+#pragma unroll
+    for (int i = 0; i < NF; ++i) acc[0] = fmaf(a[i], x[i], acc[0]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NF; i += 2) {
+      acc[0] = fmaf(a[i], x[i], acc[0]);
+      acc[0] = fmaf(-a[i + 1], x[i + 1], acc[0]);
+      acc[1] = fmaf(a[i], x[i + 1], acc[1]);
+      acc[1] = fmaf(a[i + 1], x[i], acc[1]);
+    }
+  }
+}
+
+// acc += al * conj(a) over one pack
+template <int FPE, int NF>
+__device__ __forceinline__ void upd_acc(const float (&al)[FPE], const float (&a)[NF], float (&acc)[NF]) {
+  if constexpr (FPE == 1) {
+#pragma unroll
+    for (int i = 0; i < NF; ++i) acc[i] = fmaf(al[0], a[i], acc[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NF; i += 2) {
+      acc[i] = fmaf(al[0], a[i], acc[i]);
+      acc[i] = fmaf(al[1], a[i + 1], acc[i]);
+      acc[i + 1] = fmaf(al[1], a[i], acc[i + 1]);
+      acc[i + 1] = fmaf(-al[0], a[i + 1], acc[i + 1]);
+    }
+  }
+}
+
+// c += al * g (complex or real product)
+template <int FPE>
+__device__ __forceinline__ void mul_acc(const float (&al)[FPE], const float (&g)[FPE], float (&c)[FPE]) {
+  if constexpr (FPE == 1) {
+    c[0] = fmaf(al[0], g[0], c[0]);
+  } else {
+    c[0] = fmaf(al[0], g[0], c[0]);
+    c[0] = fmaf(-al[1], g[1], c[0]);
+    c[1] = fmaf(al[0], g[1], c[1]);
+    c[1] = fmaf(al[1], g[0], c[1]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rownorm²(A, i): one CTA per row
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kz_rownorm2_kernel(const float* __restrict__ A, int64_t ldf, int64_t nfl, int64_t m,
+                                                          float* __restrict__ s2) {
+  __shared__ float s_w[8];
+  for (int64_t row = blockIdx.x; row < m; row += gridDim.x) {
+    const float* a = A + row * ldf;
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < nfl; i += 256) { float v = __ldg(a + i); acc = fmaf(v, v, acc); }
+    acc = warp_sum(acc);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_w[w];
+      s2[row] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// t = A_blk x, split over column chunks: tpart[(s * R + j) * FPE + c]
+// ---------------------------------------------------------------------------------------------------------------
+template <int FPE, int NF>
+__global__ void __launch_bounds__(KZ_DOT_THREADS) kz_dot_kernel(const float* __restrict__ A, int64_t ldf, int64_t nfl,
+                                                                const int32_t* __restrict__ rows, int R,
+                                                                const float* x, float* __restrict__ tpart) {
+  pdl_prologue();
+  constexpr int LPT = KZ_DOT_LPT, RG = KZ_DOT_RG, NW = KZ_DOT_THREADS / 32;
+  __shared__ float s_red[NW][RG * FPE];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t chunk0 = (int64_t)blockIdx.x * (KZ_DOT_THREADS * LPT * NF);
+  int64_t idx[LPT];
+  float xr[LPT][NF];
+#pragma unroll
+  for (int l = 0; l < LPT; ++l) {
+    idx[l] = chunk0 + ((int64_t)l * KZ_DOT_THREADS + tid) * NF;
+    if (idx[l] < nfl) ld_pack_cg<NF>(x + idx[l], xr[l]);
+    else {
+#pragma unroll
+      for (int i = 0; i < NF; ++i) xr[l][i] = 0.f;
+    }
+  }
+  const int j0 = blockIdx.y * RG;
+  float acc[RG][FPE];
+#pragma unroll
+  for (int r = 0; r < RG; ++r)
+#pragma unroll
+    for (int c = 0; c < FPE; ++c) acc[r][c] = 0.f;
+#pragma unroll
+  for (int r = 0; r < RG; r += 2) {
+    float a[2][LPT][NF];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int j = j0 + r + q;
+      const int row = j < R ? rows[j] : -1;
+      const float* ap = A + (int64_t)(row < 0 ? 0 : row) * ldf;
+#pragma unroll
+      for (int l = 0; l < LPT; ++l) {
+        if (row >= 0 && idx[l] < nfl) ld_pack<NF>(ap + idx[l], a[q][l]);   // stays in L2 for the update pass
+        else {
+#pragma unroll
+          for (int i = 0; i < NF; ++i) a[q][l][i] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int l = 0; l < LPT; ++l) dot_acc<FPE, NF>(a[q][l], xr[l], acc[r + q]);
+  }
+#pragma unroll
+  for (int r = 0; r < RG; ++r)
+#pragma unroll
+    for (int c = 0; c < FPE; ++c) {
+      float w = warp_sum(acc[r][c]);
+      if (lane == 0) s_red[warp][r * FPE + c] = w;
+    }
+  __syncthreads();
+  if (tid < RG * FPE) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += s_red[w][tid];
+    const int r = tid / FPE, c = tid % FPE;
+    const int j = j0 + r;
+    if (j < R) tpart[((int64_t)blockIdx.x * R + j) * FPE + c] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the triangular recurrence of one block; blockDim.x == R (multiple of 32, <= 256)
+// ---------------------------------------------------------------------------------------------------------------
+template <int FPE>
+__global__ void __launch_bounds__(KZ_MAX_R) kz_solve_kernel(const int32_t* __restrict__ rows, const float* __restrict__ denom,
+                                                            const float* __restrict__ G, int R,
+                                                            const float* tpart, int S,
+                                                            const float* u, float* vl, float ew,
+                                                            float* __restrict__ alpha_out) {
+  pdl_prologue();
+  __shared__ float s_alpha[KZ_MAX_R * FPE];
+  const int k = threadIdx.x, lane = k & 31, warp = k >> 5;
+  const int row = rows[k];
+  const float d = row >= 0 ? denom[k] : 0.f;
+  float t[FPE], uu[FPE], vv[FPE], c[FPE], mine[FPE];
+#pragma unroll
+  for (int q = 0; q < FPE; ++q) { t[q] = 0.f; c[q] = 0.f; mine[q] = 0.f; uu[q] = 0.f; vv[q] = 0.f; }
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int q = 0; q < FPE; ++q) t[q] += __ldcg(tpart + ((int64_t)s * R + k) * FPE + q);
+  if (row >= 0) {
+#pragma unroll
+    for (int q = 0; q < FPE; ++q) { uu[q] = __ldcg(u + (int64_t)row * FPE + q); vv[q] = __ldcg(vl + (int64_t)row * FPE + q); }
+  }
+  const int nb = R >> 5;
+  for (int jb = 0; jb < nb; ++jb) {
+    const int j0 = jb << 5;
+    if (warp == jb) {
+      float g[32][FPE];
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj)
+#pragma unroll
+        for (int q = 0; q < FPE; ++q) g[jj][q] = __ldg(G + ((int64_t)(j0 + jj) * R + k) * FPE + q);
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        float al[FPE];
+#pragma unroll
+        for (int q = 0; q < FPE; ++q) {
+          // alpha = denom * ((u - tau) - eps_w * vl), tau = t + c   (Kaczmarz.jl:307)
+          float tau = fadd(t[q], c[q]);
+          float a_ = fmul(d, fsub(fsub(uu[q], tau), fmul(ew, vv[q])));
+          al[q] = __shfl_sync(0xffffffffu, a_, jj);
+        }
+        if (lane > jj) mul_acc<FPE>(al, g[jj], c);
+        if (lane == jj) {
+#pragma unroll
+          for (int q = 0; q < FPE; ++q) mine[q] = al[q];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < FPE; ++q) {
+        s_alpha[k * FPE + q] = mine[q];
+        alpha_out[k * FPE + q] = mine[q];
+        if (row >= 0) vl[(int64_t)row * FPE + q] = fadd(vv[q], fmul(mine[q], ew));   // Kaczmarz.jl:309
+      }
+    }
+    __syncthreads();
+    if (k >= j0 + 32) {
+#pragma unroll 8
+      for (int jj = 0; jj < 32; ++jj) {
+        float al[FPE], g[FPE];
+#pragma unroll
+        for (int q = 0; q < FPE; ++q) {
+          al[q] = s_alpha[(j0 + jj) * FPE + q];
+          g[q] = __ldg(G + ((int64_t)(j0 + jj) * R + k) * FPE + q);
+        }
+        mul_acc<FPE>(al, g, c);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// x += sum_j alpha_j conj(a_j)
+// ---------------------------------------------------------------------------------------------------------------
+template <int FPE, int NF>
+__global__ void __launch_bounds__(KZ_UPD_THREADS) kz_update_kernel(const float* __restrict__ A, int64_t ldf, int64_t nfl,
+                                                                   const int32_t* __restrict__ rows, int R,
+                                                                   const float* alpha, float* x) {
+  pdl_prologue();
+  __shared__ float s_al[KZ_MAX_R * FPE];
+  __shared__ int s_row[KZ_MAX_R];
+  for (int i = threadIdx.x; i < R; i += KZ_UPD_THREADS) {
+    s_row[i] = rows[i];
+#pragma unroll
+    for (int q = 0; q < FPE; ++q) s_al[i * FPE + q] = __ldcg(alpha + i * FPE + q);
+  }
+  __syncthreads();
+  const int64_t idx = ((int64_t)blockIdx.x * KZ_UPD_THREADS + threadIdx.x) * NF;
+  if (idx >= nfl) return;
+  float acc[NF];
+#pragma unroll
+  for (int i = 0; i < NF; ++i) acc[i] = 0.f;
+  constexpr int U = 8;
+  for (int j0 = 0; j0 < R; j0 += U) {   // R is a multiple of 32
+    float a[U][NF];
+#pragma unroll
+    for (int r = 0; r < U; ++r) {
+      const int row = s_row[j0 + r];
+      if (row >= 0) ld_pack_stream<NF>(A + (int64_t)row * ldf + idx, a[r]);   // last use of the block
+      else {
+#pragma unroll
+        for (int i = 0; i < NF; ++i) a[r][i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < U; ++r) {
+      float al[FPE];
+#pragma unroll
+      for (int q = 0; q < FPE; ++q) al[q] = s_al[(j0 + r) * FPE + q];
+      upd_acc<FPE, NF>(al, a[r], acc);
+    }
+  }
+  float xv[NF];
+  ld_pack_cg<NF>(x + idx, xv);
+#pragma unroll
+  for (int i = 0; i < NF; ++i) xv[i] += acc[i];
+  st_pack(x + idx, xv);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// G = A_blk A_blk^H per block: 64x64 tiles (lower triangle of tiles), 256 threads, 4x4 outputs per thread
+// ---------------------------------------------------------------------------------------------------------------
+template <int FPE>
+__global__ void __launch_bounds__(256) kz_gram_kernel(const float* __restrict__ A, int64_t ldf, int64_t n,
+                                                      const int32_t* __restrict__ rows_all, int R, float* __restrict__ G_all,
+                                                      int64_t blk0) {
+  constexpr int TS = 64, KC = 16, LD = TS * FPE + 4;
+  __shared__ float As[KC][LD];
+  __shared__ float Bs[KC][LD];
+  const int64_t b = blk0 + blockIdx.y;
+  const int32_t* rows = rows_all + b * R;
+  float* G = G_all + b * (int64_t)R * R * FPE;
+  int t = blockIdx.x, ti = 0;
+  while (t >= ti + 1) { t -= ti + 1; ++ti; }
+  const int tj = t;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+  const int rowA = rows[ti * TS + lr], rowB = rows[tj * TS + lr];
+  const float* pa = A + (int64_t)(rowA < 0 ? 0 : rowA) * ldf;
+  const float* pb = A + (int64_t)(rowB < 0 ? 0 : rowB) * ldf;
+  float acc[4][4][FPE];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < FPE; ++q) acc[i][j][q] = 0.f;
+  for (int64_t k0 = 0; k0 < n; k0 += KC) {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const int64_t kk = k0 + lk + q4;
+#pragma unroll
+      for (int q = 0; q < FPE; ++q) {
+        As[lk + q4][lr * FPE + q] = (rowA >= 0 && kk < n) ? __ldg(pa + kk * FPE + q) : 0.f;
+        Bs[lk + q4][lr * FPE + q] = (rowB >= 0 && kk < n) ? __ldg(pb + kk * FPE + q) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      float a[4][FPE], bb[4][FPE];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < FPE; ++q) {
+          a[i][q] = As[kk][(ty * 4 + i) * FPE + q];
+          bb[i][q] = Bs[kk][(tx * 4 + i) * FPE + q];
+        }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (FPE == 1) {
+            acc[i][j][0] = fmaf(a[i][0], bb[j][0], acc[i][j][0]);
+          } else {   // a * conj(b)
+            acc[i][j][0] = fmaf(a[i][0], bb[j][0], acc[i][j][0]);
+            acc[i][j][0] = fmaf(a[i][1], bb[j][1], acc[i][j][0]);
+            acc[i][j][1] = fmaf(a[i][1], bb[j][0], acc[i][j][1]);
+            acc[i][j][1] = fmaf(-a[i][0], bb[j][1], acc[i][j][1]);
+          }
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kr = ti * TS + ty * 4 + i, jc = tj * TS + tx * 4 + j;
+#pragma unroll
+      for (int q = 0; q < FPE; ++q) G[((int64_t)jc * R + kr) * FPE + q] = acc[i][j][q];
+    }
+}
+
+void kz_free(rls_kaczmarz_s* K) {
+  if (!K) return;
+  cudaFree(K->d_rows); cudaFree(K->d_denom); cudaFree(K->d_G); cudaFree(K->d_tpart); cudaFree(K->d_alpha); cudaFree(K->d_s2);
+  if (K->x) rls_vec_destroy(K->x);
+  if (K->vl) rls_vec_destroy(K->vl);
+  if (K->u) rls_vec_destroy(K->u);
+  delete K;
+}
+
+}  // namespace
+
+extern "C" int32_t rls_kaczmarz_create(rls_mat_t A, int32_t block_rows, rls_kaczmarz_t* out) {
+  RLS_CHECK_ARG(A && out, "NULL argument");
+  if (A->layout != RLS_LAYOUT_ROWMAJOR) {
+    rls_set_error("Kaczmarz needs the row-major device layout (create the matrix with RLS_LAYOUT_ROWMAJOR)");
+    return RLS_ERR_UNSUPPORTED;
+  }
+  RLS_CHECK_ARG(A->m > 0 && A->n > 0, "Kaczmarz: empty matrix");
+  RLS_CHECK_ARG(A->m < (int64_t)1 << 31, "Kaczmarz: more than 2^31 rows");
+  rls_ctx_s* c = A->ctx;
+  RlsDeviceGuard g(c->device);
+  const int fpe = A->dtype == RLS_C32 ? 2 : 1;
+  int R = block_rows;
+  if (const char* e = getenv("RLS_KACZMARZ_BLOCK")) { if (R <= 0 && atoi(e) > 0) R = atoi(e); }
+  if (R <= 0) {
+    // a block should stay L2-resident between its two passes: <= 32 MB
+    const int64_t row_bytes = A->n * (int64_t)fpe * 4;
+    int64_t r = (32ll << 20) / (row_bytes > 0 ? row_bytes : 1);
+    R = r >= 256 ? 256 : r >= 128 ? 128 : 64;
+  }
+  RLS_CHECK_ARG(R == 64 || R == 128 || R == 192 || R == 256, "Kaczmarz: block_rows must be 64, 128, 192 or 256 (got %d)", R);
+  rls_kaczmarz_s* K = new rls_kaczmarz_s();
+  K->ctx = c; K->A = A; K->fpe = fpe; K->R = R;
+  const int64_t nfl = A->n * fpe, ldf = A->ld * fpe;
+  K->vec4 = (nfl % 4 == 0) && (ldf % 4 == 0) && (((uintptr_t)A->d) % 16 == 0);
+  const int nf = K->vec4 ? 4 : fpe;
+  K->S = (int)((nfl + (int64_t)KZ_DOT_THREADS * KZ_DOT_LPT * nf - 1) / ((int64_t)KZ_DOT_THREADS * KZ_DOT_LPT * nf));
+  int32_t st = RLS_OK;
+  do {
+    if (cudaMalloc(&K->d_tpart, (size_t)K->S * R * fpe * 4) != cudaSuccess || cudaMalloc(&K->d_alpha, (size_t)R * fpe * 4) != cudaSuccess ||
+        cudaMalloc(&K->d_s2, (size_t)A->m * 4) != cudaSuccess) {
+      rls_set_error("Kaczmarz: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+      st = RLS_ERR_NOMEM; break;
+    }
+    if ((st = rls_vec_create_internal(c, A->dtype, A->n, &K->x)) != RLS_OK) break;
+    if ((st = rls_vec_create_internal(c, A->dtype, A->m, &K->vl)) != RLS_OK) break;
+    if ((st = rls_vec_create_internal(c, A->dtype, A->m, &K->u)) != RLS_OK) break;
+    int64_t grid = A->m < (int64_t)c->sm_count * 8 ? A->m : (int64_t)c->sm_count * 8;
+    kz_rownorm2_kernel<<<(unsigned)grid, 256, 0, c->stream>>>((const float*)A->d, ldf, nfl, A->m, K->d_s2);
+    c->launches++;
+    if (cudaGetLastError() != cudaSuccess) { rls_set_error("Kaczmarz: rownorm2 launch failed"); st = RLS_ERR_CUDA; break; }
+  } while (0);
+  if (st != RLS_OK) { kz_free(K); return st; }
+  *out = K;
+  return RLS_OK;
+}
+
+extern "C" int32_t rls_kaczmarz_destroy(rls_kaczmarz_t K) {
+  if (!K) return RLS_OK;
+  RlsDeviceGuard g(K->ctx->device);
+  cudaStreamSynchronize(K->ctx->stream);
+  kz_free(K);
+  return RLS_OK;
+}
+
+extern "C" int32_t rls_kaczmarz_block_rows(rls_kaczmarz_t K, int32_t* block_rows) {
+  RLS_CHECK_ARG(K && block_rows, "NULL argument");
+  *block_rows = K->R;
+  return RLS_OK;
+}
+
+extern "C" int32_t rls_kaczmarz_rownorm2(rls_kaczmarz_t K, float* host, int64_t len) {
+  RLS_CHECK_ARG(K && host, "NULL argument");
+  RLS_CHECK_ARG(len == K->A->m, "rownorm2: expected %lld values", (long long)K->A->m);
+  RlsDeviceGuard g(K->ctx->device);
+  RLS_CUDA(cudaMemcpyAsync(host, K->d_s2, (size_t)len * 4, cudaMemcpyDeviceToHost, K->ctx->stream));
+  RLS_CUDA(cudaStreamSynchronize(K->ctx->stream));
+  return RLS_OK;
+}
+
+extern "C" int32_t rls_kaczmarz_set_rows(rls_kaczmarz_t K, const int64_t* rows, const float* denom, int64_t count) {
+  RLS_CHECK_ARG(K && (count == 0 || (rows && denom)), "NULL argument");
+  RLS_CHECK_ARG(count >= 0, "negative count");
+  rls_ctx_s* c = K->ctx;
+  RlsDeviceGuard g(c->device);
+  const int R = K->R, fpe = K->fpe;
+  const int64_t m = K->A->m;
+  const int64_t nblk = (count + R - 1) / R;
+  std::vector<int32_t> hr((size_t)(nblk * R), -1);
+  std::vector<float> hd((size_t)(nblk * R), 0.f);
+  std::vector<uint8_t> seen((size_t)m, 0);
+  for (int64_t i = 0; i < count; ++i) {
+    RLS_CHECK_ARG(rows[i] >= 0 && rows[i] < m, "set_rows: row %lld out of range", (long long)rows[i]);
+    RLS_CHECK_ARG(!seen[(size_t)rows[i]], "set_rows: row %lld listed twice", (long long)rows[i]);
+    seen[(size_t)rows[i]] = 1;
+    hr[(size_t)i] = (int32_t)rows[i];
+    hd[(size_t)i] = denom[i];
+  }
+  RLS_CUDA(cudaStreamSynchronize(c->stream));   // a sweep may still be reading the previous order
+  if (nblk > K->cap_blk) {
+    cudaFree(K->d_rows); cudaFree(K->d_denom); cudaFree(K->d_G);
+    K->d_rows = nullptr; K->d_denom = nullptr; K->d_G = nullptr; K->cap_blk = 0;
+    if (cudaMalloc(&K->d_rows, (size_t)nblk * R * 4) != cudaSuccess || cudaMalloc(&K->d_denom, (size_t)nblk * R * 4) != cudaSuccess ||
+        cudaMalloc(&K->d_G, (size_t)nblk * R * R * fpe * 4) != cudaSuccess) {
+      rls_set_error("Kaczmarz: cudaMalloc of the block Gram matrices failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return RLS_ERR_NOMEM;
+    }
+    K->cap_blk = nblk;
+  }
+  K->count = count; K->nblk = nblk;
+  if (nblk == 0) return RLS_OK;
+  RLS_CUDA(cudaMemcpyAsync(K->d_rows, hr.data(), hr.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  RLS_CUDA(cudaMemcpyAsync(K->d_denom, hd.data(), hd.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  RLS_CUDA(cudaStreamSynchronize(c->stream));   // hr / hd are pageable and die with this call
+  RLS_CUDA(cudaMemsetAsync(K->d_G, 0, (size_t)nblk * R * R * fpe * 4, c->stream));
+  const int T = R / 64;
+  const int64_t ldf = K->A->ld * fpe;
+  for (int64_t b0 = 0; b0 < nblk; b0 += 32768) {
+    const int64_t nb = std::min<int64_t>(32768, nblk - b0);
+    dim3 grid((unsigned)(T * (T + 1) / 2), (unsigned)nb);
+    if (fpe == 2) kz_gram_kernel<2><<<grid, 256, 0, c->stream>>>((const float*)K->A->d, ldf, K->A->n, K->d_rows, R, K->d_G, b0);
+    else kz_gram_kernel<1><<<grid, 256, 0, c->stream>>>((const float*)K->A->d, ldf, K->A->n, K->d_rows, R, K->d_G, b0);
+    c->launches++;
+  }
+  RLS_CUDA(cudaGetLastError());
+  return RLS_OK;
+}
+
+extern "C" int32_t rls_kaczmarz_init(rls_kaczmarz_t K, rls_vec_t b, rls_vec_t x0, float eps_w) {
+  RLS_CHECK_ARG(K && b, "NULL argument");
+  RLS_CHECK_ARG(b->dtype == K->A->dtype && b->len == K->A->m, "Kaczmarz init: b must have %lld elements of the matrix type", (long long)K->A->m);
+  RLS_CHECK_ARG(!x0 || (x0->dtype == K->A->dtype && x0->len == K->A->n), "Kaczmarz init: x0 must have %lld elements", (long long)K->A->n);
+  rls_ctx_s* c = K->ctx;
+  RlsDeviceGuard g(c->device);
+  const size_t es = rls_elem_size(K->A->dtype);
+  if (x0) RLS_CUDA(cudaMemcpyAsync(K->x->d, x0->d, (size_t)K->A->n * es, cudaMemcpyDeviceToDevice, c->stream));
+  else RLS_CUDA(cudaMemsetAsync(K->x->d, 0, (size_t)K->A->n * es, c->stream));
+  RLS_CUDA(cudaMemsetAsync(K->vl->d, 0, (size_t)K->A->m * es, c->stream));
+  RLS_CUDA(cudaMemcpyAsync(K->u->d, b->d, (size_t)K->A->m * es, cudaMemcpyDeviceToDevice, c->stream));
+  K->eps_w = eps_w;
+  K->initialised = true;
+  return RLS_OK;
+}
+
+template <int FPE, int NF>
+static int32_t kz_sweep_impl(rls_kaczmarz_s* K) {
+  rls_ctx_s* c = K->ctx;
+  const int R = K->R;
+  const int64_t nfl = K->A->n * FPE, ldf = K->A->ld * FPE;
+  const float* A = (const float*)K->A->d;
+  float* x = (float*)K->x->d;
+  const dim3 gdot((unsigned)K->S, (unsigned)((R + KZ_DOT_RG - 1) / KZ_DOT_RG));
+  const int64_t packs = (nfl + NF - 1) / NF;
+  const dim3 gupd((unsigned)((packs + KZ_UPD_THREADS - 1) / KZ_UPD_THREADS));
+  for (int64_t b = 0; b < K->nblk; ++b) {
+    const int32_t* rows = K->d_rows + b * R;
+    RLS_CUDA(rls_launch_pdl(c->stream, gdot, dim3(KZ_DOT_THREADS), kz_dot_kernel<FPE, NF>, A, ldf, nfl, rows, R, (const float*)x, K->d_tpart));
+    RLS_CUDA(rls_launch_pdl(c->stream, dim3(1), dim3(R), kz_solve_kernel<FPE>, rows, (const float*)(K->d_denom + b * R),
+                            (const float*)(K->d_G + b * (int64_t)R * R * FPE), R, (const float*)K->d_tpart, K->S, (const float*)K->u->d,
+                            (float*)K->vl->d, K->eps_w, K->d_alpha));
+    RLS_CUDA(rls_launch_pdl(c->stream, gupd, dim3(KZ_UPD_THREADS), kz_update_kernel<FPE, NF>, A, ldf, nfl, rows, R, (const float*)K->d_alpha, x));
+    c->launches += 3;
+  }
+  return RLS_OK;
+}
+
+extern "C" int32_t rls_kaczmarz_sweep(rls_kaczmarz_t K) {
+  RLS_CHECK_ARG(K, "NULL argument");
+  RLS_CHECK_ARG(K->initialised, "Kaczmarz sweep before init");
+  RlsDeviceGuard g(K->ctx->device);
+  if (K->fpe == 2) return K->vec4 ? kz_sweep_impl<2, 4>(K) : kz_sweep_impl<2, 2>(K);
+  return K->vec4 ? kz_sweep_impl<1, 4>(K) : kz_sweep_impl<1, 1>(K);
+}
+
+extern "C" int32_t rls_kaczmarz_vec(rls_kaczmarz_t K, const char* name, rls_vec_t* out) {
+  RLS_CHECK_ARG(K && name && out, "NULL argument");
+  if (!strcmp(name, "x")) *out = K->x;
+  else if (!strcmp(name, "vl")) *out = K->vl;
+  else if (!strcmp(name, "u")) *out = K->u;
+  else { rls_set_error("Kaczmarz state has no vector '%s' (x, vl, u)", name); return RLS_ERR_INVALID; }
+  return RLS_OK;
+}
+
+// diagnostics: 0 = block Gram matrices [nblk][R*R*fpe], 1 = dot partials of the last block [S][R][fpe],
+// 2 = alpha of the last block [R][fpe], 3 = padded denominators [nblk*R]
+extern "C" int32_t rls_kaczmarz_debug(rls_kaczmarz_t K, int32_t which, float* host, int64_t nfloats) {
+  RLS_CHECK_ARG(K && host, "NULL argument");
+  RlsDeviceGuard g(K->ctx->device);
+  const float* src = nullptr;
+  int64_t have = 0;
+  switch (which) {
+    case 0: src = K->d_G; have = K->nblk * (int64_t)K->R * K->R * K->fpe; break;
+    case 1: src = K->d_tpart; have = (int64_t)K->S * K->R * K->fpe; break;
+    case 2: src = K->d_alpha; have = (int64_t)K->R * K->fpe; break;
+    case 3: src = K->d_denom; have = K->nblk * (int64_t)K->R; break;
+    default: rls_set_error("kaczmarz_debug: which = %d", which); return RLS_ERR_INVALID;
+  }
+  RLS_CHECK_ARG(nfloats <= have, "kaczmarz_debug: %lld floats requested, %lld available", (long long)nfloats, (long long)have);
+  RLS_CUDA(cudaMemcpyAsync(host, src, (size_t)nfloats * 4, cudaMemcpyDeviceToHost, K->ctx->stream));
+  RLS_CUDA(cudaStreamSynchronize(K->ctx->stream));
+  return RLS_OK;
+}

@@ -458,9 +458,221 @@ class SplitBregman(ADMM):
         return self._scalars.outer_iteration
 
 
+class Kaczmarz(AbstractLinearSolver):
+    """Kaczmarz(A; reg, normalizeReg, randomized, subMatrixFraction, shuffleRows, seed, iterations)  Kaczmarz.jl:73-159
+
+    The constructor / init! bookkeeping of the reference stays here (L2 term and Tikhonov matrix :83-93, denom and
+    rowindex :365-392, probabilities :326-334, row order :195-203, prox! after each sweep :275-277); the row loop
+    (:270-273) runs in librls_b200 (csrc/rls_kaczmarz.cu) on a row-major device matrix.  Not accelerated:
+    greedy_randomized (the reference excludes it on GPU arrays too, test/testKaczmarz.jl:114) and a communicator
+    (the row loop is sequential; it does not shard).
+
+    Row order: Julia's RNG stream cannot be reproduced; shuffleRows / randomized draw from
+    numpy.random.default_rng(seed) — a permutation at init!, a weighted sample without replacement per iteration.
+    Every new order rebuilds the block Gram matrices, so `randomized=True` pays that build per iteration."""
+    name = "Kaczmarz"
+
+    def __init__(self, A, *, AHA=None, reg=None, normalizeReg=None, randomized=False, subMatrixFraction=0.15,
+                 shuffleRows=False, seed=1234, iterations=10, greedy_randomized=False, block_rows=0, ctx=None):
+        if greedy_randomized:
+            raise NotImplementedError("greedy randomised Kaczmarz is not on the accelerated path (no CPU fallback)")
+        if A is None:
+            raise ValueError("Kaczmarz needs the system matrix A")
+        self.ctx = ctx if ctx is not None else (A.ctx if isinstance(A, B200Matrix) else B200Context.default())
+        if self.ctx.nranks > 1:
+            raise NotImplementedError("Kaczmarz does not shard over ranks (sequential row loop)")
+        self.normalizeReg = NoNormalization() if normalizeReg is None else normalizeReg
+        dtype = A.dtype if isinstance(A, B200Matrix) else np.asarray(A).dtype
+        if dtype not in (np.float32, np.complex64):
+            raise TypeError(f"librls_b200 accelerates Float32 / ComplexF32 systems only, got {dtype} (no CPU fallback)")
+        self.dtype = np.dtype(dtype)
+        regs = [L2Regularization(np.float32(0))] if reg is None else (list(reg) if isinstance(reg, (list, tuple)) else [reg])
+        regs = list(regs)
+        # --- L2 term, Tikhonov matrix (:83-93, :377-392): the scaled matrix A·diag(1/sqrt(λ)) is what goes to the device
+        i2 = findsink(L2Regularization, regs)
+        self._tikhonov = None
+        if i2 is not None and np.ndim(lam(regs[i2])) > 0:
+            if not isinstance(self.normalizeReg, (NoNormalization, SystemMatrixBasedNormalization)):
+                raise ValueError("Tikhonov matrix for Kaczmarz is only valid with no or system matrix based normalization")
+            if not isinstance(self.normalizeReg, NoNormalization):
+                raise NotImplementedError("Tikhonov matrix together with SystemMatrixBasedNormalization")
+            if isinstance(A, B200Matrix):
+                raise NotImplementedError("a Tikhonov matrix needs the host array A (it rescales the columns before upload)")
+        if isinstance(A, B200Matrix):
+            if A.layout != "row":
+                raise ValueError("Kaczmarz needs a row-major device matrix: B200Matrix.from_numpy(A, layout='row')")
+            self.A = A
+        else:
+            self._A_host = np.asarray(A)
+            self.A = None                    # uploaded below, once a Tikhonov scaling is known
+        self.m, self.n = (self.A.m, self.A.n) if self.A is not None else self._A_host.shape
+        self._upload_and_norms(regs, i2, block_rows)
+        regs = self._normalize_ctor(regs)                                     # :82 (needs self.A for SystemMatrixBased)
+        if i2 is None:
+            self.L2 = L2Regularization(np.float32(0))
+        else:
+            self.L2 = regs.pop(i2)
+        idx = findsinks(AbstractProjectionRegularization, regs)               # :95-97
+        other = [regs[i] for i in idx]
+        regs = [r for i, r in enumerate(regs) if i not in idx]
+        if len(regs) == 1:
+            other.append(regs[0])
+        elif len(regs) > 1:
+            raise ValueError(f"Kaczmarz does not allow for more than one additional regularization term, found {len(regs)}")
+        self.reg = other
+        self._initkaczmarz(self._lam_scalar())
+        self.randomized = bool(randomized)
+        self.shuffleRows = bool(shuffleRows)
+        self.seed = int(seed)
+        self.subMatrixSize = int(np.round(subMatrixFraction * self.m))        # :121
+        self.rowIndexCycle = np.arange(len(self.rowindex))
+        self.iterations = int(iterations)
+        self._iteration = 0
+        self._order = None
+        self._scalars = capi.SolverScalars()
+        self.state = SolverState(self)
+
+    # ---------------- setup ----------------
+    def _upload_and_norms(self, regs, i2, block_rows):
+        if self.A is None:
+            Ah = self._A_host
+            if i2 is not None and np.ndim(lam(regs[i2])) > 0:                 # initikhonov :392
+                lv = np.asarray(lam(regs[i2])).astype(np.float32)
+                if lv.shape != (self.n,):
+                    raise ValueError("the Tikhonov matrix needs one λ per column of A")
+                self._tikhonov = lv
+                Ah = (Ah * (np.float32(1) / np.sqrt(lv))[None, :]).astype(self.dtype)
+            self.A = B200Matrix.from_numpy(np.asarray(Ah, dtype=self.dtype), self.ctx, layout="row")
+            del self._A_host
+        h = C.c_void_p()
+        capi.call("rls_kaczmarz_create", self.A.handle, int(block_rows), C.byref(h))
+        import weakref
+        self._handle = h
+        self._fin = weakref.finalize(self, capi.load().rls_kaczmarz_destroy, h)
+        s2 = np.empty(self.m, np.float32)
+        capi.call("rls_kaczmarz_rownorm2", h, s2.ctypes.data_as(C.c_void_p), s2.size)
+        self._s2 = s2                                                         # rownorm²(A, i), Utils.jl:16-23
+        br = C.c_int32()
+        capi.call("rls_kaczmarz_block_rows", h, C.byref(br))
+        self.block_rows = br.value
+
+    def _lam_scalar(self):
+        """λ seen by initkaczmarz: one(T) for a Tikhonov matrix (:390), λ(L2) otherwise"""
+        return np.float32(1) if self._tikhonov is not None else lam(self.L2)
+
+    def _initkaczmarz(self, lam_):
+        """:365-376: rows with s² > 0, denom = T(1.0 / (s² + λ))"""
+        keep = np.nonzero(self._s2 > 0)[0]
+        tot = self._s2[keep] + lam_                                           # Float32 (+ Float64 λ promotes)
+        self.denom = (1.0 / np.asarray(tot, dtype=np.float64)).astype(np.float32)
+        self.rowindex = keep.astype(np.int64)
+        self._lam_used = lam_
+
+    def _row_probabilities(self):
+        """:326-334, converted to T at :125"""
+        tot = np.float32(np.sum(self._s2, dtype=np.float32))
+        return (self._s2[self.rowindex].astype(np.float64) / np.float64(tot)).astype(np.float32)
+
+    def _set_order(self, used):
+        used = np.asarray(used, dtype=np.int64)
+        if self._order is not None and self._order[0] is self.denom and np.array_equal(self._order[1], used):
+            return
+        rows = np.ascontiguousarray(self.rowindex[used], dtype=np.int64)
+        den = np.ascontiguousarray(self.denom[used], dtype=np.float32)
+        capi.call("rls_kaczmarz_set_rows", self._handle, rows.ctypes.data_as(C.c_void_p), den.ctypes.data_as(C.c_void_p),
+                  rows.size)
+        self._order = (self.denom, used.copy())
+
+    # ---------------- state access ----------------
+    def _vec(self, name):
+        h = C.c_void_p()
+        capi.call("rls_kaczmarz_vec", self._handle, name.encode(), C.byref(h))
+        ln, dt = C.c_int64(), C.c_int32()
+        capi.call("rls_vec_len", h, C.byref(ln), C.byref(dt))
+        return B200Vector(self.ctx, self.dtype, ln.value, _handle=h, _owned=False)
+
+    @property
+    def x(self):
+        """solversolution(solver): the Tikhonov-matrix form returns x ./ sqrt.(λ) (:253-256)"""
+        x = self._vec("x").to_numpy()
+        if self._tikhonov is not None:
+            x = (x * (np.float32(1) / np.sqrt(self._tikhonov))).astype(self.dtype)
+        return x
+
+    @property
+    def iteration(self):
+        return self._iteration
+
+    # ---------------- init! / iterate ----------------
+    def init_(self, b, x0=0):
+        """init!(solver, state, b; x0)  :178-216"""
+        bd = b if isinstance(b, B200Vector) else B200Vector.from_numpy(np.ascontiguousarray(b, dtype=self.dtype), self.ctx)
+        lam_prev = self._lam_scalar()
+        if isinstance(self.normalizeReg, MeasurementBasedNormalization):      # :179-181 (SystemMatrixBased: unchanged)
+            f = np.float32(np.float32(bd.asum()) / np.float32(bd.length))
+            self.L2 = normalize_reg(self.L2, f)
+            self.reg = [normalize_reg(r, f) for r in self.reg]
+        lam_ = self._lam_scalar()
+        if lam_ != lam_prev:                                                  # :186-193
+            self._initkaczmarz(lam_)
+            self.rowIndexCycle = np.arange(len(self.rowindex))
+        self._rng = np.random.default_rng(self.seed)                          # :195-197
+        if self.randomized:
+            self.probabilities = self._row_probabilities()
+        elif self.shuffleRows:
+            self.rowIndexCycle = self._rng.permutation(self.rowIndexCycle)    # :201
+        if not self.randomized:
+            self._set_order(self.rowIndexCycle)
+        x0d = None
+        if not (np.isscalar(x0) and x0 == 0):
+            x0d = x0 if isinstance(x0, B200Vector) else B200Vector.from_numpy(np.asarray(x0, dtype=self.dtype), self.ctx)
+        eps_w = np.float32(1) if self._tikhonov is not None else np.float32(np.sqrt(lam_))   # :210-214
+        capi.call("rls_kaczmarz_init", self._handle, bd.handle, x0d.handle if x0d is not None else None, eps_w)
+        self._iteration = 0
+        self._b_keepalive = (bd, x0d)
+        return self
+
+    def iterate(self):
+        """iterate(solver, state)  :264-283"""
+        if self._iteration >= self.iterations:                                # done() :315
+            return False
+        if self.randomized:                                                   # sample! :267-269
+            p = self.probabilities.astype(np.float64)
+            used = self._rng.choice(len(self.rowIndexCycle), size=self.subMatrixSize, replace=False, p=p / p.sum())
+            self._set_order(used)
+        capi.call("rls_kaczmarz_sweep", self._handle)
+        if self.reg:
+            from .prox import prox_
+            xv = self._vec("x")
+            for r in self.reg:                                                # :275-277
+                prox_(r, xv)
+        self._iteration += 1
+        return True
+
+    def solve_(self, b, x0=0, callbacks=None, scheduler=None):
+        host_in = not isinstance(b, B200Vector)
+        if host_in and np.ndim(b) == 2:
+            return np.stack([self.solve_(np.asarray(b)[:, k], x0=x0, callbacks=callbacks) for k in range(np.shape(b)[1])], axis=1)
+        cbs = [] if callbacks is None else (list(callbacks) if isinstance(callbacks, (list, tuple)) else [callbacks])
+        self.init_(b, x0=x0)
+        for cb in cbs:
+            cb(self, 0)
+        k = 0
+        while self.iterate():
+            k += 1
+            for cb in cbs:
+                cb(self, k)
+        return self.x if host_in or self._tikhonov is not None else self._vec("x")
+
+    def convergence(self):
+        """solverconvergence :258: ‖A x − u‖"""
+        r = self.A.mul(self._vec("x"))
+        return {"residual": float(np.linalg.norm(r.to_numpy() - self._vec("u").to_numpy()))}
+
+
 def linearSolverList():
     """the solvers on the accelerated path (RegularizedLeastSquares.jl:213-220 lists all of upstream's)"""
-    return [CGNR, FISTA, OptISTA, POGM, ADMM, SplitBregman]
+    return [CGNR, Kaczmarz, FISTA, OptISTA, POGM, ADMM, SplitBregman]
 
 
 def createLinearSolver(solver, A=None, *, AHA=None, kwargWarning=True, **kwargs):

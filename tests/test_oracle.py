@@ -288,3 +288,75 @@ def test_split_bregman_constraint_is_enforced():
         xa = O.solve_(S, b)
         res.append(np.linalg.norm(A @ xa - b))
     assert res[1] < 0.5 * res[0]
+
+
+# ---- Kaczmarz (src/Kaczmarz.jl): the properties test/testKaczmarz.jl pins ---------------------------------------
+def _kaczmarz_system(rng, M=12, N=8):
+    A = rng.random((M, N)) + 1j * rng.random((M, N))
+    x = rng.random(N) + 1j * rng.random(N)
+    return A, x, A @ x
+
+
+def test_kaczmarz_parameters():
+    """test/testKaczmarz.jl:94-125: plain, shuffled, randomized, normalised"""
+    rng = np.random.default_rng(12345)
+    A, x, b = _kaczmarz_system(rng)
+    for kw in (dict(iterations=200), dict(iterations=200, shuffleRows=True), dict(iterations=2000, randomized=True)):
+        xa = O.Kaczmarz(A, **kw).solve(b)
+        assert np.linalg.norm(x - xa) / np.linalg.norm(x) < 0.1
+    for strategy in (O.SystemMatrixBasedNormalization(), O.MeasurementBasedNormalization()):
+        xa = O.Kaczmarz(A, iterations=200, randomized=True, reg=O.L2Regularization(0.1), normalizeReg=strategy).solve(b)
+        assert np.linalg.norm(x - xa) / np.linalg.norm(x) < 0.3
+    with pytest.raises(ValueError):
+        O.Kaczmarz(A, reg=[O.L1Regularization(1e-3), O.L21Regularization(1e-3)])
+
+
+def test_kaczmarz_tikhonov_matrix():
+    """test/testKaczmarz.jl:37-70"""
+    rng = np.random.default_rng(12345)
+    A, x, b = _kaczmarz_system(rng)
+    N = A.shape[1]
+    lamv = rng.random(N)
+    xm = O.Kaczmarz(A, iterations=100, reg=[O.L2Regularization(lamv)]).solve(b)
+    xs = O.Kaczmarz(A * (1 / np.sqrt(lamv))[None, :], iterations=100, reg=[O.L2Regularization(1.0)]).solve(b) / np.sqrt(lamv)
+    assert np.linalg.norm(xs - xm) / np.linalg.norm(xs) < 0.1
+    lam = float(rng.random())
+    x1 = O.Kaczmarz(A, iterations=100, reg=[O.L2Regularization(lam)]).solve(b)
+    x2 = O.Kaczmarz(A, iterations=100, reg=[O.L2Regularization(np.full(N, lam))]).solve(b)
+    assert np.allclose(x1, x2)
+
+
+def test_kaczmarz_fixed_point_is_the_tikhonov_solution():
+    """the iteration on the extended system [A  sqrt(λ) I] converges to argmin ‖Ax − b‖² + λ‖x‖² (Kaczmarz.jl:305-310)"""
+    rng = np.random.default_rng(7)
+    A = rng.standard_normal((30, 10)); b = rng.standard_normal(30); lam = 0.5
+    xa = O.Kaczmarz(A, iterations=3000, reg=O.L2Regularization(lam)).solve(b)
+    xr = np.linalg.solve(A.T @ A + lam * np.eye(10), A.T @ b)
+    assert np.linalg.norm(xa - xr) / np.linalg.norm(xr) < 1e-8
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64])
+def test_kaczmarz_block_gram_form_is_the_same_recurrence(dtype):
+    """the evaluation csrc/rls_kaczmarz.cu uses — per block of R rows: t = A_blk x, tau_j = t_j + sum_{k<j} alpha_k G[j,k]
+    with G = A_blk A_blk^H, x += A_blk^H alpha — reproduces the row-by-row iterates to rounding in single precision"""
+    rng = np.random.default_rng(3)
+    m, n, R = 200, 96, 64
+    A = (rng.standard_normal((m, n)) / np.sqrt(m)).astype(np.float32)
+    if dtype == np.complex64:
+        A = (A + 1j * rng.standard_normal((m, n)).astype(np.float32) / np.float32(np.sqrt(m))).astype(dtype)
+    A = A.astype(dtype)
+    b = (A @ rng.standard_normal(n).astype(dtype)).astype(dtype)
+    lam = np.float32(1e-2)
+    S = O.Kaczmarz(A, reg=O.L2Regularization(lam), iterations=4); S.init(b)
+    x = np.zeros(n, dtype); vl = np.zeros(m, dtype); ew = np.float32(np.sqrt(lam))
+    for _ in range(4):
+        S.iterate()
+        for r0 in range(0, m, R):
+            Ab = A[r0:r0 + R]; G = (Ab @ Ab.conj().T).astype(dtype); t = (Ab @ x).astype(dtype)
+            c = np.zeros(len(Ab), dtype); al = np.zeros(len(Ab), dtype)
+            for j in range(len(Ab)):
+                al[j] = S.denom[r0 + j] * (b[r0 + j] - (t[j] + c[j]) - ew * vl[r0 + j])
+                c[j + 1:] += al[j] * G[j + 1:, j]
+                vl[r0 + j] += al[j] * ew
+            x += (Ab.conj().T @ al).astype(dtype)
+        assert np.linalg.norm(x - S.x) / np.linalg.norm(S.x) < 1e-5

@@ -1,0 +1,82 @@
+"""Kernel-by-kernel check of csrc/rls_kaczmarz.cu against NumPy, then sweep timing at the C2 shape.
+Run on the GPU box:  python tools/kaczmarz_check.py [--time]"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rls_b200 as rls  # noqa: E402
+import oracle as O      # noqa: E402  (checker only)
+from oracle.philox import philox_matrix, philox_vector, IH4  # noqa: E402
+
+capi = rls._capi
+
+
+def dbg(S, which, n):
+    out = np.empty(n, np.float32)
+    capi.call("rls_kaczmarz_debug", S._handle, which, out.ctypes.data_as(C.c_void_p), n)
+    return out
+
+
+def check(dtype, m, n, R, lam=np.float32(1e-2)):
+    fpe = 2 if dtype == np.complex64 else 1
+    A = philox_matrix(dtype, m, n, 11, IH4, 1 / np.sqrt(m))
+    xt = philox_vector(dtype, n, 12, 1, IH4, 1.0)
+    b = (A @ xt).astype(dtype)
+    S = rls.Kaczmarz(A, reg=rls.L2Regularization(lam), iterations=3, block_rows=R)
+    R = S.block_rows
+    s2 = (np.abs(A.astype(np.complex128)) ** 2).sum(1)
+    print(f"[{np.dtype(dtype).name} {m}x{n} R={R}] rownorm2 rel {np.abs(S._s2 - s2).max() / s2.max():.2e}")
+    S.init_(b)
+    nblk = (m + R - 1) // R
+    G = dbg(S, 0, nblk * R * R * fpe).reshape(nblk, R, R, fpe)     # [b][j][k] = G[k, j]
+    worst = 0.0
+    for bi in range(nblk):
+        Ab = np.zeros((R, n), np.complex128); rr = min(R, m - bi * R); Ab[:rr] = A[bi * R: bi * R + rr]
+        Gref = Ab @ Ab.conj().T                                     # [k, j]
+        Gd = (G[bi, ..., 0] + (1j * G[bi, ..., 1] if fpe == 2 else 0)).T
+        low = np.tril(np.ones((R, R), bool))
+        worst = max(worst, np.abs((Gd - Gref)[low]).max() / np.abs(Gref).max())
+    print(f"    gram lower-triangle max err {worst:.2e}")
+    R0 = O.Kaczmarz(A, reg=O.L2Regularization(lam), iterations=3); R0.init(b)
+    for it in range(3):
+        S.iterate(); R0.iterate()
+        al = dbg(S, 2, R * fpe)
+        print(f"    sweep {it + 1}: x rel {np.linalg.norm(S.x - R0.x) / np.linalg.norm(R0.x):.2e}  vl rel "
+              f"{np.linalg.norm(S._vec('vl').to_numpy() - R0.vl) / max(np.linalg.norm(R0.vl), 1e-30):.2e}  |alpha_last_blk| {np.linalg.norm(al):.3e}")
+
+
+def timing(dtype, m, n, sweeps=5):
+    ctx = rls.B200Context.default(0)
+    A = rls.B200Matrix.philox(dtype, m, n, seed=12345, scale=1 / np.sqrt(m), ctx=ctx, layout="row")
+    t0 = time.perf_counter()
+    S = rls.Kaczmarz(A, reg=rls.L2Regularization(np.float32(1e-2)), iterations=sweeps)
+    b = rls.B200Vector(ctx, dtype, m).fill_philox(seed=3, stream=1, dist=capi.RLS_DIST_IH4)
+    ctx.timer_start(); S._set_order(S.rowIndexCycle); gram_ms = ctx.timer_stop()
+    S.init_(b)
+    S.iterate(); ctx.sync()
+    n0 = ctx.launch_count()
+    ctx.timer_start()
+    k = 0
+    while S.iterate():
+        k += 1
+    ms = ctx.timer_stop()
+    bytes_ = m * n * np.dtype(dtype).itemsize
+    print(f"[timing {np.dtype(dtype).name} {m}x{n}] block_rows {S.block_rows}, setup+gram {gram_ms:.1f} ms (wall incl. create "
+          f"{time.perf_counter() - t0:.2f} s), {k} sweeps: {ms / k:.3f} ms per sweep = {bytes_ / (ms / k) / 1e6:.0f} GB/s of A, "
+          f"{(ctx.launch_count() - n0) // k} launches per sweep, |x| {np.linalg.norm(S.x):.4e}")
+
+
+if __name__ == "__main__":
+    for dt in (np.float32, np.complex64):
+        check(dt, 300, 200, 64)
+        check(dt, 150, 67, 128)
+        check(dt, 520, 4100, 256)
+    if "--time" in sys.argv:
+        timing(np.float32, 16384, 65536)
+        timing(np.complex64, 8192, 65536)
+        os.environ["RLS_KACZMARZ_BLOCK"] = "256"
+        timing(np.float32, 16384, 65536)
