@@ -49,9 +49,9 @@ struct rls_kaczmarz_s {
 namespace {
 
 constexpr int KZ_DOT_THREADS = 256;
-constexpr int KZ_DOT_LPT = 4;   // loads per thread and row
-constexpr int KZ_DOT_RG = 8;    // rows per CTA
-constexpr int KZ_UPD_THREADS = 64;
+constexpr int KZ_DOT_LPT = 2;   // loads per thread and row
+constexpr int KZ_DOT_RG = 4;    // rows per CTA, all in flight at once
+constexpr int KZ_UPD_THREADS = 512;   // 32 packs x 16 row groups
 constexpr int KZ_MAX_R = 256;
 
 template <int NF> struct PackT;
@@ -173,13 +173,16 @@ __global__ void __launch_bounds__(KZ_DOT_THREADS) kz_dot_kernel(const float* __r
   __shared__ float s_red[NW][RG * FPE];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t chunk0 = (int64_t)blockIdx.x * (KZ_DOT_THREADS * LPT * NF);
+  // out-of-range packs read pack 0 against x = 0, padding rows read row 0 and are zeroed afterwards: all loads are
+  // unconditional, so the compiler can put the RG x LPT loads of a CTA in flight at once
   int64_t idx[LPT];
   float xr[LPT][NF];
 #pragma unroll
   for (int l = 0; l < LPT; ++l) {
-    idx[l] = chunk0 + ((int64_t)l * KZ_DOT_THREADS + tid) * NF;
-    if (idx[l] < nfl) ld_pack_cg<NF>(x + idx[l], xr[l]);
-    else {
+    const int64_t i0 = chunk0 + ((int64_t)l * KZ_DOT_THREADS + tid) * NF;
+    idx[l] = i0 < nfl ? i0 : 0;
+    ld_pack_cg<NF>(x + idx[l], xr[l]);
+    if (i0 >= nfl) {
 #pragma unroll
       for (int i = 0; i < NF; ++i) xr[l][i] = 0.f;
     }
@@ -190,27 +193,29 @@ __global__ void __launch_bounds__(KZ_DOT_THREADS) kz_dot_kernel(const float* __r
   for (int r = 0; r < RG; ++r)
 #pragma unroll
     for (int c = 0; c < FPE; ++c) acc[r][c] = 0.f;
+  {
+    float a[RG][LPT][NF];
+    int rowv[RG];
 #pragma unroll
-  for (int r = 0; r < RG; r += 2) {
-    float a[2][LPT][NF];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int j = j0 + r + q;
-      const int row = j < R ? rows[j] : -1;
-      const float* ap = A + (int64_t)(row < 0 ? 0 : row) * ldf;
-#pragma unroll
-      for (int l = 0; l < LPT; ++l) {
-        if (row >= 0 && idx[l] < nfl) ld_pack<NF>(ap + idx[l], a[q][l]);   // stays in L2 for the update pass
-        else {
-#pragma unroll
-          for (int i = 0; i < NF; ++i) a[q][l][i] = 0.f;
-        }
-      }
+    for (int q = 0; q < RG; ++q) {
+      const int j = j0 + q;
+      rowv[q] = j < R ? rows[j] : -1;
     }
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
+    for (int q = 0; q < RG; ++q) {
+      const float* ap = A + (int64_t)(rowv[q] < 0 ? 0 : rowv[q]) * ldf;
 #pragma unroll
-      for (int l = 0; l < LPT; ++l) dot_acc<FPE, NF>(a[q][l], xr[l], acc[r + q]);
+      for (int l = 0; l < LPT; ++l) ld_pack<NF>(ap + idx[l], a[q][l]);   // stays in L2 for the update pass
+    }
+#pragma unroll
+    for (int q = 0; q < RG; ++q) {
+#pragma unroll
+      for (int l = 0; l < LPT; ++l) dot_acc<FPE, NF>(a[q][l], xr[l], acc[q]);
+      if (rowv[q] < 0) {
+#pragma unroll
+        for (int c = 0; c < FPE; ++c) acc[q][c] = 0.f;
+      }
+    }
   }
 #pragma unroll
   for (int r = 0; r < RG; ++r)
@@ -231,19 +236,30 @@ __global__ void __launch_bounds__(KZ_DOT_THREADS) kz_dot_kernel(const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// the triangular recurrence of one block; blockDim.x == R (multiple of 32, <= 256)
+// the triangular recurrence of one block; blockDim.x == R (multiple of 32, <= 256).
+// STAGE: the block's Gram matrix (immutable) is copied to shared memory BEFORE griddepcontrol.wait, i.e. while the
+// dot kernel is still running, so that the serial part only touches shared memory and registers.
 // ---------------------------------------------------------------------------------------------------------------
-template <int FPE>
+template <int FPE, bool STAGE>
 __global__ void __launch_bounds__(KZ_MAX_R) kz_solve_kernel(const int32_t* __restrict__ rows, const float* __restrict__ denom,
                                                             const float* __restrict__ G, int R,
                                                             const float* tpart, int S,
                                                             const float* u, float* vl, float ew,
                                                             float* __restrict__ alpha_out) {
-  pdl_prologue();
+  extern __shared__ float4 s_dyn4[];
   __shared__ float s_alpha[KZ_MAX_R * FPE];
+  float* sG = reinterpret_cast<float*>(s_dyn4);
   const int k = threadIdx.x, lane = k & 31, warp = k >> 5;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (STAGE) {
+    const float4* g4 = reinterpret_cast<const float4*>(G);
+    const int n4 = R * R * FPE / 4;
+#pragma unroll 8
+    for (int i = k; i < n4; i += R) s_dyn4[i] = __ldg(g4 + i);
+  }
   const int row = rows[k];
   const float d = row >= 0 ? denom[k] : 0.f;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   float t[FPE], uu[FPE], vv[FPE], c[FPE], mine[FPE];
 #pragma unroll
   for (int q = 0; q < FPE; ++q) { t[q] = 0.f; c[q] = 0.f; mine[q] = 0.f; uu[q] = 0.f; vv[q] = 0.f; }
@@ -254,6 +270,11 @@ __global__ void __launch_bounds__(KZ_MAX_R) kz_solve_kernel(const int32_t* __res
 #pragma unroll
     for (int q = 0; q < FPE; ++q) { uu[q] = __ldcg(u + (int64_t)row * FPE + q); vv[q] = __ldcg(vl + (int64_t)row * FPE + q); }
   }
+  if (STAGE) __syncthreads();
+  auto ldG = [&](int j, int q) -> float {
+    const int64_t o = ((int64_t)j * R + k) * FPE + q;
+    return STAGE ? sG[o] : __ldg(G + o);
+  };
   const int nb = R >> 5;
   for (int jb = 0; jb < nb; ++jb) {
     const int j0 = jb << 5;
@@ -262,7 +283,7 @@ __global__ void __launch_bounds__(KZ_MAX_R) kz_solve_kernel(const int32_t* __res
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj)
 #pragma unroll
-        for (int q = 0; q < FPE; ++q) g[jj][q] = __ldg(G + ((int64_t)(j0 + jj) * R + k) * FPE + q);
+        for (int q = 0; q < FPE; ++q) g[jj][q] = ldG(j0 + jj, q);
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) {
         float al[FPE];
@@ -294,7 +315,7 @@ __global__ void __launch_bounds__(KZ_MAX_R) kz_solve_kernel(const int32_t* __res
 #pragma unroll
         for (int q = 0; q < FPE; ++q) {
           al[q] = s_alpha[(j0 + jj) * FPE + q];
-          g[q] = __ldg(G + ((int64_t)(j0 + jj) * R + k) * FPE + q);
+          g[q] = ldG(j0 + jj, q);
         }
         mul_acc<FPE>(al, g, c);
       }
@@ -303,37 +324,38 @@ __global__ void __launch_bounds__(KZ_MAX_R) kz_solve_kernel(const int32_t* __res
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// x += sum_j alpha_j conj(a_j)
+// x += sum_j alpha_j conj(a_j).  CTA = 32 packs of x (one warp-wide, contiguous) x 16 row groups (one per warp): group g
+// accumulates rows [g R/16, (g+1) R/16) of the block, the 16 partial sums meet in shared memory and warp 0 adds them in
+// a fixed order.
 // ---------------------------------------------------------------------------------------------------------------
 template <int FPE, int NF>
 __global__ void __launch_bounds__(KZ_UPD_THREADS) kz_update_kernel(const float* __restrict__ A, int64_t ldf, int64_t nfl,
                                                                    const int32_t* __restrict__ rows, int R,
                                                                    const float* alpha, float* x) {
-  pdl_prologue();
+  constexpr int NG = KZ_UPD_THREADS / 32;
   __shared__ float s_al[KZ_MAX_R * FPE];
   __shared__ int s_row[KZ_MAX_R];
-  for (int i = threadIdx.x; i < R; i += KZ_UPD_THREADS) {
-    s_row[i] = rows[i];
-#pragma unroll
-    for (int q = 0; q < FPE; ++q) s_al[i * FPE + q] = __ldcg(alpha + i * FPE + q);
-  }
+  __shared__ float s_part[NG][32][NF];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  for (int i = threadIdx.x; i < R; i += KZ_UPD_THREADS) s_row[i] = rows[i];   // immutable: before the dependency wait
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (int i = threadIdx.x; i < R * FPE; i += KZ_UPD_THREADS) s_al[i] = __ldcg(alpha + i);
   __syncthreads();
-  const int64_t idx = ((int64_t)blockIdx.x * KZ_UPD_THREADS + threadIdx.x) * NF;
-  if (idx >= nfl) return;
+  const int64_t idx0 = ((int64_t)blockIdx.x * 32 + lane) * NF;
+  const bool live = idx0 < nfl;
+  const int64_t idx = live ? idx0 : 0;   // dead lanes read pack 0 and drop the result: loads stay unconditional
   float acc[NF];
 #pragma unroll
   for (int i = 0; i < NF; ++i) acc[i] = 0.f;
-  constexpr int U = 8;
-  for (int j0 = 0; j0 < R; j0 += U) {   // R is a multiple of 32
+  const int rpg = R / NG;   // R is a multiple of 64, NG = 16
+  constexpr int U = 4;
+  for (int j0 = grp * rpg; j0 < (grp + 1) * rpg; j0 += U) {
     float a[U][NF];
 #pragma unroll
     for (int r = 0; r < U; ++r) {
-      const int row = s_row[j0 + r];
-      if (row >= 0) ld_pack_stream<NF>(A + (int64_t)row * ldf + idx, a[r]);   // last use of the block
-      else {
-#pragma unroll
-        for (int i = 0; i < NF; ++i) a[r][i] = 0.f;
-      }
+      const int row = s_row[j0 + r];     // padding rows (-1) have alpha = 0: read row 0
+      ld_pack_stream<NF>(A + (int64_t)(row < 0 ? 0 : row) * ldf + idx, a[r]);   // last use of the block
     }
 #pragma unroll
     for (int r = 0; r < U; ++r) {
@@ -343,11 +365,23 @@ __global__ void __launch_bounds__(KZ_UPD_THREADS) kz_update_kernel(const float* 
       upd_acc<FPE, NF>(al, a[r], acc);
     }
   }
-  float xv[NF];
-  ld_pack_cg<NF>(x + idx, xv);
 #pragma unroll
-  for (int i = 0; i < NF; ++i) xv[i] += acc[i];
-  st_pack(x + idx, xv);
+  for (int i = 0; i < NF; ++i) s_part[grp][lane][i] = acc[i];
+  __syncthreads();
+  if (grp == 0 && live) {
+    float xv[NF];
+    ld_pack_cg<NF>(x + idx, xv);
+    float tot[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) tot[i] = 0.f;
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+      for (int i = 0; i < NF; ++i) tot[i] += s_part[g][lane][i];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) xv[i] += tot[i];
+    st_pack(x + idx, xv);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -453,7 +487,7 @@ extern "C" int32_t rls_kaczmarz_create(rls_mat_t A, int32_t block_rows, rls_kacz
     // a block should stay L2-resident between its two passes: <= 32 MB
     const int64_t row_bytes = A->n * (int64_t)fpe * 4;
     int64_t r = (32ll << 20) / (row_bytes > 0 ? row_bytes : 1);
-    R = r >= 256 ? 256 : r >= 128 ? 128 : 64;
+    R = r >= 192 && fpe == 1 ? 192 : r >= 128 ? 128 : 64;   // Gram block <= 200 KB: staged in shared memory
   }
   RLS_CHECK_ARG(R == 64 || R == 128 || R == 192 || R == 256, "Kaczmarz: block_rows must be 64, 128, 192 or 256 (got %d)", R);
   rls_kaczmarz_s* K = new rls_kaczmarz_s();
@@ -578,13 +612,28 @@ static int32_t kz_sweep_impl(rls_kaczmarz_s* K) {
   float* x = (float*)K->x->d;
   const dim3 gdot((unsigned)K->S, (unsigned)((R + KZ_DOT_RG - 1) / KZ_DOT_RG));
   const int64_t packs = (nfl + NF - 1) / NF;
-  const dim3 gupd((unsigned)((packs + KZ_UPD_THREADS - 1) / KZ_UPD_THREADS));
+  const dim3 gupd((unsigned)((packs + 31) / 32));
+  const size_t gbytes = (size_t)R * R * FPE * 4;
+  const bool stage = gbytes <= 200 * 1024;
+  if (stage) RLS_CUDA(cudaFuncSetAttribute(kz_solve_kernel<FPE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gbytes));
   for (int64_t b = 0; b < K->nblk; ++b) {
     const int32_t* rows = K->d_rows + b * R;
     RLS_CUDA(rls_launch_pdl(c->stream, gdot, dim3(KZ_DOT_THREADS), kz_dot_kernel<FPE, NF>, A, ldf, nfl, rows, R, (const float*)x, K->d_tpart));
-    RLS_CUDA(rls_launch_pdl(c->stream, dim3(1), dim3(R), kz_solve_kernel<FPE>, rows, (const float*)(K->d_denom + b * R),
-                            (const float*)(K->d_G + b * (int64_t)R * R * FPE), R, (const float*)K->d_tpart, K->S, (const float*)K->u->d,
-                            (float*)K->vl->d, K->eps_w, K->d_alpha));
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(1); cfg.blockDim = dim3(R); cfg.dynamicSmemBytes = stage ? gbytes : 0; cfg.stream = c->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = rls_pdl_enabled() ? 1 : 0;
+      const float* den = K->d_denom + b * R;
+      const float* Gb = K->d_G + b * (int64_t)R * R * FPE;
+      const float* tp = K->d_tpart;
+      const float* uu = (const float*)K->u->d;
+      float* vl = (float*)K->vl->d;
+      RLS_CUDA(cudaLaunchKernelEx(&cfg, stage ? kz_solve_kernel<FPE, true> : kz_solve_kernel<FPE, false>, rows, den, Gb, R, tp, K->S, uu, vl,
+                                  K->eps_w, K->d_alpha));
+    }
     RLS_CUDA(rls_launch_pdl(c->stream, gupd, dim3(KZ_UPD_THREADS), kz_update_kernel<FPE, NF>, A, ldf, nfl, rows, R, (const float*)K->d_alpha, x));
     c->launches += 3;
   }

@@ -71,11 +71,13 @@ def timing(dtype, m, n, sweeps=5):
 
 
 if __name__ == "__main__":
-    for dt in (np.float32, np.complex64):
+    for dt in (() if "--time-only" in sys.argv else (np.float32, np.complex64)):
         check(dt, 300, 200, 64)
         check(dt, 150, 67, 128)
         check(dt, 520, 4100, 256)
-    if "--time" in sys.argv:
+    if "--time-only" in sys.argv:
+        timing(np.float32, 16384, 65536, sweeps=2)
+    elif "--time" in sys.argv:
         timing(np.float32, 16384, 65536)
         timing(np.complex64, 8192, 65536)
         os.environ["RLS_KACZMARZ_BLOCK"] = "256"
