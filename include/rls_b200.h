@@ -303,7 +303,9 @@ int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_host, int64_t 
  * block Gram matrix A_blk A_blk^H (built once per order), so that one iteration is one HBM sweep over A instead of m
  * dependent dot/axpy pairs.  The constructor logic (L2 / denom / rowindex / probabilities / row order, Kaczmarz.jl:73-159,
  * :326-392) and the prox! calls after the sweep (:275-277, rls_prox_*) stay with the host, as in the reference.
- * block_rows: 64, 128, 192, 256, or 0 = sized so that a block stays L2-resident. */
+ * block_rows: 64, 128, 192, 256, or 0 = 64 / 128 (sized so that a block stays L2-resident).  With 64 or 128 and rows
+ * of a multiple of 16 bytes a whole iteration is ONE cooperative kernel (columns of x pinned to CTAs, one grid-wide
+ * exchange per block); otherwise three kernels per block are chained on the stream. */
 int32_t rls_kaczmarz_create(rls_mat_t A, int32_t block_rows, rls_kaczmarz_t* out);
 int32_t rls_kaczmarz_destroy(rls_kaczmarz_t K);
 int32_t rls_kaczmarz_block_rows(rls_kaczmarz_t K, int32_t* block_rows);
@@ -318,6 +320,10 @@ int32_t rls_kaczmarz_init(rls_kaczmarz_t K, rls_vec_t b, rls_vec_t x0, float eps
 int32_t rls_kaczmarz_sweep(rls_kaczmarz_t K);
 /* state vectors "x", "vl", "u" (borrowed handles) */
 int32_t rls_kaczmarz_vec(rls_kaczmarz_t K, const char* name, rls_vec_t* out);
+/* synchronise; reports a timed-out block exchange of the one-kernel sweep (every device-side wait is bounded) */
+int32_t rls_kaczmarz_check(rls_kaczmarz_t K);
+/* kernel plan of the sweep, for diagnostics ("persistent: grid=148 ..." / "chained: 3 kernels per block ...") */
+int32_t rls_kaczmarz_describe(rls_kaczmarz_t K, char* buf, int32_t len);
 /* diagnostics: 0 = block Gram matrices, 1 = dot partials of the last block, 2 = alpha of the last block, 3 = denominators */
 int32_t rls_kaczmarz_debug(rls_kaczmarz_t K, int32_t which, float* host, int64_t nfloats);
 

@@ -147,6 +147,8 @@ SIGNATURES = {
     "rls_kaczmarz_sweep": [_P],
     "rls_kaczmarz_vec": [_P, C.c_char_p, _PP],
     "rls_kaczmarz_debug": [_P, _I32, _P, _I64],
+    "rls_kaczmarz_check": [_P],
+    "rls_kaczmarz_describe": [_P, C.c_char_p, _I32],
 }
 _SPECIAL = {"rls_abi_version": ([], _I32), "rls_last_error": ([], C.c_char_p)}
 

@@ -44,6 +44,15 @@ struct rls_kaczmarz_s {
   rls_vec_s *x = nullptr, *vl = nullptr, *u = nullptr;
   float eps_w = 0.f;
   bool initialised = false;
+  // persistent sweep kernel (one cooperative launch per iteration)
+  float* d_Dinv = nullptr;     // [nblk][R/32][32 jj][32 lane][fpe]: inverses of the 32x32 diagonal blocks of D^-1 + strictlower(G)
+  float* d_tpart2 = nullptr;   // [NC][R][fpe]
+  unsigned long long* d_sync = nullptr;   // [0] arrivals, [1] alpha-ready, both monotonic
+  int* d_abort = nullptr;
+  unsigned long long epoch = 0;           // blocks completed since the counters were reset
+  int pgrid = 0, pP = 0, pIT = 0;
+  size_t psmem = 0;
+  bool persistent = false;
 };
 
 namespace {
@@ -459,9 +468,352 @@ __global__ void __launch_bounds__(256) kz_gram_kernel(const float* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Inverses of the 32x32 diagonal blocks of M = D^-1 + strictlower(G) (the matrix of the block recurrence
+// M alpha = r): with them a diagonal block of the forward substitution is 32 independent shuffle+FMA per lane
+// instead of a 32-step dependent chain.  One warp per diagonal block, inversion in double, lane = column.
+// Padding rows (denom 0, alpha must stay 0) get a zero row and a zero column.
+// ---------------------------------------------------------------------------------------------------------------
+template <int FPE>
+__global__ void __launch_bounds__(32) kz_dinv_kernel(const float* __restrict__ G_all, const float* __restrict__ denom_all, int R,
+                                                     float* __restrict__ Dinv_all) {
+  const int64_t b = blockIdx.y;
+  const int jb = blockIdx.x, lane = threadIdx.x, j0 = jb * 32;
+  const float* G = G_all + b * (int64_t)R * R * FPE;
+  const float* den = denom_all + b * R;
+  float* out = Dinv_all + ((b * (R / 32) + jb) * 32 * 32) * FPE;
+  __shared__ double sM[32][32][FPE];   // M[i][k], k <= i
+  for (int i = 0; i < 32; ++i) {
+    const int k = lane;
+    double v[FPE];
+#pragma unroll
+    for (int q = 0; q < FPE; ++q) v[q] = 0.0;
+    if (k < i) {
+#pragma unroll
+      for (int q = 0; q < FPE; ++q) v[q] = (double)G[((int64_t)(j0 + k) * R + (j0 + i)) * FPE + q];   // G[row i, col k]
+    } else if (k == i) {
+      const float d = den[j0 + i];
+      v[0] = d > 0.f ? 1.0 / (double)d : 1.0;
+    }
+#pragma unroll
+    for (int q = 0; q < FPE; ++q) sM[i][k][q] = v[q];
+  }
+  __syncwarp();
+  // column `lane` of X = M^-1 by forward substitution
+  double X[32][FPE];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    double acc[FPE];
+#pragma unroll
+    for (int q = 0; q < FPE; ++q) acc[q] = 0.0;
+    acc[0] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < i; ++k) {
+      if constexpr (FPE == 1) acc[0] -= sM[i][k][0] * X[k][0];
+      else {
+        acc[0] -= sM[i][k][0] * X[k][0] - sM[i][k][1] * X[k][1];
+        acc[1] -= sM[i][k][0] * X[k][1] + sM[i][k][1] * X[k][0];
+      }
+    }
+    const double dii = sM[i][i][0];   // real diagonal
+#pragma unroll
+    for (int q = 0; q < FPE; ++q) X[i][q] = acc[q] / dii;
+  }
+  const bool dead_col = !(den[j0 + lane] > 0.f);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const bool dead = dead_col || !(den[j0 + i] > 0.f);
+    // X[i][lane] = element (row i, column lane); stored so that lane = ROW reads coalesced: [jj = column][row]
+#pragma unroll
+    for (int q = 0; q < FPE; ++q) out[((int64_t)lane * 32 + i) * FPE + q] = dead ? 0.f : (float)X[i][q];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One Kaczmarz iteration in ONE cooperative launch.  CTA c owns the columns [c P, (c+1) P) (P packs of 4 floats) of x
+// for the whole sweep, in shared memory; a block of R rows needs only ONE grid-wide exchange:
+//     every CTA:  partial t_j over its columns                      -> tpart, arrive
+//     CTA 0:      waits for all arrivals, runs the block recurrence -> alpha, ready flag
+//     every CTA:  waits for alpha, x_slice += sum_j alpha_j conj(a_j[slice])          (rows again, from L2)
+// and no second barrier, because nobody else touches a CTA's columns.  While waiting for alpha every CTA prefetches
+// its part of the next block into L2 (cp.async.bulk.prefetch), so the HBM stream overlaps the serial recurrence.
+// Every wait is bounded; a time-out raises the abort flag and all CTAs leave.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int KZ_PT = 512;            // threads of the persistent kernel
+constexpr int KZ_PW = KZ_PT / 32;
+constexpr int KZ_PMAX_R = 128;
+constexpr unsigned KZ_SPIN_LIMIT = 1u << 22;
+
+struct KzSweep {
+  const float* A; int64_t ldf; int64_t npacks;
+  const int32_t* rows; const float* denom; const float* G; const float* Dinv;
+  int R; int nblk; int P;
+  const float* u; float* vl; float ew; float* x;
+  float* tpart; float* alpha;
+  unsigned long long* sync; int* abort_flag;
+  unsigned long long epoch;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+// thread 0 waits until *p >= target (bounded), everybody learns whether to go on
+__device__ __forceinline__ bool kz_wait(const unsigned long long* p, unsigned long long target, int* abort_flag, int* s_flag) {
+  if (threadIdx.x == 0) {
+    unsigned spins = 0;
+    int ok = 1;
+    while (ld_acquire_u64(p) < target) {
+      if (++spins > KZ_SPIN_LIMIT || *((volatile int*)abort_flag)) { *abort_flag = 1; ok = 0; break; }
+      if (spins > 64) __nanosleep(32);
+    }
+    *s_flag = ok;
+  }
+  __syncthreads();
+  const bool ok = *s_flag != 0;
+  __syncthreads();
+  return ok;
+}
+
+template <int FPE, int IT>
+__global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
+  extern __shared__ float4 kz_smem4[];
+  __shared__ float s_alpha[KZ_PMAX_R * FPE];
+  __shared__ int s_rows[KZ_PMAX_R];
+  __shared__ float s_t[KZ_PMAX_R * FPE];
+  __shared__ int s_flag;
+  const int R = p.R, P = p.P;
+  float* sG = reinterpret_cast<float*>(kz_smem4);           // [R*R*FPE]   (CTA 0)
+  float4* xs4 = kz_smem4 + (size_t)R * R * FPE / 4;          // [P]
+  float4* red4 = xs4 + P;                                    // [KZ_PW][P]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = blockIdx.x, NC = gridDim.x;
+  const int64_t pk0 = (int64_t)cta * P;
+  const int np = (int)(p.npacks - pk0 < (int64_t)P ? (p.npacks - pk0 > 0 ? p.npacks - pk0 : 0) : P);
+  const float4* A4 = reinterpret_cast<const float4*>(p.A) + (np > 0 ? pk0 : 0);   // this CTA's first column pack
+  const int64_t ld4 = p.ldf / 4;
+  float4* x4 = reinterpret_cast<float4*>(p.x);
+  for (int i = tid; i < np; i += KZ_PT) xs4[i] = __ldcg(x4 + pk0 + i);
+  bool alive = true;
+  for (int b = 0; b < p.nblk && alive; ++b) {
+    const int32_t* rows_b = p.rows + (int64_t)b * R;
+    __syncthreads();                       // s_rows / s_alpha / red4 of the previous block are free; xs4 is complete
+    for (int i = tid; i < R; i += KZ_PT) s_rows[i] = rows_b[i];
+    if (cta == 0) {                        // the block's Gram matrix -> shared memory, asynchronously
+      const float4* g4 = reinterpret_cast<const float4*>(p.G + (int64_t)b * R * R * FPE);
+      const int n4 = R * R * FPE / 4;
+      for (int i = tid; i < n4; i += KZ_PT) {
+        unsigned dst = (unsigned)__cvta_generic_to_shared(kz_smem4 + i);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(g4 + i) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __syncthreads();
+    // ---- partial t_j over this CTA's columns: warp w takes rows w, w+16, ... two at a time
+    for (int j = warp; j < R; j += 2 * KZ_PW) {
+      float4 a[2][IT];
+      int rowv[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        rowv[h] = s_rows[j + h * KZ_PW];
+        const float4* ap = A4 + (int64_t)(rowv[h] < 0 ? 0 : rowv[h]) * ld4;
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+          const int pk = it * 32 + lane;
+          a[h][it] = __ldg(ap + (pk < np ? pk : 0));
+        }
+      }
+      __syncwarp();                        // keeps the 2 x IT loads ahead of their consumers
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float acc[FPE];
+#pragma unroll
+        for (int q = 0; q < FPE; ++q) acc[q] = 0.f;
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+          const int pk = it * 32 + lane;
+          if (pk < np) {
+            const float4 xv = xs4[pk];
+            const float av[4] = {a[h][it].x, a[h][it].y, a[h][it].z, a[h][it].w};
+            const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+            dot_acc<FPE, 4>(av, xa, acc);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < FPE; ++q) acc[q] = warp_sum(acc[q]);
+        if (lane == 0) {
+#pragma unroll
+          for (int q = 0; q < FPE; ++q) p.tpart[((int64_t)cta * R + j + h * KZ_PW) * FPE + q] = rowv[h] < 0 ? 0.f : acc[q];
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { __threadfence(); atomicAdd(p.sync, 1ull); }
+    // ---- the next block's rows (this CTA's columns) -> L2 while the recurrence runs
+    if (b + 1 < p.nblk && np > 0) {
+      const int32_t* rows_n = p.rows + (int64_t)(b + 1) * R;
+      for (int j = tid; j < R; j += KZ_PT) {
+        const int row = rows_n[j];
+        if (row >= 0) {
+          const float4* src = A4 + (int64_t)row * ld4;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(np * 16) : "memory");
+        }
+      }
+    }
+    // ---- CTA 0: the block recurrence
+    if (cta == 0) {
+      const int k = tid;
+      const bool mine_row = k < R;
+      const int row = mine_row ? s_rows[k] : -1;
+      float dv[32][FPE];                   // this row of the inverted diagonal block: Dinv[jj][k]
+      float uu[FPE], vv[FPE];
+#pragma unroll
+      for (int q = 0; q < FPE; ++q) { uu[q] = 0.f; vv[q] = 0.f; }
+      if (mine_row) {
+        const float* dp = p.Dinv + (((int64_t)b * (R / 32) + (k >> 5)) * 32 * 32) * FPE;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+#pragma unroll
+          for (int q = 0; q < FPE; ++q) dv[jj][q] = __ldg(dp + ((int64_t)jj * 32 + lane) * FPE + q);
+        if (row >= 0) {
+#pragma unroll
+          for (int q = 0; q < FPE; ++q) { uu[q] = __ldcg(p.u + (int64_t)row * FPE + q); vv[q] = __ldcg(p.vl + (int64_t)row * FPE + q); }
+        }
+      }
+      alive = kz_wait(p.sync, (p.epoch + (unsigned long long)b + 1ull) * (unsigned long long)NC, p.abort_flag, &s_flag);
+      if (alive) {
+        // t_k = sum over CTAs: TPR threads per row, fixed order, then a shuffle tree
+        const int TPR = KZ_PT / R;         // 4 (R = 128) or 8 (R = 64)
+        const int kr = tid / TPR, part = tid % TPR;
+        float tp[FPE];
+#pragma unroll
+        for (int q = 0; q < FPE; ++q) tp[q] = 0.f;
+        for (int c = part; c < NC; c += TPR)
+#pragma unroll
+          for (int q = 0; q < FPE; ++q) tp[q] += __ldcg(p.tpart + ((int64_t)c * R + kr) * FPE + q);
+#pragma unroll
+        for (int q = 0; q < FPE; ++q)
+          for (int o = TPR >> 1; o > 0; o >>= 1) tp[q] += __shfl_xor_sync(0xffffffffu, tp[q], o);
+        if (part == 0) {
+#pragma unroll
+          for (int q = 0; q < FPE; ++q) s_t[kr * FPE + q] = tp[q];
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        float r[FPE], c[FPE];
+#pragma unroll
+        for (int q = 0; q < FPE; ++q) { c[q] = 0.f; r[q] = 0.f; }
+        if (mine_row) {
+#pragma unroll
+          for (int q = 0; q < FPE; ++q) r[q] = fsub(fsub(uu[q], s_t[k * FPE + q]), fmul(p.ew, vv[q]));   // u - t - eps_w vl
+        }
+        const int nb = R >> 5;
+        for (int jb = 0; jb < nb; ++jb) {
+          const int j0 = jb << 5;
+          if (mine_row && warp == jb) {
+            float rr[FPE], al[FPE];
+#pragma unroll
+            for (int q = 0; q < FPE; ++q) { rr[q] = fsub(r[q], c[q]); al[q] = 0.f; }
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              float rj[FPE];
+#pragma unroll
+              for (int q = 0; q < FPE; ++q) rj[q] = __shfl_sync(0xffffffffu, rr[q], jj);
+              mul_acc<FPE>(dv[jj], rj, al);      // alpha_k += Minv[k][jj] r_jj   (zero above the diagonal)
+            }
+#pragma unroll
+            for (int q = 0; q < FPE; ++q) {
+              s_alpha[k * FPE + q] = al[q];
+              p.alpha[k * FPE + q] = al[q];
+              if (row >= 0) p.vl[(int64_t)row * FPE + q] = fadd(vv[q], fmul(al[q], p.ew));   // Kaczmarz.jl:309
+            }
+          }
+          __syncthreads();
+          if (mine_row && k >= j0 + 32) {
+#pragma unroll 8
+            for (int jj = 0; jj < 32; ++jj) {
+              float al[FPE], g[FPE];
+#pragma unroll
+              for (int q = 0; q < FPE; ++q) {
+                al[q] = s_alpha[(j0 + jj) * FPE + q];
+                g[q] = sG[((int64_t)(j0 + jj) * R + k) * FPE + q];
+              }
+              mul_acc<FPE>(al, g, c);
+            }
+          }
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); st_release_u64(p.sync + 1, p.epoch + (unsigned long long)b + 1ull); }
+      }
+    } else {
+      alive = kz_wait(p.sync + 1, p.epoch + (unsigned long long)b + 1ull, p.abort_flag, &s_flag);
+      if (alive) {
+        for (int i = tid; i < R * FPE; i += KZ_PT) s_alpha[i] = __ldcg(p.alpha + i);
+      }
+    }
+    if (!alive) break;
+    __syncthreads();
+    // ---- x_slice += sum_j alpha_j conj(a_j[slice]); rows again (L2), warp w takes rows w, w+16, ...
+    float4 acc4[IT];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) acc4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = warp; j < R; j += 2 * KZ_PW) {
+      float4 a[2][IT];
+      int rowv[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        rowv[h] = s_rows[j + h * KZ_PW];
+        const float4* ap = A4 + (int64_t)(rowv[h] < 0 ? 0 : rowv[h]) * ld4;
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+          const int pk = it * 32 + lane;
+          a[h][it] = __ldcs(ap + (pk < np ? pk : 0));     // last use of the block
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float al[FPE];
+#pragma unroll
+        for (int q = 0; q < FPE; ++q) al[q] = s_alpha[(j + h * KZ_PW) * FPE + q];   // 0 for padding rows
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+          const float av[4] = {a[h][it].x, a[h][it].y, a[h][it].z, a[h][it].w};
+          float ac[4] = {acc4[it].x, acc4[it].y, acc4[it].z, acc4[it].w};
+          upd_acc<FPE, 4>(al, av, ac);
+          acc4[it] = make_float4(ac[0], ac[1], ac[2], ac[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int pk = it * 32 + lane;
+      if (pk < np) red4[(size_t)warp * P + pk] = acc4[it];
+    }
+    __syncthreads();
+    for (int i = tid; i < np; i += KZ_PT) {
+      float4 v = xs4[i];
+#pragma unroll
+      for (int w = 0; w < KZ_PW; ++w) {
+        const float4 t = red4[(size_t)w * P + i];
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+      }
+      xs4[i] = v;
+    }
+  }
+  __syncthreads();
+  if (alive)
+    for (int i = tid; i < np; i += KZ_PT) x4[pk0 + i] = xs4[i];
+}
+
 void kz_free(rls_kaczmarz_s* K) {
   if (!K) return;
   cudaFree(K->d_rows); cudaFree(K->d_denom); cudaFree(K->d_G); cudaFree(K->d_tpart); cudaFree(K->d_alpha); cudaFree(K->d_s2);
+  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_sync); cudaFree(K->d_abort);
   if (K->x) rls_vec_destroy(K->x);
   if (K->vl) rls_vec_destroy(K->vl);
   if (K->u) rls_vec_destroy(K->u);
@@ -469,6 +821,52 @@ void kz_free(rls_kaczmarz_s* K) {
 }
 
 }  // namespace
+
+// persistent-kernel plan for the current row order: inverted diagonal blocks, exchange buffers, launch geometry
+static int32_t kz_plan_persistent(rls_kaczmarz_s* K) {
+  rls_ctx_s* c = K->ctx;
+  const int R = K->R, fpe = K->fpe;
+  K->persistent = false;
+  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_sync); cudaFree(K->d_abort);
+  K->d_Dinv = nullptr; K->d_tpart2 = nullptr; K->d_sync = nullptr; K->d_abort = nullptr;
+  if (!rls_env_flag("RLS_KACZMARZ_PERSISTENT", true)) return RLS_OK;
+  if (!K->vec4 || !(R == 64 || R == 128) || K->nblk == 0 || K->nblk > 0x7fffffff) return RLS_OK;
+  const int64_t npacks = K->A->n * fpe / 4;
+  int NC = (int)std::min<int64_t>(c->sm_count, npacks);
+  const int P = (int)((npacks + NC - 1) / NC);
+  if (P > 256) return RLS_OK;
+  NC = (int)((npacks + P - 1) / P);
+  const int IT = P <= 128 ? 4 : 8;
+  const size_t smem = ((size_t)R * R * fpe + (size_t)(1 + KZ_PW) * P * 4) * 4;
+  const void* fn = fpe == 2 ? (IT == 4 ? (const void*)kz_sweep_kernel<2, 4> : (const void*)kz_sweep_kernel<2, 8>)
+                            : (IT == 4 ? (const void*)kz_sweep_kernel<1, 4> : (const void*)kz_sweep_kernel<1, 8>);
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return RLS_OK; }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, KZ_PT, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return RLS_OK; }
+  if (NC > per_sm * c->sm_count) return RLS_OK;
+  if (cudaMalloc(&K->d_Dinv, (size_t)K->nblk * R * 32 * fpe * 4) != cudaSuccess || cudaMalloc(&K->d_tpart2, (size_t)NC * R * fpe * 4) != cudaSuccess ||
+      cudaMalloc(&K->d_sync, 2 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&K->d_abort, sizeof(int)) != cudaSuccess) {
+    rls_set_error("Kaczmarz: cudaMalloc of the sweep-kernel buffers failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return RLS_ERR_NOMEM;
+  }
+  RLS_CUDA(cudaMemsetAsync(K->d_sync, 0, 2 * sizeof(unsigned long long), c->stream));
+  RLS_CUDA(cudaMemsetAsync(K->d_abort, 0, sizeof(int), c->stream));
+  K->epoch = 0;
+  for (int64_t b0 = 0; b0 < K->nblk; b0 += 32768) {
+    const int64_t nb = std::min<int64_t>(32768, K->nblk - b0);
+    dim3 grid((unsigned)(R / 32), (unsigned)nb);
+    const float* Gp = K->d_G + b0 * (int64_t)R * R * fpe;
+    const float* dp = K->d_denom + b0 * R;
+    float* op = K->d_Dinv + b0 * (int64_t)R * 32 * fpe;
+    if (fpe == 2) kz_dinv_kernel<2><<<grid, 32, 0, c->stream>>>(Gp, dp, R, op);
+    else kz_dinv_kernel<1><<<grid, 32, 0, c->stream>>>(Gp, dp, R, op);
+    c->launches++;
+  }
+  RLS_CUDA(cudaGetLastError());
+  K->pgrid = NC; K->pP = P; K->pIT = IT; K->psmem = smem;
+  K->persistent = true;
+  return RLS_OK;
+}
 
 extern "C" int32_t rls_kaczmarz_create(rls_mat_t A, int32_t block_rows, rls_kaczmarz_t* out) {
   RLS_CHECK_ARG(A && out, "NULL argument");
@@ -487,7 +885,7 @@ extern "C" int32_t rls_kaczmarz_create(rls_mat_t A, int32_t block_rows, rls_kacz
     // a block should stay L2-resident between its two passes: <= 32 MB
     const int64_t row_bytes = A->n * (int64_t)fpe * 4;
     int64_t r = (32ll << 20) / (row_bytes > 0 ? row_bytes : 1);
-    R = r >= 192 && fpe == 1 ? 192 : r >= 128 ? 128 : 64;   // Gram block <= 200 KB: staged in shared memory
+    R = r >= 128 ? 128 : 64;   // 64 / 128: the persistent sweep kernel keeps the block's Gram matrix in shared memory
   }
   RLS_CHECK_ARG(R == 64 || R == 128 || R == 192 || R == 256, "Kaczmarz: block_rows must be 64, 128, 192 or 256 (got %d)", R);
   rls_kaczmarz_s* K = new rls_kaczmarz_s();
@@ -584,6 +982,7 @@ extern "C" int32_t rls_kaczmarz_set_rows(rls_kaczmarz_t K, const int64_t* rows, 
     c->launches++;
   }
   RLS_CUDA(cudaGetLastError());
+  RLS_TRY(kz_plan_persistent(K));
   return RLS_OK;
 }
 
@@ -598,6 +997,11 @@ extern "C" int32_t rls_kaczmarz_init(rls_kaczmarz_t K, rls_vec_t b, rls_vec_t x0
   else RLS_CUDA(cudaMemsetAsync(K->x->d, 0, (size_t)K->A->n * es, c->stream));
   RLS_CUDA(cudaMemsetAsync(K->vl->d, 0, (size_t)K->A->m * es, c->stream));
   RLS_CUDA(cudaMemcpyAsync(K->u->d, b->d, (size_t)K->A->m * es, cudaMemcpyDeviceToDevice, c->stream));
+  if (K->d_sync) {
+    RLS_CUDA(cudaMemsetAsync(K->d_sync, 0, 2 * sizeof(unsigned long long), c->stream));
+    RLS_CUDA(cudaMemsetAsync(K->d_abort, 0, sizeof(int), c->stream));
+    K->epoch = 0;
+  }
   K->eps_w = eps_w;
   K->initialised = true;
   return RLS_OK;
@@ -616,10 +1020,12 @@ static int32_t kz_sweep_impl(rls_kaczmarz_s* K) {
   const size_t gbytes = (size_t)R * R * FPE * 4;
   const bool stage = gbytes <= 200 * 1024;
   if (stage) RLS_CUDA(cudaFuncSetAttribute(kz_solve_kernel<FPE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gbytes));
+  int skip = 0;   // RLS_KACZMARZ_SKIP: timing experiments only (1 = dot, 2 = solve, 4 = update); results are wrong
+  if (const char* e = getenv("RLS_KACZMARZ_SKIP")) skip = atoi(e);
   for (int64_t b = 0; b < K->nblk; ++b) {
     const int32_t* rows = K->d_rows + b * R;
-    RLS_CUDA(rls_launch_pdl(c->stream, gdot, dim3(KZ_DOT_THREADS), kz_dot_kernel<FPE, NF>, A, ldf, nfl, rows, R, (const float*)x, K->d_tpart));
-    {
+    if (!(skip & 1)) RLS_CUDA(rls_launch_pdl(c->stream, gdot, dim3(KZ_DOT_THREADS), kz_dot_kernel<FPE, NF>, A, ldf, nfl, rows, R, (const float*)x, K->d_tpart));
+    if (!(skip & 2)) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(1); cfg.blockDim = dim3(R); cfg.dynamicSmemBytes = stage ? gbytes : 0; cfg.stream = c->stream;
       cudaLaunchAttribute at[1];
@@ -634,7 +1040,7 @@ static int32_t kz_sweep_impl(rls_kaczmarz_s* K) {
       RLS_CUDA(cudaLaunchKernelEx(&cfg, stage ? kz_solve_kernel<FPE, true> : kz_solve_kernel<FPE, false>, rows, den, Gb, R, tp, K->S, uu, vl,
                                   K->eps_w, K->d_alpha));
     }
-    RLS_CUDA(rls_launch_pdl(c->stream, gupd, dim3(KZ_UPD_THREADS), kz_update_kernel<FPE, NF>, A, ldf, nfl, rows, R, (const float*)K->d_alpha, x));
+    if (!(skip & 4)) RLS_CUDA(rls_launch_pdl(c->stream, gupd, dim3(KZ_UPD_THREADS), kz_update_kernel<FPE, NF>, A, ldf, nfl, rows, R, (const float*)K->d_alpha, x));
     c->launches += 3;
   }
   return RLS_OK;
@@ -644,6 +1050,22 @@ extern "C" int32_t rls_kaczmarz_sweep(rls_kaczmarz_t K) {
   RLS_CHECK_ARG(K, "NULL argument");
   RLS_CHECK_ARG(K->initialised, "Kaczmarz sweep before init");
   RlsDeviceGuard g(K->ctx->device);
+  if (K->persistent && K->nblk > 0) {
+    rls_ctx_s* c = K->ctx;
+    KzSweep sp;
+    sp.A = (const float*)K->A->d; sp.ldf = K->A->ld * K->fpe; sp.npacks = K->A->n * K->fpe / 4;
+    sp.rows = K->d_rows; sp.denom = K->d_denom; sp.G = K->d_G; sp.Dinv = K->d_Dinv;
+    sp.R = K->R; sp.nblk = (int)K->nblk; sp.P = K->pP;
+    sp.u = (const float*)K->u->d; sp.vl = (float*)K->vl->d; sp.ew = K->eps_w; sp.x = (float*)K->x->d;
+    sp.tpart = K->d_tpart2; sp.alpha = K->d_alpha; sp.sync = K->d_sync; sp.abort_flag = K->d_abort; sp.epoch = K->epoch;
+    const void* fn = K->fpe == 2 ? (K->pIT == 4 ? (const void*)kz_sweep_kernel<2, 4> : (const void*)kz_sweep_kernel<2, 8>)
+                                 : (K->pIT == 4 ? (const void*)kz_sweep_kernel<1, 4> : (const void*)kz_sweep_kernel<1, 8>);
+    void* args[] = {&sp};
+    RLS_CUDA(cudaLaunchCooperativeKernel(fn, dim3(K->pgrid), dim3(KZ_PT), args, K->psmem, c->stream));
+    c->launches++;
+    K->epoch += (unsigned long long)K->nblk;
+    return RLS_OK;
+  }
   if (K->fpe == 2) return K->vec4 ? kz_sweep_impl<2, 4>(K) : kz_sweep_impl<2, 2>(K);
   return K->vec4 ? kz_sweep_impl<1, 4>(K) : kz_sweep_impl<1, 1>(K);
 }
@@ -674,5 +1096,30 @@ extern "C" int32_t rls_kaczmarz_debug(rls_kaczmarz_t K, int32_t which, float* ho
   RLS_CHECK_ARG(nfloats <= have, "kaczmarz_debug: %lld floats requested, %lld available", (long long)nfloats, (long long)have);
   RLS_CUDA(cudaMemcpyAsync(host, src, (size_t)nfloats * 4, cudaMemcpyDeviceToHost, K->ctx->stream));
   RLS_CUDA(cudaStreamSynchronize(K->ctx->stream));
+  return RLS_OK;
+}
+
+// synchronise and report a timed-out exchange of the persistent sweep kernel (bounded waits raise an abort flag)
+extern "C" int32_t rls_kaczmarz_check(rls_kaczmarz_t K) {
+  RLS_CHECK_ARG(K, "NULL argument");
+  RlsDeviceGuard g(K->ctx->device);
+  int flag = 0;
+  if (K->d_abort) RLS_CUDA(cudaMemcpyAsync(&flag, K->d_abort, sizeof(int), cudaMemcpyDeviceToHost, K->ctx->stream));
+  RLS_CUDA(cudaStreamSynchronize(K->ctx->stream));
+  if (flag) {
+    rls_set_error("Kaczmarz sweep kernel timed out waiting for the block exchange (abort flag set)");
+    return RLS_ERR_CUDA;
+  }
+  return RLS_OK;
+}
+
+/* "sweep: one cooperative kernel ..." or "sweep: 3 kernels per block ..." */
+extern "C" int32_t rls_kaczmarz_describe(rls_kaczmarz_t K, char* buf, int32_t len) {
+  RLS_CHECK_ARG(K && buf && len > 0, "bad argument");
+  if (K->persistent)
+    snprintf(buf, (size_t)len, "persistent: grid=%d x %d threads, %d packs of x per CTA, smem=%zu, block_rows=%d, blocks=%lld", K->pgrid, KZ_PT,
+             K->pP, K->psmem, K->R, (long long)K->nblk);
+  else
+    snprintf(buf, (size_t)len, "chained: 3 kernels per block, block_rows=%d, blocks=%lld, vec4=%d", K->R, (long long)K->nblk, (int)K->vec4);
   return RLS_OK;
 }

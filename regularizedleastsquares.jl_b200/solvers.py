@@ -591,9 +591,16 @@ class Kaczmarz(AbstractLinearSolver):
         capi.call("rls_vec_len", h, C.byref(ln), C.byref(dt))
         return B200Vector(self.ctx, self.dtype, ln.value, _handle=h, _owned=False)
 
+    def describe(self):
+        """kernel plan of the sweep ("persistent: ..." = one cooperative kernel per iteration, "chained: ..." otherwise)"""
+        buf = C.create_string_buffer(256)
+        capi.call("rls_kaczmarz_describe", self._handle, buf, 256)
+        return buf.value.decode()
+
     @property
     def x(self):
         """solversolution(solver): the Tikhonov-matrix form returns x ./ sqrt.(λ) (:253-256)"""
+        capi.call("rls_kaczmarz_check", self._handle)
         x = self._vec("x").to_numpy()
         if self._tikhonov is not None:
             x = (x * (np.float32(1) / np.sqrt(self._tikhonov))).astype(self.dtype)
@@ -662,7 +669,10 @@ class Kaczmarz(AbstractLinearSolver):
             k += 1
             for cb in cbs:
                 cb(self, k)
-        return self.x if host_in or self._tikhonov is not None else self._vec("x")
+        if host_in or self._tikhonov is not None:
+            return self.x
+        capi.call("rls_kaczmarz_check", self._handle)
+        return self._vec("x")
 
     def convergence(self):
         """solverconvergence :258: ‖A x − u‖"""

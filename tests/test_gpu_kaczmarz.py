@@ -13,6 +13,14 @@ TOL = 1e-5
 DTYPES = [np.float32, np.complex64]
 
 
+@pytest.fixture(autouse=True, params=["persistent", "chained"])
+def sweep_path(request, monkeypatch):
+    """every test runs on both sweep implementations: one cooperative kernel per iteration, and three chained kernels
+    per block (the path for block sizes / shapes the persistent kernel does not take)"""
+    monkeypatch.setenv("RLS_KACZMARZ_PERSISTENT", "1" if request.param == "persistent" else "0")
+    return request.param
+
+
 def system(dtype, m, n, seed=300):
     A, _ = rand_matrix(dtype, m, n, seed)
     xt = rand_vector(dtype, n, seed + 1)
@@ -57,10 +65,11 @@ def test_block_sizes_and_float64_lambda(rls, ctx, dtype, block_rows):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_larger_system(rls, ctx, dtype):
-    """rows of 16384 elements: several column chunks in the dot kernel, blocks of 256 rows"""
+def test_larger_system(rls, ctx, dtype, sweep_path):
+    """rows of 16384 elements: several column chunks in the dot kernel / more than one pack per lane in the sweep kernel"""
     A, xt, b = system(dtype, 1024, 16384, seed=320)
     S = rls.createLinearSolver(rls.Kaczmarz, A, reg=rls.L2Regularization(np.float32(1e-2)), iterations=3)
+    assert S.init_(b).describe().startswith(sweep_path)
     R = O.createLinearSolver(O.Kaczmarz, A, reg=O.L2Regularization(np.float32(1e-2)), iterations=3)
     stepwise(S, R, b, 3)
 

@@ -65,20 +65,35 @@ def timing(dtype, m, n, sweeps=5):
         k += 1
     ms = ctx.timer_stop()
     bytes_ = m * n * np.dtype(dtype).itemsize
-    print(f"[timing {np.dtype(dtype).name} {m}x{n}] block_rows {S.block_rows}, setup+gram {gram_ms:.1f} ms (wall incl. create "
+    print(f"[timing {np.dtype(dtype).name} {m}x{n}] {S.describe()} | block_rows {S.block_rows}, setup+gram {gram_ms:.1f} ms (wall incl. create "
           f"{time.perf_counter() - t0:.2f} s), {k} sweeps: {ms / k:.3f} ms per sweep = {bytes_ / (ms / k) / 1e6:.0f} GB/s of A, "
           f"{(ctx.launch_count() - n0) // k} launches per sweep, |x| {np.linalg.norm(S.x):.4e}")
 
 
 if __name__ == "__main__":
-    for dt in (() if "--time-only" in sys.argv else (np.float32, np.complex64)):
+    for dt in (() if ("--time-only" in sys.argv or "--components" in sys.argv) else (np.float32, np.complex64)):
         check(dt, 300, 200, 64)
         check(dt, 150, 67, 128)
         check(dt, 520, 4100, 256)
-    if "--time-only" in sys.argv:
+    if "--components" in sys.argv:
+        os.environ["RLS_KACZMARZ_PERSISTENT"] = "0"
+        for skip in (0, 1, 2, 4, 3, 5, 6):
+            os.environ["RLS_KACZMARZ_SKIP"] = str(skip)
+            print("skip mask", skip, end=" ")
+            timing(np.float32, 16384, 65536, sweeps=3)
+        os.environ["RLS_KACZMARZ_SKIP"] = "0"
+        os.environ["RLS_PDL"] = "0"
+        print("no PDL", end=" ")
+        timing(np.float32, 16384, 65536, sweeps=3)
+    elif "--time-only" in sys.argv:
         timing(np.float32, 16384, 65536, sweeps=2)
     elif "--time" in sys.argv:
         timing(np.float32, 16384, 65536)
         timing(np.complex64, 8192, 65536)
-        os.environ["RLS_KACZMARZ_BLOCK"] = "256"
+        os.environ["RLS_KACZMARZ_BLOCK"] = "64"
+        timing(np.float32, 16384, 65536)
+        os.environ["RLS_KACZMARZ_BLOCK"] = "128"
+        timing(np.complex64, 8192, 65536)
+        del os.environ["RLS_KACZMARZ_BLOCK"]
+        os.environ["RLS_KACZMARZ_PERSISTENT"] = "0"
         timing(np.float32, 16384, 65536)
