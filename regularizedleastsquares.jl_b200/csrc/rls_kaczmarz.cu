@@ -50,6 +50,7 @@ struct rls_kaczmarz_s {
   unsigned long long* d_sync = nullptr;   // [0] arrivals, [1] alpha-ready, both monotonic
   int* d_abort = nullptr;
   unsigned long long epoch = 0;           // blocks completed since the counters were reset
+  long long* d_trace = nullptr;
   int pgrid = 0, pP = 0, pIT = 0;
   size_t psmem = 0;
   bool persistent = false;
@@ -552,6 +553,7 @@ struct KzSweep {
   float* tpart; float* alpha;
   unsigned long long* sync; int* abort_flag;
   unsigned long long epoch;
+  long long* trace; int trace_block;   // RLS_KACZMARZ_TRACE: clock64 stamps of CTA 0 and CTA 5 in one block
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -581,10 +583,11 @@ __device__ __forceinline__ bool kz_wait(const unsigned long long* p, unsigned lo
 
 template <int FPE, int IT>
 __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
+  constexpr int HB = 16 / IT;   // rows per batch: HB x IT 128-bit loads in flight per thread
   extern __shared__ float4 kz_smem4[];
   __shared__ float s_alpha[KZ_PMAX_R * FPE];
   __shared__ int s_rows[KZ_PMAX_R];
-  __shared__ float s_t[KZ_PMAX_R * FPE];
+  __shared__ __align__(16) float s_t[KZ_PMAX_R * FPE];
   __shared__ int s_flag;
   const int R = p.R, P = p.P;
   float* sG = reinterpret_cast<float*>(kz_smem4);           // [R*R*FPE]   (CTA 0)
@@ -599,26 +602,33 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
   float4* x4 = reinterpret_cast<float4*>(p.x);
   for (int i = tid; i < np; i += KZ_PT) xs4[i] = __ldcg(x4 + pk0 + i);
   bool alive = true;
+#define KZ_STAMP(i) do { if (p.trace && b == p.trace_block && tid == 0 && (cta == 0 || cta == 5)) p.trace[(cta ? 16 : 0) + (i)] = clock64(); } while (0)
   for (int b = 0; b < p.nblk && alive; ++b) {
     const int32_t* rows_b = p.rows + (int64_t)b * R;
+    KZ_STAMP(0);
     __syncthreads();                       // s_rows / s_alpha / red4 of the previous block are free; xs4 is complete
     for (int i = tid; i < R; i += KZ_PT) s_rows[i] = rows_b[i];
     if (cta == 0) {                        // the block's Gram matrix -> shared memory, asynchronously
-      const float4* g4 = reinterpret_cast<const float4*>(p.G + (int64_t)b * R * R * FPE);
+      // (its 32x32 diagonal blocks are replaced by their inverted counterparts from Dinv: same [column][row] layout)
+      const float* gsrc = p.G + (int64_t)b * R * R * FPE;
+      const float* dsrc = p.Dinv + (int64_t)b * R * 32 * FPE;
       const int n4 = R * R * FPE / 4;
       for (int i = tid; i < n4; i += KZ_PT) {
+        const int f = i * 4, jc = f / (R * FPE), kr = (f - jc * R * FPE) / FPE;
+        const float* src = (jc >> 5) == (kr >> 5) ? dsrc + ((int64_t)jc * 32 + (kr & 31)) * FPE : gsrc + f;
         unsigned dst = (unsigned)__cvta_generic_to_shared(kz_smem4 + i);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(g4 + i) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
     __syncthreads();
-    // ---- partial t_j over this CTA's columns: warp w takes rows w, w+16, ... two at a time
-    for (int j = warp; j < R; j += 2 * KZ_PW) {
-      float4 a[2][IT];
-      int rowv[2];
+    KZ_STAMP(1);
+    // ---- partial t_j over this CTA's columns: warp w takes rows w, w+16, ... HB at a time
+    for (int j = warp; j < R; j += HB * KZ_PW) {
+      float4 a[HB][IT];
+      int rowv[HB];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < HB; ++h) {
         rowv[h] = s_rows[j + h * KZ_PW];
         const float4* ap = A4 + (int64_t)(rowv[h] < 0 ? 0 : rowv[h]) * ld4;
 #pragma unroll
@@ -627,9 +637,9 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
           a[h][it] = __ldg(ap + (pk < np ? pk : 0));
         }
       }
-      __syncwarp();                        // keeps the 2 x IT loads ahead of their consumers
+      __syncwarp();                        // keeps the HB x IT loads ahead of their consumers
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < HB; ++h) {
         float acc[FPE];
 #pragma unroll
         for (int q = 0; q < FPE; ++q) acc[q] = 0.f;
@@ -652,7 +662,9 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
       }
     }
     __syncthreads();
+    KZ_STAMP(2);
     if (tid == 0) { __threadfence(); atomicAdd(p.sync, 1ull); }
+    KZ_STAMP(3);
     // ---- the next block's rows (this CTA's columns) -> L2 while the recurrence runs
     if (b + 1 < p.nblk && np > 0) {
       const int32_t* rows_n = p.rows + (int64_t)(b + 1) * R;
@@ -664,46 +676,54 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
         }
       }
     }
+    KZ_STAMP(4);
     // ---- CTA 0: the block recurrence
     if (cta == 0) {
       const int k = tid;
       const bool mine_row = k < R;
       const int row = mine_row ? s_rows[k] : -1;
-      float dv[32][FPE];                   // this row of the inverted diagonal block: Dinv[jj][k]
       float uu[FPE], vv[FPE];
 #pragma unroll
       for (int q = 0; q < FPE; ++q) { uu[q] = 0.f; vv[q] = 0.f; }
       if (mine_row) {
-        const float* dp = p.Dinv + (((int64_t)b * (R / 32) + (k >> 5)) * 32 * 32) * FPE;
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj)
-#pragma unroll
-          for (int q = 0; q < FPE; ++q) dv[jj][q] = __ldg(dp + ((int64_t)jj * 32 + lane) * FPE + q);
         if (row >= 0) {
 #pragma unroll
           for (int q = 0; q < FPE; ++q) { uu[q] = __ldcg(p.u + (int64_t)row * FPE + q); vv[q] = __ldcg(p.vl + (int64_t)row * FPE + q); }
         }
       }
       alive = kz_wait(p.sync, (p.epoch + (unsigned long long)b + 1ull) * (unsigned long long)NC, p.abort_flag, &s_flag);
+      KZ_STAMP(5);
       if (alive) {
-        // t_k = sum over CTAs: TPR threads per row, fixed order, then a shuffle tree
-        const int TPR = KZ_PT / R;         // 4 (R = 128) or 8 (R = 64)
-        const int kr = tid / TPR, part = tid % TPR;
-        float tp[FPE];
+        // t = sum of the CTAs' partials: thread = (4 consecutive floats of t, part); each part sums its CTAs in a fixed
+        // order with 10 independent 128-bit loads in flight, then a shuffle tree over the parts
+        {
+          const int nq = R * FPE / 4;            // float4s of t
+          const int parts = KZ_PT / nq;          // 8, 16 or 32: a power of two, parts of one float4 sit in one warp
+          const int qd = tid / parts, part = tid % parts;
+          const float4* tp4 = reinterpret_cast<const float4*>(p.tpart);
+          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c0 = part; c0 < NC; c0 += parts * 10) {
+            float4 v[10];
 #pragma unroll
-        for (int q = 0; q < FPE; ++q) tp[q] = 0.f;
-        for (int c = part; c < NC; c += TPR)
+            for (int i = 0; i < 10; ++i) {
+              const int c = c0 + i * parts;
+              v[i] = c < NC ? __ldcg(tp4 + (int64_t)c * nq + qd) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-          for (int q = 0; q < FPE; ++q) tp[q] += __ldcg(p.tpart + ((int64_t)c * R + kr) * FPE + q);
-#pragma unroll
-        for (int q = 0; q < FPE; ++q)
-          for (int o = TPR >> 1; o > 0; o >>= 1) tp[q] += __shfl_xor_sync(0xffffffffu, tp[q], o);
-        if (part == 0) {
-#pragma unroll
-          for (int q = 0; q < FPE; ++q) s_t[kr * FPE + q] = tp[q];
+            for (int i = 0; i < 10; ++i) { sum.x += v[i].x; sum.y += v[i].y; sum.z += v[i].z; sum.w += v[i].w; }
+          }
+          for (int o = parts >> 1; o > 0; o >>= 1) {
+            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+            sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
+            sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
+          }
+          if (part == 0) reinterpret_cast<float4*>(s_t)[qd] = sum;
         }
+        KZ_STAMP(6);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        KZ_STAMP(7);
         float r[FPE], c[FPE];
 #pragma unroll
         for (int q = 0; q < FPE; ++q) { c[q] = 0.f; r[q] = 0.f; }
@@ -723,7 +743,10 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
               float rj[FPE];
 #pragma unroll
               for (int q = 0; q < FPE; ++q) rj[q] = __shfl_sync(0xffffffffu, rr[q], jj);
-              mul_acc<FPE>(dv[jj], rj, al);      // alpha_k += Minv[k][jj] r_jj   (zero above the diagonal)
+              float dv[FPE];                     // Minv[k][jj], staged in place of G's diagonal block
+#pragma unroll
+              for (int q = 0; q < FPE; ++q) dv[q] = sG[((int64_t)(j0 + jj) * R + k) * FPE + q];
+              mul_acc<FPE>(dv, rj, al);          // alpha_k += Minv[k][jj] r_jj   (zero above the diagonal)
             }
 #pragma unroll
             for (int q = 0; q < FPE; ++q) {
@@ -747,7 +770,9 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
           }
         }
         __syncthreads();
+        KZ_STAMP(8);
         if (tid == 0) { __threadfence(); st_release_u64(p.sync + 1, p.epoch + (unsigned long long)b + 1ull); }
+        KZ_STAMP(9);
       }
     } else {
       alive = kz_wait(p.sync + 1, p.epoch + (unsigned long long)b + 1ull, p.abort_flag, &s_flag);
@@ -757,15 +782,16 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
     }
     if (!alive) break;
     __syncthreads();
+    KZ_STAMP(10);
     // ---- x_slice += sum_j alpha_j conj(a_j[slice]); rows again (L2), warp w takes rows w, w+16, ...
     float4 acc4[IT];
 #pragma unroll
     for (int it = 0; it < IT; ++it) acc4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = warp; j < R; j += 2 * KZ_PW) {
-      float4 a[2][IT];
-      int rowv[2];
+    for (int j = warp; j < R; j += HB * KZ_PW) {
+      float4 a[HB][IT];
+      int rowv[HB];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < HB; ++h) {
         rowv[h] = s_rows[j + h * KZ_PW];
         const float4* ap = A4 + (int64_t)(rowv[h] < 0 ? 0 : rowv[h]) * ld4;
 #pragma unroll
@@ -776,7 +802,7 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
       }
       __syncwarp();
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < HB; ++h) {
         float al[FPE];
 #pragma unroll
         for (int q = 0; q < FPE; ++q) al[q] = s_alpha[(j + h * KZ_PW) * FPE + q];   // 0 for padding rows
@@ -795,6 +821,7 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
       if (pk < np) red4[(size_t)warp * P + pk] = acc4[it];
     }
     __syncthreads();
+    KZ_STAMP(11);
     for (int i = tid; i < np; i += KZ_PT) {
       float4 v = xs4[i];
 #pragma unroll
@@ -804,7 +831,9 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
       }
       xs4[i] = v;
     }
+    KZ_STAMP(12);
   }
+#undef KZ_STAMP
   __syncthreads();
   if (alive)
     for (int i = tid; i < np; i += KZ_PT) x4[pk0 + i] = xs4[i];
@@ -813,7 +842,7 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
 void kz_free(rls_kaczmarz_s* K) {
   if (!K) return;
   cudaFree(K->d_rows); cudaFree(K->d_denom); cudaFree(K->d_G); cudaFree(K->d_tpart); cudaFree(K->d_alpha); cudaFree(K->d_s2);
-  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_sync); cudaFree(K->d_abort);
+  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_sync); cudaFree(K->d_abort); cudaFree(K->d_trace);
   if (K->x) rls_vec_destroy(K->x);
   if (K->vl) rls_vec_destroy(K->vl);
   if (K->u) rls_vec_destroy(K->u);
@@ -1058,6 +1087,11 @@ extern "C" int32_t rls_kaczmarz_sweep(rls_kaczmarz_t K) {
     sp.R = K->R; sp.nblk = (int)K->nblk; sp.P = K->pP;
     sp.u = (const float*)K->u->d; sp.vl = (float*)K->vl->d; sp.ew = K->eps_w; sp.x = (float*)K->x->d;
     sp.tpart = K->d_tpart2; sp.alpha = K->d_alpha; sp.sync = K->d_sync; sp.abort_flag = K->d_abort; sp.epoch = K->epoch;
+    sp.trace = nullptr; sp.trace_block = 0;
+    if (rls_env_flag("RLS_KACZMARZ_TRACE", false)) {
+      if (!K->d_trace) { RLS_CUDA(cudaMalloc(&K->d_trace, 32 * sizeof(long long))); RLS_CUDA(cudaMemsetAsync(K->d_trace, 0, 32 * sizeof(long long), c->stream)); }
+      sp.trace = K->d_trace; sp.trace_block = (int)(K->nblk / 2);
+    }
     const void* fn = K->fpe == 2 ? (K->pIT == 4 ? (const void*)kz_sweep_kernel<2, 4> : (const void*)kz_sweep_kernel<2, 8>)
                                  : (K->pIT == 4 ? (const void*)kz_sweep_kernel<1, 4> : (const void*)kz_sweep_kernel<1, 8>);
     void* args[] = {&sp};
@@ -1080,7 +1114,7 @@ extern "C" int32_t rls_kaczmarz_vec(rls_kaczmarz_t K, const char* name, rls_vec_
 }
 
 // diagnostics: 0 = block Gram matrices [nblk][R*R*fpe], 1 = dot partials of the last block [S][R][fpe],
-// 2 = alpha of the last block [R][fpe], 3 = padded denominators [nblk*R]
+// 2 = alpha of the last block [R][fpe], 3 = padded denominators [nblk*R], 4 = RLS_KACZMARZ_TRACE stamps (32 x int64)
 extern "C" int32_t rls_kaczmarz_debug(rls_kaczmarz_t K, int32_t which, float* host, int64_t nfloats) {
   RLS_CHECK_ARG(K && host, "NULL argument");
   RlsDeviceGuard g(K->ctx->device);
@@ -1091,6 +1125,7 @@ extern "C" int32_t rls_kaczmarz_debug(rls_kaczmarz_t K, int32_t which, float* ho
     case 1: src = K->d_tpart; have = (int64_t)K->S * K->R * K->fpe; break;
     case 2: src = K->d_alpha; have = (int64_t)K->R * K->fpe; break;
     case 3: src = K->d_denom; have = K->nblk * (int64_t)K->R; break;
+    case 4: src = (const float*)K->d_trace; have = K->d_trace ? 64 : 0; break;   // 32 clock64 stamps
     default: rls_set_error("kaczmarz_debug: which = %d", which); return RLS_ERR_INVALID;
   }
   RLS_CHECK_ARG(nfloats <= have, "kaczmarz_debug: %lld floats requested, %lld available", (long long)nfloats, (long long)have);

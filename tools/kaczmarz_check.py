@@ -70,7 +70,33 @@ def timing(dtype, m, n, sweeps=5):
           f"{(ctx.launch_count() - n0) // k} launches per sweep, |x| {np.linalg.norm(S.x):.4e}")
 
 
+def trace(dtype, m, n):
+    """phase stamps (clock64) of CTA 0 (solver + worker) and CTA 5 (worker) in one block of the persistent sweep"""
+    os.environ["RLS_KACZMARZ_TRACE"] = "1"
+    ctx = rls.B200Context.default(0)
+    A = rls.B200Matrix.philox(dtype, m, n, seed=12345, scale=1 / np.sqrt(m), ctx=ctx, layout="row")
+    S = rls.Kaczmarz(A, reg=rls.L2Regularization(np.float32(1e-2)), iterations=3)
+    b = rls.B200Vector(ctx, dtype, m).fill_philox(seed=3, stream=1, dist=capi.RLS_DIST_IH4)
+    S.init_(b)
+    while S.iterate():
+        pass
+    ctx.sync()
+    raw = dbg(S, 4, 64).view(np.int64)
+    names = ["top", "staged", "dot done", "arrived", "prefetched", "all arrived", "t summed", "G in smem", "recurrence",
+             "published", "alpha here", "rows re-read", "x updated"]
+    print(f"[trace {np.dtype(dtype).name} {m}x{n}] {S.describe()}")
+    for c, nm in ((0, "CTA 0"), (1, "CTA 5")):
+        st = raw[c * 16: c * 16 + 13]
+        print("   ", nm, " ".join(f"{names[i]}=+{(st[i] - st[0]) / 1.9e3:.2f}us" for i in range(13) if st[i] != 0))
+    del os.environ["RLS_KACZMARZ_TRACE"]
+
+
 if __name__ == "__main__":
+    if "--trace" in sys.argv:
+        trace(np.float32, 16384, 65536)
+        os.environ["RLS_KACZMARZ_BLOCK"] = "64"
+        trace(np.float32, 16384, 65536)
+        sys.exit(0)
     for dt in (() if ("--time-only" in sys.argv or "--components" in sys.argv) else (np.float32, np.complex64)):
         check(dt, 300, 200, 64)
         check(dt, 150, 67, 128)
