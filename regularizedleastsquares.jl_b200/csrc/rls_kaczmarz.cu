@@ -46,8 +46,9 @@ struct rls_kaczmarz_s {
   bool initialised = false;
   // persistent sweep kernel (one cooperative launch per iteration)
   float* d_Dinv = nullptr;     // [nblk][R/32][32 jj][32 lane][fpe]: inverses of the 32x32 diagonal blocks of D^-1 + strictlower(G)
-  float* d_tpart2 = nullptr;   // [NC][R][fpe]
-  unsigned long long* d_sync = nullptr;   // [0] arrivals, [1] alpha-ready, both monotonic
+  float* d_tpart2 = nullptr;   // [NC][R][fpe] tagged pairs {value, tag}
+  float* d_alpha2 = nullptr;   // [R][fpe] tagged pairs
+  size_t tagged_bytes = 0, alpha2_bytes = 0;
   int* d_abort = nullptr;
   unsigned long long epoch = 0;           // blocks completed since the counters were reset
   long long* d_trace = nullptr;
@@ -533,9 +534,9 @@ __global__ void __launch_bounds__(32) kz_dinv_kernel(const float* __restrict__ G
 // ---------------------------------------------------------------------------------------------------------------
 // One Kaczmarz iteration in ONE cooperative launch.  CTA c owns the columns [c P, (c+1) P) (P packs of 4 floats) of x
 // for the whole sweep, in shared memory; a block of R rows needs only ONE grid-wide exchange:
-//     every CTA:  partial t_j over its columns                      -> tpart, arrive
-//     CTA 0:      waits for all arrivals, runs the block recurrence -> alpha, ready flag
-//     every CTA:  waits for alpha, x_slice += sum_j alpha_j conj(a_j[slice])          (rows again, from L2)
+//     every CTA:  partial t_j over its columns                      -> tagged partials
+//     CTA 0:      polls the partials, runs the block recurrence     -> tagged alpha
+//     every CTA:  polls alpha, x_slice += sum_j alpha_j conj(a_j[slice])              (rows again, from L2)
 // and no second barrier, because nobody else touches a CTA's columns.  While waiting for alpha every CTA prefetches
 // its part of the next block into L2 (cp.async.bulk.prefetch), so the HBM stream overlaps the serial recurrence.
 // Every wait is bounded; a time-out raises the abort flag and all CTAs leave.
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(32) kz_dinv_kernel(const float* __restrict__ G
 constexpr int KZ_PT = 512;            // threads of the persistent kernel
 constexpr int KZ_PW = KZ_PT / 32;
 constexpr int KZ_PMAX_R = 128;
-constexpr unsigned KZ_SPIN_LIMIT = 1u << 22;
+constexpr unsigned KZ_SPIN_LIMIT = 1u << 20;   // polls of ~1 us each before a wait gives up
 
 struct KzSweep {
   const float* A; int64_t ldf; int64_t npacks;
@@ -551,34 +552,26 @@ struct KzSweep {
   int R; int nblk; int P;
   const float* u; float* vl; float ew; float* x;
   float* tpart; float* alpha;
-  unsigned long long* sync; int* abort_flag;
+  int* abort_flag;
   unsigned long long epoch;
   long long* trace; int trace_block;   // RLS_KACZMARZ_TRACE: clock64 stamps of CTA 0 and CTA 5 in one block
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+// Both exchanges carry their flag IN the data: every float travels as an 8-byte {value, tag} pair written with one
+// store (tag = number of the block since init), and the reader polls the pair itself.  No fence, no counter: a value is
+// usable the moment its own tag matches.
+__device__ __forceinline__ void st_tagged(float* slot, float v, unsigned tag) {
+  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" :: "l"(slot), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_tagged(const float* slot) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(slot) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-// thread 0 waits until *p >= target (bounded), everybody learns whether to go on
-__device__ __forceinline__ bool kz_wait(const unsigned long long* p, unsigned long long target, int* abort_flag, int* s_flag) {
-  if (threadIdx.x == 0) {
-    unsigned spins = 0;
-    int ok = 1;
-    while (ld_acquire_u64(p) < target) {
-      if (++spins > KZ_SPIN_LIMIT || *((volatile int*)abort_flag)) { *abort_flag = 1; ok = 0; break; }
-      if (spins > 64) __nanosleep(32);
-    }
-    *s_flag = ok;
-  }
-  __syncthreads();
-  const bool ok = *s_flag != 0;
-  __syncthreads();
-  return ok;
+__device__ __forceinline__ uint4 ld_tagged2(const float* slot) {   // two consecutive pairs
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(slot) : "memory");
+  return v;
 }
 
 template <int FPE, int IT>
@@ -588,7 +581,6 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
   __shared__ float s_alpha[KZ_PMAX_R * FPE];
   __shared__ int s_rows[KZ_PMAX_R];
   __shared__ __align__(16) float s_t[KZ_PMAX_R * FPE];
-  __shared__ int s_flag;
   const int R = p.R, P = p.P;
   float* sG = reinterpret_cast<float*>(kz_smem4);           // [R*R*FPE]   (CTA 0)
   float4* xs4 = kz_smem4 + (size_t)R * R * FPE / 4;          // [P]
@@ -605,6 +597,7 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
 #define KZ_STAMP(i) do { if (p.trace && b == p.trace_block && tid == 0 && (cta == 0 || cta == 5)) p.trace[(cta ? 16 : 0) + (i)] = clock64(); } while (0)
   for (int b = 0; b < p.nblk && alive; ++b) {
     const int32_t* rows_b = p.rows + (int64_t)b * R;
+    const unsigned tag = (unsigned)(p.epoch + (unsigned long long)b + 1ull);
     KZ_STAMP(0);
     __syncthreads();                       // s_rows / s_alpha / red4 of the previous block are free; xs4 is complete
     for (int i = tid; i < R; i += KZ_PT) s_rows[i] = rows_b[i];
@@ -657,14 +650,12 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
         for (int q = 0; q < FPE; ++q) acc[q] = warp_sum(acc[q]);
         if (lane == 0) {
 #pragma unroll
-          for (int q = 0; q < FPE; ++q) p.tpart[((int64_t)cta * R + j + h * KZ_PW) * FPE + q] = rowv[h] < 0 ? 0.f : acc[q];
+          for (int q = 0; q < FPE; ++q)
+            st_tagged(p.tpart + 2 * (((int64_t)cta * R + j + h * KZ_PW) * FPE + q), rowv[h] < 0 ? 0.f : acc[q], tag);
         }
       }
     }
-    __syncthreads();
     KZ_STAMP(2);
-    if (tid == 0) { __threadfence(); atomicAdd(p.sync, 1ull); }
-    KZ_STAMP(3);
     // ---- the next block's rows (this CTA's columns) -> L2 while the recurrence runs
     if (b + 1 < p.nblk && np > 0) {
       const int32_t* rows_n = p.rows + (int64_t)(b + 1) * R;
@@ -691,35 +682,45 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
           for (int q = 0; q < FPE; ++q) { uu[q] = __ldcg(p.u + (int64_t)row * FPE + q); vv[q] = __ldcg(p.vl + (int64_t)row * FPE + q); }
         }
       }
-      alive = kz_wait(p.sync, (p.epoch + (unsigned long long)b + 1ull) * (unsigned long long)NC, p.abort_flag, &s_flag);
+      {
+        // t = sum of the CTAs' partials.  thread = (2 consecutive floats of t, part); each part polls its CTAs' tagged
+        // pairs 8 at a time (all loads in flight), and adds them in a fixed order once they are all there; then a
+        // shuffle tree over the parts.  Early CTAs are consumed while late ones are still streaming.
+        const int nq = R * FPE / 2;
+        const int parts = KZ_PT / nq;            // 4, 8 or 16: a power of two, the parts of one pair sit in one warp
+        const int qd = tid / parts, part = tid % parts;
+        float sx = 0.f, sy = 0.f;
+        int bad = 0;
+        for (int c0 = part; c0 < NC && !bad; c0 += parts * 8) {
+          uint4 v[8];
+          unsigned pending = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (c0 + i * parts < NC) pending |= 1u << i;
+          const unsigned want = pending;
+          unsigned spins = 0;
+          while (pending) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (pending >> i & 1u) v[i] = ld_tagged2(p.tpart + 2 * ((int64_t)(c0 + i * parts) * R * FPE + 2 * qd));
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if ((pending >> i & 1u) && v[i].y == tag && v[i].w == tag) pending &= ~(1u << i);
+            if (pending && (++spins > KZ_SPIN_LIMIT || ((spins & 255u) == 0u && *((volatile int*)p.abort_flag)))) { *p.abort_flag = 1; bad = 1; break; }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (want >> i & 1u) { sx += __uint_as_float(v[i].x); sy += __uint_as_float(v[i].z); }
+        }
+        for (int o = parts >> 1; o > 0; o >>= 1) {
+          sx += __shfl_xor_sync(0xffffffffu, sx, o);
+          sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        }
+        if (part == 0) { s_t[2 * qd] = sx; s_t[2 * qd + 1] = sy; }
+        alive = !__syncthreads_or(bad);
+      }
       KZ_STAMP(5);
       if (alive) {
-        // t = sum of the CTAs' partials: thread = (4 consecutive floats of t, part); each part sums its CTAs in a fixed
-        // order with 10 independent 128-bit loads in flight, then a shuffle tree over the parts
-        {
-          const int nq = R * FPE / 4;            // float4s of t
-          const int parts = KZ_PT / nq;          // 8, 16 or 32: a power of two, parts of one float4 sit in one warp
-          const int qd = tid / parts, part = tid % parts;
-          const float4* tp4 = reinterpret_cast<const float4*>(p.tpart);
-          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int c0 = part; c0 < NC; c0 += parts * 10) {
-            float4 v[10];
-#pragma unroll
-            for (int i = 0; i < 10; ++i) {
-              const int c = c0 + i * parts;
-              v[i] = c < NC ? __ldcg(tp4 + (int64_t)c * nq + qd) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int i = 0; i < 10; ++i) { sum.x += v[i].x; sum.y += v[i].y; sum.z += v[i].z; sum.w += v[i].w; }
-          }
-          for (int o = parts >> 1; o > 0; o >>= 1) {
-            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
-            sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
-            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
-            sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
-          }
-          if (part == 0) reinterpret_cast<float4*>(s_t)[qd] = sum;
-        }
         KZ_STAMP(6);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
@@ -751,7 +752,7 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
 #pragma unroll
             for (int q = 0; q < FPE; ++q) {
               s_alpha[k * FPE + q] = al[q];
-              p.alpha[k * FPE + q] = al[q];
+              st_tagged(p.alpha + 2 * (k * FPE + q), al[q], tag);
               if (row >= 0) p.vl[(int64_t)row * FPE + q] = fadd(vv[q], fmul(al[q], p.ew));   // Kaczmarz.jl:309
             }
           }
@@ -769,16 +770,21 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
             }
           }
         }
-        __syncthreads();
         KZ_STAMP(8);
-        if (tid == 0) { __threadfence(); st_release_u64(p.sync + 1, p.epoch + (unsigned long long)b + 1ull); }
-        KZ_STAMP(9);
       }
     } else {
-      alive = kz_wait(p.sync + 1, p.epoch + (unsigned long long)b + 1ull, p.abort_flag, &s_flag);
-      if (alive) {
-        for (int i = tid; i < R * FPE; i += KZ_PT) s_alpha[i] = __ldcg(p.alpha + i);
+      int bad = 0;
+      if (tid < R * FPE) {               // R * FPE <= 256 threads poll one tagged alpha each
+        unsigned spins = 0;
+        uint2 e = ld_tagged(p.alpha + 2 * tid);
+        while (e.y != tag) {
+          if (++spins > KZ_SPIN_LIMIT || ((spins & 255u) == 0u && *((volatile int*)p.abort_flag))) { *p.abort_flag = 1; bad = 1; break; }
+          if (spins > 64) __nanosleep(32);
+          e = ld_tagged(p.alpha + 2 * tid);
+        }
+        s_alpha[tid] = __uint_as_float(e.x);
       }
+      alive = !__syncthreads_or(bad);
     }
     if (!alive) break;
     __syncthreads();
@@ -842,7 +848,7 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
 void kz_free(rls_kaczmarz_s* K) {
   if (!K) return;
   cudaFree(K->d_rows); cudaFree(K->d_denom); cudaFree(K->d_G); cudaFree(K->d_tpart); cudaFree(K->d_alpha); cudaFree(K->d_s2);
-  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_sync); cudaFree(K->d_abort); cudaFree(K->d_trace);
+  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_alpha2); cudaFree(K->d_abort); cudaFree(K->d_trace);
   if (K->x) rls_vec_destroy(K->x);
   if (K->vl) rls_vec_destroy(K->vl);
   if (K->u) rls_vec_destroy(K->u);
@@ -856,8 +862,8 @@ static int32_t kz_plan_persistent(rls_kaczmarz_s* K) {
   rls_ctx_s* c = K->ctx;
   const int R = K->R, fpe = K->fpe;
   K->persistent = false;
-  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_sync); cudaFree(K->d_abort);
-  K->d_Dinv = nullptr; K->d_tpart2 = nullptr; K->d_sync = nullptr; K->d_abort = nullptr;
+  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_alpha2); cudaFree(K->d_abort);
+  K->d_Dinv = nullptr; K->d_tpart2 = nullptr; K->d_alpha2 = nullptr; K->d_abort = nullptr;
   if (!rls_env_flag("RLS_KACZMARZ_PERSISTENT", true)) return RLS_OK;
   if (!K->vec4 || !(R == 64 || R == 128) || K->nblk == 0 || K->nblk > 0x7fffffff) return RLS_OK;
   const int64_t npacks = K->A->n * fpe / 4;
@@ -873,12 +879,16 @@ static int32_t kz_plan_persistent(rls_kaczmarz_s* K) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, KZ_PT, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return RLS_OK; }
   if (NC > per_sm * c->sm_count) return RLS_OK;
-  if (cudaMalloc(&K->d_Dinv, (size_t)K->nblk * R * 32 * fpe * 4) != cudaSuccess || cudaMalloc(&K->d_tpart2, (size_t)NC * R * fpe * 4) != cudaSuccess ||
-      cudaMalloc(&K->d_sync, 2 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&K->d_abort, sizeof(int)) != cudaSuccess) {
+  K->tagged_bytes = (size_t)NC * R * fpe * 8;
+  K->alpha2_bytes = (size_t)R * fpe * 8;
+  if (cudaMalloc(&K->d_Dinv, (size_t)K->nblk * R * 32 * fpe * 4) != cudaSuccess || cudaMalloc(&K->d_tpart2, K->tagged_bytes) != cudaSuccess ||
+      cudaMalloc(&K->d_alpha2, K->alpha2_bytes) != cudaSuccess || cudaMalloc(&K->d_abort, sizeof(int)) != cudaSuccess) {
     rls_set_error("Kaczmarz: cudaMalloc of the sweep-kernel buffers failed: %s", cudaGetErrorString(cudaGetLastError()));
     return RLS_ERR_NOMEM;
   }
-  RLS_CUDA(cudaMemsetAsync(K->d_sync, 0, 2 * sizeof(unsigned long long), c->stream));
+  // tags count blocks from 1: zeroed buffers never match
+  RLS_CUDA(cudaMemsetAsync(K->d_tpart2, 0, K->tagged_bytes, c->stream));
+  RLS_CUDA(cudaMemsetAsync(K->d_alpha2, 0, K->alpha2_bytes, c->stream));
   RLS_CUDA(cudaMemsetAsync(K->d_abort, 0, sizeof(int), c->stream));
   K->epoch = 0;
   for (int64_t b0 = 0; b0 < K->nblk; b0 += 32768) {
@@ -1026,8 +1036,9 @@ extern "C" int32_t rls_kaczmarz_init(rls_kaczmarz_t K, rls_vec_t b, rls_vec_t x0
   else RLS_CUDA(cudaMemsetAsync(K->x->d, 0, (size_t)K->A->n * es, c->stream));
   RLS_CUDA(cudaMemsetAsync(K->vl->d, 0, (size_t)K->A->m * es, c->stream));
   RLS_CUDA(cudaMemcpyAsync(K->u->d, b->d, (size_t)K->A->m * es, cudaMemcpyDeviceToDevice, c->stream));
-  if (K->d_sync) {
-    RLS_CUDA(cudaMemsetAsync(K->d_sync, 0, 2 * sizeof(unsigned long long), c->stream));
+  if (K->d_tpart2) {   // tags restart at 1 with zeroed exchange buffers
+    RLS_CUDA(cudaMemsetAsync(K->d_tpart2, 0, K->tagged_bytes, c->stream));
+    RLS_CUDA(cudaMemsetAsync(K->d_alpha2, 0, K->alpha2_bytes, c->stream));
     RLS_CUDA(cudaMemsetAsync(K->d_abort, 0, sizeof(int), c->stream));
     K->epoch = 0;
   }
@@ -1086,7 +1097,7 @@ extern "C" int32_t rls_kaczmarz_sweep(rls_kaczmarz_t K) {
     sp.rows = K->d_rows; sp.denom = K->d_denom; sp.G = K->d_G; sp.Dinv = K->d_Dinv;
     sp.R = K->R; sp.nblk = (int)K->nblk; sp.P = K->pP;
     sp.u = (const float*)K->u->d; sp.vl = (float*)K->vl->d; sp.ew = K->eps_w; sp.x = (float*)K->x->d;
-    sp.tpart = K->d_tpart2; sp.alpha = K->d_alpha; sp.sync = K->d_sync; sp.abort_flag = K->d_abort; sp.epoch = K->epoch;
+    sp.tpart = K->d_tpart2; sp.alpha = K->d_alpha2; sp.abort_flag = K->d_abort; sp.epoch = K->epoch;
     sp.trace = nullptr; sp.trace_block = 0;
     if (rls_env_flag("RLS_KACZMARZ_TRACE", false)) {
       if (!K->d_trace) { RLS_CUDA(cudaMalloc(&K->d_trace, 32 * sizeof(long long))); RLS_CUDA(cudaMemsetAsync(K->d_trace, 0, 32 * sizeof(long long), c->stream)); }

@@ -82,8 +82,8 @@ def trace(dtype, m, n):
         pass
     ctx.sync()
     raw = dbg(S, 4, 64).view(np.int64)
-    names = ["top", "staged", "dot done", "arrived", "prefetched", "all arrived", "t summed", "G in smem", "recurrence",
-             "published", "alpha here", "rows re-read", "x updated"]
+    names = ["top", "staged", "dot done", "-", "prefetched", "t summed", "-", "G in smem", "alpha out",
+             "-", "alpha here", "rows re-read", "x updated"]
     print(f"[trace {np.dtype(dtype).name} {m}x{n}] {S.describe()}")
     for c, nm in ((0, "CTA 0"), (1, "CTA 5")):
         st = raw[c * 16: c * 16 + 13]
