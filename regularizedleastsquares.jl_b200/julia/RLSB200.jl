@@ -12,9 +12,10 @@ module RLSB200
 
 using RegularizedLeastSquares
 using LinearAlgebra
+using Random, StatsBase                 # Kaczmarz: sample! of the randomised row order stays in Julia
 import RegularizedLeastSquares: init!, iterate, solve!, prox!, solversolution, solverconvergence,
        L1Regularization, L2Regularization, L21Regularization, TVRegularization, PositiveRegularization,
-       RealRegularization, FISTA, POGM, OptISTA, CGNR, ADMM, SplitBregman, λ, sink
+       RealRegularization, FISTA, POGM, OptISTA, CGNR, ADMM, SplitBregman, Kaczmarz, λ, sink
 
 const LIB = get(ENV, "RLS_B200_LIB", "librls_b200.so")
 
@@ -215,5 +216,55 @@ function sync_scalars!(solver, state)
   state.norm_x₀ = sc[].norm_x0; state.iteration = sc[].iteration
   state
 end
+
+# ---- Kaczmarz (src/Kaczmarz.jl): the row loop of iterate runs in librls_b200, everything else stays as upstream -------
+# The solver is constructed on the HOST matrix as usual (L2 / Tikhonov handling, denom, rowindex, probabilities:
+# Kaczmarz.jl:73-159); `B200Kaczmarz(solver)` uploads solver.A with rows contiguous and owns the device-side plan.
+mutable struct B200Kaczmarz{T}
+  handle::Ptr{Cvoid}
+  A::B200Matrix{T}
+  order::Vector{Int64}        # the visiting order last sent to the device (usedIndices mapped through rowindex)
+end
+function B200Kaczmarz(solver::Kaczmarz; block_rows::Integer = 0)
+  T = eltype(solver.A)
+  A = B200Matrix(Matrix(solver.A); layout = :row)
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:rls_kaczmarz_create, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), A.handle, Int32(block_rows), h))
+  k = B200Kaczmarz{T}(h[], A, Int64[])
+  finalizer(x -> ccall((:rls_kaczmarz_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle), k)
+end
+function set_rows!(k::B200Kaczmarz, solver::Kaczmarz, usedIndices)
+  rows = Int64[solver.rowindex[i] - 1 for i in usedIndices]        # 0-based, distinct
+  rows == k.order && return k
+  denom = Float32[solver.denom[i] for i in usedIndices]
+  GC.@preserve rows denom check(ccall((:rls_kaczmarz_set_rows, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float32}, Int64),
+                                      k.handle, rows, denom, length(rows)))
+  k.order = rows
+  k
+end
+# init!(solver, state, b; x0): Kaczmarz.jl:178-216 runs first (normalisation, denom, shuffle); then the device state
+function init!(k::B200Kaczmarz, solver::Kaczmarz, b::B200Vector; x0 = nothing)
+  solver.randomized || set_rows!(k, solver, solver.state.usedIndices)
+  check(ccall((:rls_kaczmarz_init, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Float32), k.handle, b.handle,
+              x0 === nothing ? C_NULL : x0.handle, Float32(real(solver.state.ɛw))))
+end
+# iterate(solver, state): Kaczmarz.jl:264-283 with the row loop :270-273 replaced by one library call
+function iterate(k::B200Kaczmarz, solver::Kaczmarz, state = solver.state)
+  RegularizedLeastSquares.done(solver, state) && return nothing
+  if solver.randomized
+    StatsBase.sample!(Random.GLOBAL_RNG, solver.rowIndexCycle, weights(solver.probabilities), state.usedIndices, replace = false)
+    set_rows!(k, solver, state.usedIndices)
+  end
+  check(ccall((:rls_kaczmarz_sweep, LIB), Int32, (Ptr{Cvoid},), k.handle))
+  xh = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:rls_kaczmarz_vec, LIB), Int32, (Ptr{Cvoid}, Cstring, Ref{Ptr{Cvoid}}), k.handle, "x", xh))
+  x = B200Vector{eltype(k.A)}(xh[], size(k.A, 2), false)            # borrowed handle
+  for r in solver.reg
+    prox!(r, x)                                                      # rls_prox_* (Kaczmarz.jl:275-277)
+  end
+  state.iteration += 1
+  return x, state
+end
+kaczmarz_check(k::B200Kaczmarz) = check(ccall((:rls_kaczmarz_check, LIB), Int32, (Ptr{Cvoid},), k.handle))
 
 end # module
