@@ -48,6 +48,7 @@ struct rls_kaczmarz_s {
   float* d_Dinv = nullptr;     // [nblk][R/32][32 jj][32 lane][fpe]: inverses of the 32x32 diagonal blocks of D^-1 + strictlower(G)
   float* d_tpart2 = nullptr;   // [NC][R][fpe] tagged pairs {value, tag}
   float* d_alpha2 = nullptr;   // [R][fpe] tagged pairs
+  float* d_tsum = nullptr;     // [R][fpe] tagged pairs: t summed over the CTAs, one reducer CTA per row
   size_t tagged_bytes = 0, alpha2_bytes = 0;
   int* d_abort = nullptr;
   unsigned long long epoch = 0;           // blocks completed since the counters were reset
@@ -535,7 +536,8 @@ __global__ void __launch_bounds__(32) kz_dinv_kernel(const float* __restrict__ G
 // One Kaczmarz iteration in ONE cooperative launch.  CTA c owns the columns [c P, (c+1) P) (P packs of 4 floats) of x
 // for the whole sweep, in shared memory; a block of R rows needs only ONE grid-wide exchange:
 //     every CTA:  partial t_j over its columns                      -> tagged partials
-//     CTA 0:      polls the partials, runs the block recurrence     -> tagged alpha
+//     CTA j:      polls the 148 partials of row j, sums them        -> tagged t_j          (one reducer CTA per row)
+//     CTA 0:      polls t, runs the block recurrence                -> tagged alpha
 //     every CTA:  polls alpha, x_slice += sum_j alpha_j conj(a_j[slice])              (rows again, from L2)
 // and no second barrier, because nobody else touches a CTA's columns.  While waiting for alpha every CTA prefetches
 // its part of the next block into L2 (cp.async.bulk.prefetch), so the HBM stream overlaps the serial recurrence.
@@ -551,7 +553,7 @@ struct KzSweep {
   const int32_t* rows; const float* denom; const float* G; const float* Dinv;
   int R; int nblk; int P;
   const float* u; float* vl; float ew; float* x;
-  float* tpart; float* alpha;
+  float* tpart; float* tsum; float* alpha;
   int* abort_flag;
   unsigned long long epoch;
   long long* trace; int trace_block;   // RLS_KACZMARZ_TRACE: clock64 stamps of CTA 0 and CTA 5 in one block
@@ -581,6 +583,7 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
   __shared__ float s_alpha[KZ_PMAX_R * FPE];
   __shared__ int s_rows[KZ_PMAX_R];
   __shared__ __align__(16) float s_t[KZ_PMAX_R * FPE];
+  __shared__ float s_red[KZ_PW][FPE];
   const int R = p.R, P = p.P;
   float* sG = reinterpret_cast<float*>(kz_smem4);           // [R*R*FPE]   (CTA 0)
   float4* xs4 = kz_smem4 + (size_t)R * R * FPE / 4;          // [P]
@@ -668,6 +671,38 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
       }
     }
     KZ_STAMP(4);
+    // ---- reducers: CTA c sums row c (c + NC, ...) of the partials over all CTAs — thread i polls CTA i's tagged value,
+    //      a shuffle tree and the warps in order make the sum — and publishes t_row, again tagged
+    for (int rr = cta; rr < R && alive; rr += NC) {
+      float v[FPE];
+#pragma unroll
+      for (int q = 0; q < FPE; ++q) v[q] = 0.f;
+      int bad = 0;
+      if (tid < NC) {
+        const float* slot = p.tpart + 2 * (((int64_t)tid * R + rr) * FPE);
+        unsigned spins = 0;
+        for (;;) {
+          bool ready;
+          if constexpr (FPE == 1) { const uint2 e = ld_tagged(slot); ready = e.y == tag; v[0] = __uint_as_float(e.x); }
+          else { const uint4 e = ld_tagged2(slot); ready = e.y == tag && e.w == tag; v[0] = __uint_as_float(e.x); v[FPE - 1] = __uint_as_float(e.z); }
+          if (ready) break;
+          if (++spins > KZ_SPIN_LIMIT || ((spins & 255u) == 0u && *((volatile int*)p.abort_flag))) { *p.abort_flag = 1; bad = 1; break; }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < FPE; ++q) {
+        v[q] = warp_sum(v[q]);
+        if (lane == 0) s_red[warp][q] = v[q];
+      }
+      alive = !__syncthreads_or(bad);
+      if (alive && tid < FPE) {
+        float tot = 0.f;
+        for (int w = 0; w < (NC + 31) / 32; ++w) tot += s_red[w][tid];
+        st_tagged(p.tsum + 2 * (rr * FPE + tid), tot, tag);
+      }
+      __syncthreads();
+    }
+    if (!alive) break;
     // ---- CTA 0: the block recurrence
     if (cta == 0) {
       const int k = tid;
@@ -683,40 +718,16 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
         }
       }
       {
-        // t = sum of the CTAs' partials.  thread = (2 consecutive floats of t, part); each part polls its CTAs' tagged
-        // pairs 8 at a time (all loads in flight), and adds them in a fixed order once they are all there; then a
-        // shuffle tree over the parts.  Early CTAs are consumed while late ones are still streaming.
-        const int nq = R * FPE / 2;
-        const int parts = KZ_PT / nq;            // 4, 8 or 16: a power of two, the parts of one pair sit in one warp
-        const int qd = tid / parts, part = tid % parts;
-        float sx = 0.f, sy = 0.f;
         int bad = 0;
-        for (int c0 = part; c0 < NC && !bad; c0 += parts * 8) {
-          uint4 v[8];
-          unsigned pending = 0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (c0 + i * parts < NC) pending |= 1u << i;
-          const unsigned want = pending;
+        if (tid < R * FPE) {             // one tagged t value per thread, published by the row's reducer CTA
           unsigned spins = 0;
-          while (pending) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (pending >> i & 1u) v[i] = ld_tagged2(p.tpart + 2 * ((int64_t)(c0 + i * parts) * R * FPE + 2 * qd));
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if ((pending >> i & 1u) && v[i].y == tag && v[i].w == tag) pending &= ~(1u << i);
-            if (pending && (++spins > KZ_SPIN_LIMIT || ((spins & 255u) == 0u && *((volatile int*)p.abort_flag)))) { *p.abort_flag = 1; bad = 1; break; }
+          uint2 e = ld_tagged(p.tsum + 2 * tid);
+          while (e.y != tag) {
+            if (++spins > KZ_SPIN_LIMIT || ((spins & 255u) == 0u && *((volatile int*)p.abort_flag))) { *p.abort_flag = 1; bad = 1; break; }
+            e = ld_tagged(p.tsum + 2 * tid);
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (want >> i & 1u) { sx += __uint_as_float(v[i].x); sy += __uint_as_float(v[i].z); }
+          s_t[tid] = __uint_as_float(e.x);
         }
-        for (int o = parts >> 1; o > 0; o >>= 1) {
-          sx += __shfl_xor_sync(0xffffffffu, sx, o);
-          sy += __shfl_xor_sync(0xffffffffu, sy, o);
-        }
-        if (part == 0) { s_t[2 * qd] = sx; s_t[2 * qd + 1] = sy; }
         alive = !__syncthreads_or(bad);
       }
       KZ_STAMP(5);
@@ -848,7 +859,7 @@ __global__ void __launch_bounds__(KZ_PT, 1) kz_sweep_kernel(const KzSweep p) {
 void kz_free(rls_kaczmarz_s* K) {
   if (!K) return;
   cudaFree(K->d_rows); cudaFree(K->d_denom); cudaFree(K->d_G); cudaFree(K->d_tpart); cudaFree(K->d_alpha); cudaFree(K->d_s2);
-  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_alpha2); cudaFree(K->d_abort); cudaFree(K->d_trace);
+  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_alpha2); cudaFree(K->d_tsum); cudaFree(K->d_abort); cudaFree(K->d_trace);
   if (K->x) rls_vec_destroy(K->x);
   if (K->vl) rls_vec_destroy(K->vl);
   if (K->u) rls_vec_destroy(K->u);
@@ -862,8 +873,8 @@ static int32_t kz_plan_persistent(rls_kaczmarz_s* K) {
   rls_ctx_s* c = K->ctx;
   const int R = K->R, fpe = K->fpe;
   K->persistent = false;
-  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_alpha2); cudaFree(K->d_abort);
-  K->d_Dinv = nullptr; K->d_tpart2 = nullptr; K->d_alpha2 = nullptr; K->d_abort = nullptr;
+  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_alpha2); cudaFree(K->d_tsum); cudaFree(K->d_abort);
+  K->d_Dinv = nullptr; K->d_tpart2 = nullptr; K->d_alpha2 = nullptr; K->d_tsum = nullptr; K->d_abort = nullptr;
   if (!rls_env_flag("RLS_KACZMARZ_PERSISTENT", true)) return RLS_OK;
   if (!K->vec4 || !(R == 64 || R == 128) || K->nblk == 0 || K->nblk > 0x7fffffff) return RLS_OK;
   const int64_t npacks = K->A->n * fpe / 4;
@@ -882,13 +893,15 @@ static int32_t kz_plan_persistent(rls_kaczmarz_s* K) {
   K->tagged_bytes = (size_t)NC * R * fpe * 8;
   K->alpha2_bytes = (size_t)R * fpe * 8;
   if (cudaMalloc(&K->d_Dinv, (size_t)K->nblk * R * 32 * fpe * 4) != cudaSuccess || cudaMalloc(&K->d_tpart2, K->tagged_bytes) != cudaSuccess ||
-      cudaMalloc(&K->d_alpha2, K->alpha2_bytes) != cudaSuccess || cudaMalloc(&K->d_abort, sizeof(int)) != cudaSuccess) {
+      cudaMalloc(&K->d_alpha2, K->alpha2_bytes) != cudaSuccess || cudaMalloc(&K->d_tsum, K->alpha2_bytes) != cudaSuccess ||
+      cudaMalloc(&K->d_abort, sizeof(int)) != cudaSuccess) {
     rls_set_error("Kaczmarz: cudaMalloc of the sweep-kernel buffers failed: %s", cudaGetErrorString(cudaGetLastError()));
     return RLS_ERR_NOMEM;
   }
   // tags count blocks from 1: zeroed buffers never match
   RLS_CUDA(cudaMemsetAsync(K->d_tpart2, 0, K->tagged_bytes, c->stream));
   RLS_CUDA(cudaMemsetAsync(K->d_alpha2, 0, K->alpha2_bytes, c->stream));
+  RLS_CUDA(cudaMemsetAsync(K->d_tsum, 0, K->alpha2_bytes, c->stream));
   RLS_CUDA(cudaMemsetAsync(K->d_abort, 0, sizeof(int), c->stream));
   K->epoch = 0;
   for (int64_t b0 = 0; b0 < K->nblk; b0 += 32768) {
@@ -921,10 +934,9 @@ extern "C" int32_t rls_kaczmarz_create(rls_mat_t A, int32_t block_rows, rls_kacz
   int R = block_rows;
   if (const char* e = getenv("RLS_KACZMARZ_BLOCK")) { if (R <= 0 && atoi(e) > 0) R = atoi(e); }
   if (R <= 0) {
-    // a block should stay L2-resident between its two passes: <= 32 MB
-    const int64_t row_bytes = A->n * (int64_t)fpe * 4;
-    int64_t r = (32ll << 20) / (row_bytes > 0 ? row_bytes : 1);
-    R = r >= 128 ? 128 : 64;   // 64 / 128: the persistent sweep kernel keeps the block's Gram matrix in shared memory
+    // 128 rows per block: the per-block exchange (~7 us) amortises over more rows, the Gram tile (64 / 128 KB) still fits
+    // the solver CTA's shared memory, and two blocks (current + prefetched) stay L2-resident up to 512 KB rows
+    R = A->m > 64 ? 128 : 64;
   }
   RLS_CHECK_ARG(R == 64 || R == 128 || R == 192 || R == 256, "Kaczmarz: block_rows must be 64, 128, 192 or 256 (got %d)", R);
   rls_kaczmarz_s* K = new rls_kaczmarz_s();
@@ -1039,6 +1051,7 @@ extern "C" int32_t rls_kaczmarz_init(rls_kaczmarz_t K, rls_vec_t b, rls_vec_t x0
   if (K->d_tpart2) {   // tags restart at 1 with zeroed exchange buffers
     RLS_CUDA(cudaMemsetAsync(K->d_tpart2, 0, K->tagged_bytes, c->stream));
     RLS_CUDA(cudaMemsetAsync(K->d_alpha2, 0, K->alpha2_bytes, c->stream));
+    RLS_CUDA(cudaMemsetAsync(K->d_tsum, 0, K->alpha2_bytes, c->stream));
     RLS_CUDA(cudaMemsetAsync(K->d_abort, 0, sizeof(int), c->stream));
     K->epoch = 0;
   }
@@ -1097,7 +1110,7 @@ extern "C" int32_t rls_kaczmarz_sweep(rls_kaczmarz_t K) {
     sp.rows = K->d_rows; sp.denom = K->d_denom; sp.G = K->d_G; sp.Dinv = K->d_Dinv;
     sp.R = K->R; sp.nblk = (int)K->nblk; sp.P = K->pP;
     sp.u = (const float*)K->u->d; sp.vl = (float*)K->vl->d; sp.ew = K->eps_w; sp.x = (float*)K->x->d;
-    sp.tpart = K->d_tpart2; sp.alpha = K->d_alpha2; sp.abort_flag = K->d_abort; sp.epoch = K->epoch;
+    sp.tpart = K->d_tpart2; sp.tsum = K->d_tsum; sp.alpha = K->d_alpha2; sp.abort_flag = K->d_abort; sp.epoch = K->epoch;
     sp.trace = nullptr; sp.trace_block = 0;
     if (rls_env_flag("RLS_KACZMARZ_TRACE", false)) {
       if (!K->d_trace) { RLS_CUDA(cudaMalloc(&K->d_trace, 32 * sizeof(long long))); RLS_CUDA(cudaMemsetAsync(K->d_trace, 0, 32 * sizeof(long long), c->stream)); }
