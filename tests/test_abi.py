@@ -64,6 +64,8 @@ def test_library_is_sm100a_and_uses_tma(rls):
     assert "UTCHMMA" in sass and "LDTM" in sass, "the multi-RHS / Gram GEMM must run on tcgen05 with TMEM accumulators"
     assert "STAS" in sass, "the cluster exchange of the one-pass kernel uses st.async into peer shared memory"
     assert not re.search(r"(?<![A-Z])HMMA", sass), "no warp-level mma.sync / wmma tensor-core code"
+    assert "UBLKPF" in sass, "the Kaczmarz sweep kernel prefetches the next block's rows into L2 with bulk prefetches"
+    assert "LDGSTS" in sass, "the Kaczmarz sweep kernel stages the block Gram tile with cp.async"
 
 
 def test_no_gpu_means_loud_failure_not_fallback(rls):
