@@ -92,6 +92,9 @@ def trace(dtype, m, n):
 
 
 if __name__ == "__main__":
+    if "--ncu" in sys.argv:          # small enough for ncu's kernel replay (save / restore of device memory)
+        timing(np.float32, 2048, 65536, sweeps=3)
+        sys.exit(0)
     if "--trace" in sys.argv:
         trace(np.float32, 16384, 65536)
         os.environ["RLS_KACZMARZ_BLOCK"] = "64"
