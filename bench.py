@@ -77,6 +77,9 @@ class ClockSampler(threading.Thread):
 
 
 _CPU_PROBLEM = {}
+METRIC = "FISTA-L1 iterations/s on dense A (Float32 16384x65536 per GPU)"
+WORKLOAD = ("C2: FISTA + L1Regularization(1f-3), dense Float32 A 16384x65536, 200 iterations per solve!, "
+            "rho = 0.95/lambda_max (30 power iterations), relTol = 0")
 
 
 def cpu_sample(iters=100, m_sub=8192, threads=None):
@@ -119,12 +122,14 @@ def run_reference(args):
     value = float(np.mean(vals))
     sample = (f"{iters} FISTA-L1 iterations per step on the full 16384x65536 Float32 system "
               f"(oracle loop, NumPy/OpenBLAS two-gemv normal operator, all host threads)")
-    line = {"metric": "FISTA-L1 iterations/s on dense A (Float32 16384x65536)", "value": value, "unit": "iterations/s",
+    line = {"metric": METRIC, "value": value, "unit": "iterations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * ITERS / value if value > 0 else None, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "C2: FISTA + L1Regularization, dense Float32 A 16384x65536, 200 iterations",
-                       "note": "Julia is not installed in this image; the reference arm is the float32-faithful oracle port"},
+            "config": {"workload": WORKLOAD, "iterations_per_step": ITERS,
+                       "note": "Julia is not installed in this image; the reference arm is the float32-faithful oracle port "
+                               "(NumPy/OpenBLAS, rho = 0.1 fixed: the per-iteration cost does not depend on it); each step "
+                               "times a bounded number of iterations of the full-size problem"},
             "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
@@ -241,12 +246,11 @@ def run_b200(args):
                          f"{dt:.1f} s; restated reference, Julia is not installed"}
     if rank == 0:
         line = {
-            "metric": "FISTA-L1 iterations/s on dense A (Float32 16384x65536 per GPU)",
+            "metric": METRIC,
             "value": its_per_s * world, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: FISTA + L1Regularization(1f-3), dense Float32 A 16384x65536, 200 iterations per "
-                                   "solve!, rho = 0.95/lambda_max (30 power iterations), relTol = 0",
+            "config": {"workload": WORKLOAD,
                        "normal_operator": AHA.form, "iterations_per_step": ITERS,
                        "parallelism": "single GPU" if world == 1 else f"row-sharded x{world}: (16384*{world})x65536, one "
                                       "NCCL allreduce of the 65536-vector per iteration; value = shard-iterations/s",
