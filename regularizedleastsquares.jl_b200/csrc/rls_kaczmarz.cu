@@ -50,6 +50,7 @@ struct rls_kaczmarz_s {
   float* d_alpha2 = nullptr;   // [R][fpe] tagged pairs
   float* d_tsum = nullptr;     // [R][fpe] tagged pairs: t summed over the CTAs, one reducer CTA per row
   size_t tagged_bytes = 0, alpha2_bytes = 0;
+  int64_t dinv_cap = 0;        // blocks d_Dinv has room for
   int* d_abort = nullptr;
   unsigned long long epoch = 0;           // blocks completed since the counters were reset
   long long* d_trace = nullptr;
@@ -873,8 +874,6 @@ static int32_t kz_plan_persistent(rls_kaczmarz_s* K) {
   rls_ctx_s* c = K->ctx;
   const int R = K->R, fpe = K->fpe;
   K->persistent = false;
-  cudaFree(K->d_Dinv); cudaFree(K->d_tpart2); cudaFree(K->d_alpha2); cudaFree(K->d_tsum); cudaFree(K->d_abort);
-  K->d_Dinv = nullptr; K->d_tpart2 = nullptr; K->d_alpha2 = nullptr; K->d_tsum = nullptr; K->d_abort = nullptr;
   if (!rls_env_flag("RLS_KACZMARZ_PERSISTENT", true)) return RLS_OK;
   if (!K->vec4 || !(R == 64 || R == 128) || K->nblk == 0 || K->nblk > 0x7fffffff) return RLS_OK;
   const int64_t npacks = K->A->n * fpe / 4;
@@ -890,20 +889,31 @@ static int32_t kz_plan_persistent(rls_kaczmarz_s* K) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, KZ_PT, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return RLS_OK; }
   if (NC > per_sm * c->sm_count) return RLS_OK;
-  K->tagged_bytes = (size_t)NC * R * fpe * 8;
-  K->alpha2_bytes = (size_t)R * fpe * 8;
-  if (cudaMalloc(&K->d_Dinv, (size_t)K->nblk * R * 32 * fpe * 4) != cudaSuccess || cudaMalloc(&K->d_tpart2, K->tagged_bytes) != cudaSuccess ||
-      cudaMalloc(&K->d_alpha2, K->alpha2_bytes) != cudaSuccess || cudaMalloc(&K->d_tsum, K->alpha2_bytes) != cudaSuccess ||
-      cudaMalloc(&K->d_abort, sizeof(int)) != cudaSuccess) {
-    rls_set_error("Kaczmarz: cudaMalloc of the sweep-kernel buffers failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return RLS_ERR_NOMEM;
+  // the exchange buffers depend only on the geometry (allocated once); the inverted diagonal blocks grow with the order
+  if (!K->d_tpart2) {
+    K->tagged_bytes = (size_t)NC * R * fpe * 8;
+    K->alpha2_bytes = (size_t)R * fpe * 8;
+    if (cudaMalloc(&K->d_tpart2, K->tagged_bytes) != cudaSuccess || cudaMalloc(&K->d_alpha2, K->alpha2_bytes) != cudaSuccess ||
+        cudaMalloc(&K->d_tsum, K->alpha2_bytes) != cudaSuccess || cudaMalloc(&K->d_abort, sizeof(int)) != cudaSuccess) {
+      rls_set_error("Kaczmarz: cudaMalloc of the sweep-kernel buffers failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return RLS_ERR_NOMEM;
+    }
+    // tags count blocks from 1: zeroed buffers never match; later orders keep counting (tags only ever grow)
+    RLS_CUDA(cudaMemsetAsync(K->d_tpart2, 0, K->tagged_bytes, c->stream));
+    RLS_CUDA(cudaMemsetAsync(K->d_alpha2, 0, K->alpha2_bytes, c->stream));
+    RLS_CUDA(cudaMemsetAsync(K->d_tsum, 0, K->alpha2_bytes, c->stream));
+    RLS_CUDA(cudaMemsetAsync(K->d_abort, 0, sizeof(int), c->stream));
+    K->epoch = 0;
   }
-  // tags count blocks from 1: zeroed buffers never match
-  RLS_CUDA(cudaMemsetAsync(K->d_tpart2, 0, K->tagged_bytes, c->stream));
-  RLS_CUDA(cudaMemsetAsync(K->d_alpha2, 0, K->alpha2_bytes, c->stream));
-  RLS_CUDA(cudaMemsetAsync(K->d_tsum, 0, K->alpha2_bytes, c->stream));
-  RLS_CUDA(cudaMemsetAsync(K->d_abort, 0, sizeof(int), c->stream));
-  K->epoch = 0;
+  if (K->nblk > K->dinv_cap) {
+    cudaFree(K->d_Dinv);
+    K->d_Dinv = nullptr; K->dinv_cap = 0;
+    if (cudaMalloc(&K->d_Dinv, (size_t)K->nblk * R * 32 * fpe * 4) != cudaSuccess) {
+      rls_set_error("Kaczmarz: cudaMalloc of the inverted diagonal blocks failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return RLS_ERR_NOMEM;
+    }
+    K->dinv_cap = K->nblk;
+  }
   for (int64_t b0 = 0; b0 < K->nblk; b0 += 32768) {
     const int64_t nb = std::min<int64_t>(32768, K->nblk - b0);
     dim3 grid((unsigned)(R / 32), (unsigned)nb);
