@@ -303,7 +303,7 @@ int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_host, int64_t 
  * block Gram matrix A_blk A_blk^H (built once per order), so that one iteration is one HBM sweep over A instead of m
  * dependent dot/axpy pairs.  The constructor logic (L2 / denom / rowindex / probabilities / row order, Kaczmarz.jl:73-159,
  * :326-392) and the prox! calls after the sweep (:275-277, rls_prox_*) stay with the host, as in the reference.
- * block_rows: 64, 128, 192, 256, or 0 = 64 / 128 (sized so that a block stays L2-resident).  With 64 or 128 and rows
+ * block_rows: 64, 128, 192, 256, or 0 = the library's choice (128; 64 for systems of at most 64 rows).  With 64 or 128 and rows
  * of a multiple of 16 bytes a whole iteration is ONE cooperative kernel (columns of x pinned to CTAs, one grid-wide
  * exchange per block); otherwise three kernels per block are chained on the stream. */
 int32_t rls_kaczmarz_create(rls_mat_t A, int32_t block_rows, rls_kaczmarz_t* out);
