@@ -43,6 +43,8 @@ CASES = {
     "optista_l1_f32": (np.float32, 96, 160, 530, lambda A: O.OptISTA(A, reg=O.L1Regularization(np.float32(2e-2)), iterations=12, rho=np.float32(0.2), relTol=0.0), 12),
     "cgnr_l2_c64": (np.complex64, 160, 96, 540, lambda A: O.CGNR(A, reg=O.L2Regularization(np.float32(1e-3)), iterations=10, relTol=0.0), 10),
     "admm_l1_c64": (np.complex64, 128, 96, 550, lambda A: O.ADMM(A, reg=O.L1Regularization(np.float32(1e-2)), iterations=8, iterationsCG=10, rho=0.1, absTol=0.0, relTol=0.0), 8),
+    "kaczmarz_l2_f32": (np.float32, 160, 96, 570, lambda A: O.Kaczmarz(A, reg=O.L2Regularization(np.float32(1e-2)), iterations=6), 6),
+    "kaczmarz_l2_l1_pos_c64": (np.complex64, 96, 160, 580, lambda A: O.Kaczmarz(A, reg=[O.L2Regularization(np.float32(1e-2)), O.L1Regularization(np.float32(1e-3)), O.PositiveRegularization()], iterations=6), 6),
     "admm_tv_f32": (np.float32, 128, 12 * 8, 560, lambda A: O.ADMM(A, reg=O.TVRegularization(np.float32(1e-2), shape=(12, 8)), iterations=8, iterationsCG=10, rho=0.1, absTol=0.0, relTol=0.0), 8),
 }
 
