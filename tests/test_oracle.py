@@ -360,3 +360,37 @@ def test_kaczmarz_block_gram_form_is_the_same_recurrence(dtype):
                 vl[r0 + j] += al[j] * ew
             x += (Ab.conj().T @ al).astype(dtype)
         assert np.linalg.norm(x - S.x) / np.linalg.norm(S.x) < 1e-5
+
+
+@pytest.mark.parametrize("corr", [0.0, 0.99, 0.9999])
+def test_kaczmarz_inverted_diagonal_blocks_stay_accurate_on_correlated_rows(corr):
+    """the sweep kernel solves the block recurrence (D^-1 + strictlower(G)) alpha = r by blocked forward substitution with
+    the 32x32 diagonal blocks inverted once (in double, stored in single).  Nearly parallel rows make G ill-conditioned
+    (cond ~ 2e5 at row correlation 0.9999); the iterates must still follow the row-by-row loop."""
+    rng = np.random.default_rng(11)
+    m, n, R, lam = 256, 512, 128, np.float32(1e-2)
+    base = rng.standard_normal(n).astype(np.float32)
+    A = ((np.sqrt(1 - corr ** 2) * rng.standard_normal((m, n)).astype(np.float32) + corr * base[None, :]) / np.float32(np.sqrt(m))).astype(np.float32)
+    b = (A @ rng.standard_normal(n).astype(np.float32)).astype(np.float32)
+    S = O.Kaczmarz(A, reg=O.L2Regularization(lam), iterations=3); S.init(b)
+    ew = np.float32(np.sqrt(lam))
+    x = np.zeros(n, np.float32); vl = np.zeros(m, np.float32)
+    blocks = []
+    for r0 in range(0, m, R):
+        G = (A[r0:r0 + R] @ A[r0:r0 + R].T).astype(np.float32)
+        inv = [np.linalg.inv(np.tril(G[j:j + 32, j:j + 32].astype(np.float64), -1) +
+                             np.diag(1.0 / S.denom[r0 + j:r0 + j + 32].astype(np.float64))).astype(np.float32) for j in range(0, R, 32)]
+        blocks.append((G, inv))
+    for _ in range(3):
+        S.iterate()
+        for bi, r0 in enumerate(range(0, m, R)):
+            G, inv = blocks[bi]
+            Ab = A[r0:r0 + R]
+            r = (b[r0:r0 + R] - (Ab @ x).astype(np.float32) - ew * vl[r0:r0 + R]).astype(np.float32)
+            c = np.zeros(R, np.float32); al = np.zeros(R, np.float32)
+            for jb, j0 in enumerate(range(0, R, 32)):
+                al[j0:j0 + 32] = inv[jb] @ (r[j0:j0 + 32] - c[j0:j0 + 32])
+                c[j0 + 32:] += G[j0 + 32:, j0:j0 + 32] @ al[j0:j0 + 32]
+            vl[r0:r0 + R] += al * ew
+            x += Ab.T @ al
+        assert np.linalg.norm(x - S.x) / np.linalg.norm(S.x) < 1e-5
