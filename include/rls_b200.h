@@ -120,6 +120,10 @@ int32_t rls_ctx_peer_export(rls_ctx_t ctx, int64_t max_floats, void* handle64);
 int32_t rls_ctx_peer_import(rls_ctx_t ctx, const void* handles /* nranks x 64 bytes, rank order */, int32_t nranks);
 /* sum-allreduce of a device vector across ranks (the n-vector A_i' r_i) */
 int32_t rls_vec_allreduce(rls_vec_t v);
+/* sum of n <= 8 host doubles over the ranks, in place: the global scalars of a row-sharded solve — ‖A‖_F²
+ * (SystemMatrixBasedNormalization, src/Regularization/NormalizedRegularization.jl:47-58), ‖b‖₁ and length(b)
+ * (MeasurementBasedNormalization, :40-43).  No-op on a single rank. */
+int32_t rls_ctx_allreduce_f64(rls_ctx_t ctx, double* vals, int32_t n);
 
 /* ============================ vectors ========================================= */
 /* `similar(b, n)` on the device: FISTA.jl:94-103, CGNR.jl:91-100, ADMM.jl:166-184 */

@@ -335,11 +335,17 @@ def prox_l21(x, lam, slices):
     T = real_type(x.dtype)
     lam = T(lam)
     L = x.size // slices
-    xv = x.reshape(-1)[: L * slices].reshape(slices, L)
-    g = np.array([_norm2(xv[:, j]) for j in range(L)], dtype=T)
+    if L == 0:
+        if x.size == 0:
+            return x
+        raise ValueError("step cannot be zero")          # x[i:0:end] throws upstream
+    xv = x.reshape(-1)
+    # group j = x[j:L:end]: `slices` elements, one more where length(x) is not a multiple of slices
+    g = np.array([_norm2(xv[j::L]) for j in range(L)], dtype=T)
     with np.errstate(invalid="ignore", divide="ignore"):
         f = np.maximum((g - lam) / g, T(0))
-    xv[...] = xv * f[None, :]
+    for j in range(L):
+        xv[j::L] = xv[j::L] * f[j]
     return x
 
 
@@ -407,8 +413,8 @@ def reg_norm(reg, x, lam=None):
         return lam * _norm2(x) ** 2
     if isinstance(reg0, L21Regularization):
         L = x.size // reg0.slices
-        xv = x.reshape(reg0.slices, L)
-        return lam * sum(_norm2(xv[:, j]) for j in range(L))
+        xv = x.reshape(-1)
+        return lam * sum(_norm2(xv[j::L]) for j in range(L))
     if isinstance(reg0, TVRegularization):
         return lam * np.sum(_hypot_abs(grad_op(x, reg0.shape, reg0.dims)))
     raise TypeError(reg)

@@ -83,6 +83,7 @@ SIGNATURES = {
     "rls_ctx_comm_init": [_P, _I32, _I32, _P],
     "rls_ctx_comm_info": [_P, _PI32, _PI32],
     "rls_vec_allreduce": [_P],
+    "rls_ctx_allreduce_f64": [_P, _PF64, _I32],
     "rls_ctx_peer_export": [_P, _I64, _P],
     "rls_ctx_peer_import": [_P, _P, _I32],
     "rls_vec_create": [_P, _I32, _I64, _PP],

@@ -79,6 +79,12 @@ class B200Context:
         capi.call("rls_ctx_comm_init", self.handle, int(rank), int(nranks), buf)
         self.rank, self.nranks = int(rank), int(nranks)
 
+    def allreduce_f64(self, *vals):
+        """Sum of up to 8 host scalars over the ranks (the global ‖A‖_F², ‖b‖₁, length(b) of a row-sharded solve)."""
+        buf = (C.c_double * len(vals))(*[float(v) for v in vals])
+        capi.call("rls_ctx_allreduce_f64", self.handle, buf, len(vals))
+        return [float(v) for v in buf]
+
 
 def _peer_export(self, max_floats):
     buf = C.create_string_buffer(64)
@@ -194,7 +200,7 @@ class B200Matrix:
     """Dense system matrix (or this rank's row shard of it) in HBM.
 
     The host side is always column-major (Julia `Matrix`).  `layout="row"` keeps the ROWS contiguous on
-    the device, which lets the normal operator A'(A x) sweep HBM once (csrc/rls_rowpass.cu); `layout="col"`
+    the device, which lets the normal operator A'(A x) sweep HBM once (csrc/rls_rowstream.cu); `layout="col"`
     mirrors the host storage (what `rls_mat_wrap_device` adopts from a CuArray); `"auto"` (default) lets
     the library choose (row-major whenever the one-pass kernel supports the shape)."""
     def __init__(self, ctx, dtype, m, n, host=None, layout="auto"):

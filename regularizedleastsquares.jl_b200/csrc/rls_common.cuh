@@ -120,6 +120,7 @@ bool rls_env_flag(const char* name, bool dflt);
 // internal (non-ABI) helpers used across translation units
 int32_t rls_vec_create_internal(rls_ctx_s* ctx, int32_t dtype, int64_t len, rls_vec_s** out);
 int32_t rls_allreduce_raw(rls_ctx_s* ctx, void* buf, int64_t nfloats);  // float sum-allreduce in place
+int32_t rls_allreduce_f64_host(rls_ctx_s* c, double* vals, int n);    // host doubles, sum over ranks in place
 bool rls_p2p_available(const rls_ctx_s* c, int64_t nfloats);
 int32_t rls_p2p_allreduce(rls_ctx_s* c, const float* src, int64_t sstride, int nsrc, int64_t nf, float* res, const int* gate);
 int32_t rls_p2p_check_abort(rls_ctx_s* c);
@@ -137,7 +138,7 @@ struct NormalPartials { const float* gpart; int64_t gstride; int ncl; };
 // with np->ncl == 0 and nothing launched when the operator cannot defer (not row-major one-pass, or row-sharded)
 int32_t rls_normal_apply_deferred_raw(rls_normal_t op, const void* x, const float* xold, const float* th_old, const float* th,
                                       const int* gate, NormalPartials* np);
-// row-major one-pass kernels (rls_rowpass.cu)
+// row-major one-pass kernels (rls_rowstream.cu)
 struct RowPlan;
 int32_t rls_rowpass_plan_create(rls_ctx_s* c, rls_mat_s* A, RowPlan** out);
 void rls_rowpass_plan_destroy(RowPlan* p);

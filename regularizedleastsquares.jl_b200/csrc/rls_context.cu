@@ -317,6 +317,30 @@ int32_t rls_allreduce_raw(rls_ctx_s* c, void* buf, int64_t nfloats) {
   return RLS_OK;
 }
 
+// Sum of n <= RLS_MAX_ACC host doubles over the ranks (in place): the scalars a row-sharded solve needs globally —
+// ‖A‖_F² (SystemMatrixBasedNormalization, NormalizedRegularization.jl:47-58), ‖b‖₁ and length(b)
+// (MeasurementBasedNormalization :40-43; ADMM's σ_abs = sqrt(length(b))·absTol, ADMM.jl:212).
+int32_t rls_allreduce_f64_host(rls_ctx_s* c, double* vals, int n) {
+  if (c->nranks <= 1) return RLS_OK;
+  RLS_CHECK_ARG(c->nccl_comm, "context has nranks>1 but no communicator");
+  RLS_CHECK_ARG(vals && n >= 1 && n <= RLS_MAX_ACC, "allreduce_f64: 1..%d values", RLS_MAX_ACC);
+  RLS_CUDA(cudaStreamSynchronize(c->stream));  // red_out_host may still be the target of an earlier download
+  memcpy(c->red_out_host, vals, sizeof(double) * n);
+  RLS_CUDA(cudaMemcpyAsync(c->red_out, c->red_out_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  // ncclFloat64 = 8, ncclSum = 0
+  RLS_NCCL(p_ncclAllReduce(c->red_out, c->red_out, (size_t)n, 8, 0, c->nccl_comm, c->stream));
+  RLS_CUDA(cudaMemcpyAsync(c->red_out_host, c->red_out, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  RLS_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(vals, c->red_out_host, sizeof(double) * n);
+  return RLS_OK;
+}
+
+extern "C" int32_t rls_ctx_allreduce_f64(rls_ctx_t c, double* vals, int32_t n) {
+  RLS_CHECK_ARG(c && vals, "NULL argument");
+  RlsDeviceGuard g(c->device);
+  return rls_allreduce_f64_host(c, vals, n);
+}
+
 extern "C" int32_t rls_vec_allreduce(rls_vec_t v) {
   RLS_CHECK_ARG(v, "vec is NULL");
   RlsDeviceGuard g(v->ctx->device);
@@ -594,7 +618,7 @@ extern "C" int32_t rls_mat_create_layout(rls_ctx_t ctx, int32_t dtype, int64_t m
   RLS_CHECK_ARG(!host || ld >= m, "ld < m");
   RLS_CHECK_ARG(layout >= RLS_LAYOUT_COLMAJOR && layout <= RLS_LAYOUT_AUTO, "unknown layout %d", layout);
   if (layout == RLS_LAYOUT_AUTO) {
-    // rows of at most 16 x 8192 floats fit the cluster decomposition of rls_rowpass.cu
+    // rows of at most 16 x 8192 floats fit the cluster decomposition of rls_rowstream.cu
     const int64_t nf = n * (dtype == RLS_C32 ? 2 : 1);
     // and pay off once A no longer sits in L2: below ~64 MB an iteration is launch-latency bound and the
     // two-kernel column-major path is the shorter one (measured on C1: 40 vs 56 us per CGNR iteration)

@@ -1115,6 +1115,14 @@ extern "C" int32_t rls_kaczmarz_sweep(rls_kaczmarz_t K) {
   RlsDeviceGuard g(K->ctx->device);
   if (K->persistent && K->nblk > 0) {
     rls_ctx_s* c = K->ctx;
+    if (K->epoch + (unsigned long long)K->nblk + 2ull > 0xffffffffull) {
+      // the exchange tags are the low 32 bits of epoch + block + 1: before they wrap (a tag of 0 would match a zeroed
+      // or stale slot) restart the epoch with clean exchange buffers, as rls_kaczmarz_init does
+      RLS_CUDA(cudaMemsetAsync(K->d_tpart2, 0, K->tagged_bytes, c->stream));
+      RLS_CUDA(cudaMemsetAsync(K->d_alpha2, 0, K->alpha2_bytes, c->stream));
+      RLS_CUDA(cudaMemsetAsync(K->d_tsum, 0, K->alpha2_bytes, c->stream));
+      K->epoch = 0;
+    }
     KzSweep sp;
     sp.A = (const float*)K->A->d; sp.ldf = K->A->ld * K->fpe; sp.npacks = K->A->n * K->fpe / 4;
     sp.rows = K->d_rows; sp.denom = K->d_denom; sp.G = K->d_G; sp.Dinv = K->d_Dinv;

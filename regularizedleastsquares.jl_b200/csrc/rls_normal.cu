@@ -481,7 +481,7 @@ extern "C" int32_t rls_normal_create(rls_mat_t A, int32_t form, rls_normal_t* ou
   op->dtype_ = A->dtype;
   const double bytes = (double)A->m * (double)A->n * (double)rls_elem_size(A->dtype);
   if (A->layout == RLS_LAYOUT_ROWMAJOR && form != RLS_NORMAL_GRAM) {
-    // rows contiguous: the cluster kernel of rls_rowpass.cu sweeps A once (ONEPASS, also what AUTO
+    // rows contiguous: the streaming cluster kernel of rls_rowstream.cu sweeps A once (ONEPASS, also what AUTO
     // resolves to) or runs as two sweeps y = A x, g = A' y (TWOPASS, kept for comparison)
     op->row = rls_mat_rowplan(A);
     if (!op->row) { delete op; return RLS_ERR_UNSUPPORTED; }

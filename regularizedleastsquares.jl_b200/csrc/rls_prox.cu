@@ -32,19 +32,20 @@ __global__ void __launch_bounds__(PB) prox_ew_kernel(T* __restrict__ x, int64_t 
   }
 }
 
-// ProxL21.jl:30-35: group j = { x[j + s*L] }, s = 0..slices-1 ; x *= max((g-λ)/g, 0) (0/0 -> NaN kept)
+// ProxL21.jl:30-35: L = length(x) ÷ slices; group j = x[j:L:end] (slices elements, one more for the first
+// length(x) - L*slices groups when the division leaves a remainder) ; x *= max((g-λ)/g, 0) (0/0 -> NaN kept)
 template <typename T>
-__global__ void __launch_bounds__(PB) prox_l21_kernel(T* __restrict__ x, int64_t L, int64_t slices, float lam,
+__global__ void __launch_bounds__(PB) prox_l21_kernel(T* __restrict__ x, int64_t L, int64_t n, float lam,
                                                       const float* __restrict__ lam_dev, const int* __restrict__ gate) {
   if (gate && *gate) return;
   const float thr = lam_dev ? *lam_dev : lam;
   for (int64_t j = (int64_t)blockIdx.x * PB + threadIdx.x; j < L; j += (int64_t)gridDim.x * PB) {
     double s = 0.0;
-    for (int64_t k = 0; k < slices; ++k) s += Elem<T>::abs2(x[j + k * L]);
+    for (int64_t e = j; e < n; e += L) s += Elem<T>::abs2(x[e]);
     const float g = (float)sqrt(s);
     const float q = fdiv(fsub(g, thr), g);
     const float ff = isnan(q) ? q : fmaxf(q, 0.f);  // Julia's max(NaN,0) is NaN (0/0 group, quirk 7); fmaxf would hide it
-    for (int64_t k = 0; k < slices; ++k) x[j + k * L] = Elem<T>::scale(x[j + k * L], ff);
+    for (int64_t e = j; e < n; e += L) x[e] = Elem<T>::scale(x[e], ff);
   }
 }
 
@@ -237,11 +238,13 @@ int32_t rls_prox_launch(rls_ctx_s* c, int32_t dtype, void* x, int64_t n, const r
     case RLS_REG_L21: {
       RLS_CHECK_ARG(reg->slices >= 1, "L21: slices must be >= 1");
       int64_t L = n / reg->slices;
-      if (L == 0) return RLS_OK;
+      if (n == 0) return RLS_OK;
+      // upstream x[i:0:end] throws (zero step) when there are more slices than elements
+      RLS_CHECK_ARG(L >= 1, "L21: %lld slices exceed the %lld elements of x", (long long)reg->slices, (long long)n);
       if (dtype == RLS_C32)
-        prox_l21_kernel<float2><<<ew_grid(c, L), PB, 0, c->stream>>>((float2*)x, L, reg->slices, lam, lam_dev, gate);
+        prox_l21_kernel<float2><<<ew_grid(c, L), PB, 0, c->stream>>>((float2*)x, L, n, lam, lam_dev, gate);
       else
-        prox_l21_kernel<float><<<ew_grid(c, L), PB, 0, c->stream>>>((float*)x, L, reg->slices, lam, lam_dev, gate);
+        prox_l21_kernel<float><<<ew_grid(c, L), PB, 0, c->stream>>>((float*)x, L, n, lam, lam_dev, gate);
       c->launches++;
       break;
     }

@@ -126,6 +126,10 @@ __device__ inline void scalar_step(DevState* S, int step, int arg, const double*
       break;
     }
     case STEP_FISTA_GRAD:
+      // λ is re-normalised by init! AFTER the state was set up (FISTA.jl:128, rls_solver_set_reg): form ρλ for the
+      // non-elementwise prox (L21 / TV) from the current λ, as the elementwise path does inside its kernel
+      S->thr = thr_from(S, 0, S->rho);
+      // fallthrough
     case STEP_POGM_GRAD:
     case STEP_OPTISTA_GRAD:
       S->save[0] = t[0];

@@ -717,6 +717,13 @@ static int32_t init_lane_t(rls_solver_s* s, Lane& L, const void* b_dev, int64_t 
   const int g = ew_grid(c, n);
   const size_t nb = (size_t)n * sizeof(T);
   s->m = b_len;
+  if (c->nranks > 1 && s->A) {
+    // row-sharded: length(b) in σ_abs = sqrt(length(b))·absTol (ADMM.jl:212) is the GLOBAL row count, so that all
+    // ranks take the same stopping decision
+    double len = (double)b_len;
+    RLS_TRY(rls_allreduce_f64_host(c, &len, 1));
+    s->m = (int64_t)(len + 0.5);
+  }
   RLS_TRY(push_config(s, L));
   L.enq_swaps = 0;
   L.base_iter = 0;

@@ -68,7 +68,7 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// bounded wait (see rls_rowpass.cu): a protocol error ends the launch instead of hanging the GPU
+// bounded wait (see rls_async.cuh): a protocol error ends the launch instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity, volatile int* s_abort, int* g_abort) {
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();

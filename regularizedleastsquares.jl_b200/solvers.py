@@ -99,12 +99,8 @@ class AbstractLinearSolver:
             if self.A is None:
                 raise ValueError("SystemMatrixBasedNormalization requires supplying A to the constructor of the solver")
             fro2 = self.A.frob2()           # Σ_m ‖A[m,:]‖² (NormalizedRegularization.jl:47-58)
-            if self.ctx.nranks > 1:
-                import torch
-                import torch.distributed as dist
-                t = torch.tensor([fro2], dtype=torch.float64)
-                dist.all_reduce(t)
-                fro2 = float(t[0])
+            if self.ctx.nranks > 1:     # row shards: Σ over all rows of the global matrix
+                fro2 = self.ctx.allreduce_f64(fro2)[0]
             e = np.float32(np.sqrt(fro2))
             f = np.float32(e * e / np.float32(self.A.n))
         else:
@@ -145,8 +141,14 @@ class AbstractLinearSolver:
         if not isinstance(self.normalizeReg, MeasurementBasedNormalization):
             return
         src = self._norm_source(b_host, b_dev)          # FISTA family: x₀ = A'b ; CGNR/ADMM: b
-        f = np.float32(np.float32(src.asum()) / np.float32(src.length)) if isinstance(src, B200Vector) \
-            else np.float32(np.sum(np.abs(src), dtype=np.float32) / np.float32(src.size))
+        if isinstance(src, B200Vector):
+            asum, length = src.asum(), src.length
+        else:
+            asum, length = float(np.sum(np.abs(src), dtype=np.float32)), src.size
+        if self.ctx.nranks > 1 and self._norm_source_is_sharded:
+            # b is row-sharded: ‖b‖₁ and length(b) are sums over the ranks (x₀ = A'b is replicated and is not)
+            asum, length = self.ctx.allreduce_f64(asum, length)
+        f = np.float32(np.float32(asum) / np.float32(length))
         self._apply_factor(f)
 
     def _apply_factor(self, f):
@@ -165,6 +167,8 @@ class AbstractLinearSolver:
 
     def _norm_source(self, b_host, b_dev):
         return self._vec("x0")
+
+    _norm_source_is_sharded = False
 
     # ---------------- the iterator protocol ----------------
     def _b_to_device(self, b):
@@ -343,6 +347,8 @@ class CGNR(AbstractLinearSolver):
     def _norm_source(self, b_host, b_dev):
         return b_dev if b_dev is not None else np.asarray(b_host)
 
+    _norm_source_is_sharded = True
+
     def _apply_factor(self, f):
         super()._apply_factor(f)
         self.L2 = self.reg
@@ -399,6 +405,8 @@ class ADMM(AbstractLinearSolver):
 
     def _norm_source(self, b_host, b_dev):
         return b_dev if b_dev is not None else np.asarray(b_host)
+
+    _norm_source_is_sharded = True
 
     def convergence(self):
         k = len(self.reg)

@@ -169,6 +169,23 @@ def test_prox_l21(rls, ctx, dtype, slices):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,slices", [(1003, 8), (37, 5), (9, 4), (13, 13)])
+def test_prox_l21_length_not_a_multiple_of_slices(rls, ctx, dtype, n, slices):
+    """ProxL21.jl:30-35: L = n ÷ slices and group j is x[j:L:end] — the trailing n - L*slices elements belong to the
+    first groups (they enter the group norms and are rescaled), nothing is left untouched."""
+    x = rand_vector(dtype, n, 59)
+    a = x.copy(); b = x.copy()
+    rls.prox_(rls.L21Regularization(np.float32(0.7), slices=slices), a)
+    O.prox_(O.L21Regularization(np.float32(0.7), slices=slices), b)
+    assert rel(a, b) < 1e-6
+    L = n // slices
+    if n % slices:
+        assert not np.array_equal(a[L * slices:], x[L * slices:])     # the tail was thresholded too
+    with pytest.raises(Exception):                                    # more slices than elements: x[i:0:end] throws upstream
+        rls.prox_(rls.L21Regularization(np.float32(0.7), slices=n + 1), x.copy())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape,dims", [((64, 48), None), ((64, 48), (1,)), ((64, 48), (2,)), ((300,), None),
                                         ((12, 10, 9), None), ((12, 10, 9), (1, 3)), ((1, 40), None)])
 def test_gradient_op_and_tv(rls, ctx, dtype, shape, dims):

@@ -269,6 +269,26 @@ def test_measurement_based_normalization(rls, ctx):
     assert rel(rls.solve_(S, b), R.solve(b)) < TOL
 
 
+@pytest.mark.parametrize("solver", ["FISTA", "POGM", "OptISTA"])
+@pytest.mark.parametrize("regname", ["TV", "L21"])
+def test_measurement_based_normalization_non_elementwise_prox(rls, ctx, solver, regname):
+    """init! re-normalises λ AFTER the solver state exists (FISTA.jl:128): the threshold ρλ of the TV / L21 prox must
+    follow it — on the first solve and again when the next b has another scale."""
+    dtype = np.complex64
+    A, xt, b = problem(dtype, 192, 256)
+    rho = rho_for(A)
+    if regname == "TV":
+        mk = lambda M: M.TVRegularization(np.float32(5e-2), shape=(16, 16))
+    else:
+        mk = lambda M: M.L21Regularization(np.float32(5e-2), slices=4)
+    S = getattr(rls, solver)(A, iterations=15, rho=rho, relTol=0.0, reg=mk(rls), normalizeReg=rls.MeasurementBasedNormalization())
+    R = getattr(O, solver)(A, iterations=15, rho=rho, relTol=0.0, reg=mk(O), normalizeReg=O.MeasurementBasedNormalization())
+    for scale in (1.0, 37.0, 0.02):            # the factor ‖A'b‖₁/n changes from solve to solve
+        bs = (b * np.float32(scale)).astype(dtype)
+        x = rls.solve_(S, bs); xr = R.solve(bs)
+        assert rel(x, xr) < 2e-5, (solver, regname, scale)
+
+
 def test_power_iterations_and_default_rho(rls, ctx):
     dtype = np.complex64
     A, xt, b = problem(dtype, 256, 512)

@@ -111,6 +111,22 @@ def test_prox_l2_l1():
     assert 0.5 * np.linalg.norm(noisy - x_l1) ** 2 + O.reg_norm(r, x_l1) <= O.reg_norm(r, noisy)
 
 
+def test_prox_l21_ragged_groups_by_hand():
+    """ProxL21.jl:30-35 with length(x) = 7, slices = 3: L = 2, groups x[1:2:end] = {1,3,5,7} and x[2:2:end] = {2,4,6}
+    (1-based) — every element is rescaled by its group's factor, including the seventh."""
+    x = np.array([3.0, 1.0, 4.0, 2.0, 12.0, 2.0, 0.0])
+    lam = 1.0
+    g0, g1 = np.linalg.norm(x[0::2]), np.linalg.norm(x[1::2])      # 13, 3
+    want = x.copy()
+    want[0::2] *= (g0 - lam) / g0
+    want[1::2] *= (g1 - lam) / g1
+    got = O.prox_(O.L21Regularization(lam, slices=3), x.copy())
+    assert np.allclose(got, want, rtol=1e-15)
+    assert np.isclose(O.reg_norm(O.L21Regularization(lam, slices=3), x), lam * (g0 + g1))
+    with pytest.raises(ValueError):
+        O.prox_(O.L21Regularization(lam, slices=8), x.copy())
+
+
 def test_prox_l21():
     """test/testProxMaps.jl:44-72 (N=256, 8 slices, last 2 noisy)."""
     rng = np.random.default_rng(1234)
