@@ -1,17 +1,19 @@
 #!/usr/bin/env python
-"""bench.py — FISTA-L1 iterations/s on a dense Float32 A 16384 x 65536 (BASELINE.json
-configs[1]) through librls_b200, with the roofline of the normal-operator kernel and the
-restated-reference CPU baseline beside it.
+"""bench.py — FISTA-L1 and CGNR iterations/s on the dense ComplexF32 system 262144 x 65536 (137.4 GB; BASELINE.json
+configs[4], the configuration its metric "iterations/s ... at 1/2/4/8" and its north-star target are quoted on) through
+librls_b200, with the roofline of the one-pass normal-operator kernel and the restated-reference CPU baseline beside it.
 
-  python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun)
-  python bench.py --impl reference ...                    (the oracle port on the host cores)
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference ...                    (the oracle port on the host cores, bounded row sample)
 
-A "step" is one solve!(solver, b): `iterations` (200) FISTA iterations on one right-hand
-side.  `value` times K steps with b already resident in HBM; `e2e` times the same K steps
-through the public API with host buffers (H2D of b and D2H of x inside the timed region).
-N>1 is weak scaling: every rank holds one 16384 x 65536 row shard of a (16384*N) x 65536
-system, one NCCL allreduce of the n-vector per iteration; `value` counts shard-iterations
-(iterations/s x N), so N=1 is plain iterations/s.
+STRONG scaling: the global problem is fixed; A is row-partitioned over the N ranks (N = 1: the whole 137.4 GB matrix in
+the 180 GB of one B200), x and every n-vector are replicated, one NCCL all-reduce of the 65536-vector per iteration.
+A "step" is one solve!(solver, b): init! (one back-projection A'b) + 100 FISTA-L1 iterations on one right-hand side;
+`value` = true iterations/s of the whole job (not multiplied by N), timed over K steps with b resident in HBM; `e2e`
+times the same K steps through the public API with HOST buffers (H2D of the b shard and D2H of x inside the timed
+region).  `cgnr` carries the same measurement for CGNR + L2 (50 iterations per step).  At N > 1 the run first solves a
+small twin (8192 x 65536) row-sharded AND on rank 0's GPU alone and asserts rel-L2 <= 1e-5 between the two.
+`secondary_c2` keeps round 1's line: FISTA-L1 on one Float32 16384 x 65536 shard per GPU (weak scaling).
 """
 import argparse
 import json
@@ -21,14 +23,25 @@ import sys
 import threading
 import time
 
-import numpy as np
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-M, N_COLS, ITERS = 16384, 65536, 200
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 for N > 1: the CPU arm must use all host threads it can, and say how many
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
+import numpy as np  # noqa: E402
+
+M_GLOBAL, N_COLS = 262144, 65536
+FISTA_ITERS, CGNR_ITERS = 100, 50
 LAMBDA = np.float32(1e-3)
 SEED = 12345
+TWIN_M = 8192
+METRIC = "FISTA-L1 iterations/s on dense ComplexF32 A 262144x65536, row-sharded over N GPUs (strong scaling)"
+WORKLOAD = ("C5: FISTA + L1Regularization(1f-3) [value] and CGNR + L2Regularization(1f-3) [cgnr] on the dense ComplexF32 "
+            "system 262144x65536 (137.4 GB, Philox CN(0,1)/sqrt(m) generated on the devices), rho = 0.95/lambda_max "
+            "(10 power iterations), relTol = 0; one step = one solve! = init! + 100 (FISTA) / 50 (CGNR) iterations")
 
 
 def measured_peaks():
@@ -76,68 +89,111 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
-_CPU_PROBLEM = {}
-METRIC = "FISTA-L1 iterations/s on dense A (Float32 16384x65536 per GPU)"
-WORKLOAD = ("C2: FISTA + L1Regularization(1f-3), dense Float32 A 16384x65536, 200 iterations per solve!, "
-            "rho = 0.95/lambda_max (30 power iterations), relTol = 0")
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's loop (NumPy -> threaded OpenBLAS cgemv) on a bounded ROW SAMPLE of the same Philox matrix
+# ------------------------------------------------------------------------------------------------------------------
+_CPU = {}
 
 
-def cpu_sample(iters=100, m_sub=8192, threads=None):
-    """The oracle's FISTA loop (NumPy -> threaded OpenBLAS sgemv) on the workload (m_sub = 16384: the full system;
-    smaller: a row subsample whose iterations/s are scaled linearly in m).  The matrix is generated once per process."""
-    import oracle as O
-    if m_sub not in _CPU_PROBLEM:
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(p.get("num_threads", 1)) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", "1"))
+
+
+def cpu_problem(m_sub):
+    """Rows [0, m_sub) of the global C5 matrix (the very entries the devices generate) and the matching part of b."""
+    if m_sub not in _CPU:
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle.philox import philox_values, IH4
+        scale = np.float32(1.0 / np.sqrt(M_GLOBAL))
+        A = np.empty((m_sub, N_COLS), dtype=np.complex64, order="F")
+        rows = np.arange(m_sub, dtype=np.uint64)
+
+        def fill(j0):
+            cols = np.arange(j0, min(N_COLS, j0 + 128), dtype=np.uint64)
+            idx = rows[:, None] + cols[None, :] * np.uint64(M_GLOBAL)
+            A[:, j0:j0 + cols.size] = philox_values(SEED, idx, 0, 0, IH4, scale) + 1j * philox_values(SEED, idx, 0, 1, IH4, scale)
+
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:   # NumPy releases the GIL inside the big array ops
+            list(ex.map(fill, range(0, N_COLS, 128)))
         rng = np.random.default_rng(SEED)
-        A = np.empty((m_sub, N_COLS), dtype=np.float32, order="F")
-        for j0 in range(0, N_COLS, 4096):     # column blocks: no second 4 GB temporary
-            A[:, j0:j0 + 4096] = rng.standard_normal((m_sub, min(4096, N_COLS - j0)), dtype=np.float32) / np.float32(np.sqrt(M))
-        _CPU_PROBLEM[m_sub] = (A, rng.standard_normal(m_sub, dtype=np.float32))
-    A, b = _CPU_PROBLEM[m_sub]
-    S = O.FISTA(A, reg=O.L1Regularization(LAMBDA), iterations=iters + 2, rho=np.float32(0.1), relTol=0.0)
+        b = (rng.standard_normal(m_sub) + 1j * rng.standard_normal(m_sub)).astype(np.complex64)
+        _CPU[m_sub] = (A, b)
+    return _CPU[m_sub]
+
+
+def cpu_step(kind, m_sub, iters):
+    """`iters` iterations of the oracle solver on the row sample; returns (iterations done, seconds)."""
+    import oracle as O
+    A, b = cpu_problem(m_sub)
+    if kind == "fista":
+        S = O.FISTA(A, reg=O.L1Regularization(LAMBDA), iterations=iters + 1, rho=np.float32(0.05), relTol=0.0)
+    else:
+        S = O.CGNR(A, reg=O.L2Regularization(LAMBDA), iterations=iters + 1, relTol=0.0)
     S.init(b)
-    S.iterate(); S.iterate()
+    S.iterate()                      # first touch of the work arrays
     t0 = time.perf_counter()
     k = 0
-    while S.iterate():
+    while k < iters and S.iterate():
         k += 1
-    dt = time.perf_counter() - t0
-    its_sub = k / dt
-    return its_sub * (m_sub / M), k, dt
+    return k, time.perf_counter() - t0
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return                                  # N > 1: rank 0 alone runs the CPU arm
     cores = os.cpu_count()
-    m_sub = M                      # the full 16384 x 65536 system
-    v0, _, _ = cpu_sample(iters=5, m_sub=m_sub)          # warm-up; also sizes a step to ~6 s of CPU work
-    iters = int(max(10, min(100, round(v0 * 6.0))))
+    m_sub = 4096                                # 2.1 GB of the 137.4 GB: the gemv pair is DRAM-bound, i.e. linear in m
+    scale_to_full = m_sub / M_GLOBAL
+    t_gen = time.perf_counter()
+    cpu_problem(m_sub)
+    t_gen = time.perf_counter() - t_gen
+    k0, dt0 = cpu_step("fista", m_sub, 4)
+    iters = int(max(8, min(60, round(k0 / dt0 * 4.0))))     # ~4 s of CPU work per step
+    for _ in range(min(args.warmup, 1)):
+        cpu_step("fista", m_sub, iters)
     t0 = time.perf_counter()
-    vals = []
+    k_tot, dt_tot = 0, 0.0
     for _ in range(args.steps):
-        v, k, dt = cpu_sample(iters=iters, m_sub=m_sub)
-        vals.append(v)
+        k, dt = cpu_step("fista", m_sub, iters)
+        k_tot += k
+        dt_tot += dt
     wall = time.perf_counter() - t0
-    value = float(np.mean(vals))
-    sample = (f"{iters} FISTA-L1 iterations per step on the full 16384x65536 Float32 system "
-              f"(oracle loop, NumPy/OpenBLAS two-gemv normal operator, all host threads)")
+    value = k_tot / dt_tot * scale_to_full
+    kc, dtc = cpu_step("cgnr", m_sub, iters)
+    threads = blas_threads()
+    sample = (f"{iters} FISTA-L1 iterations per step x {args.steps} steps of the oracle loop (NumPy + OpenBLAS cgemv pair, {threads} BLAS "
+              f"threads on {cores} host cores) on rows 0..{m_sub - 1} of the same Philox matrix ({m_sub}x{N_COLS} ComplexF32, 2.1 GB); "
+              f"iterations/s scaled by {m_sub}/{M_GLOBAL} to the full system (the iteration is DRAM-bound in A: linear in m)")
     line = {"metric": METRIC, "value": value, "unit": "iterations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * ITERS / value if value > 0 else None, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "iterations_per_step": ITERS,
-                       "note": "Julia is not installed in this image; the reference arm is the float32-faithful oracle port "
-                               "(NumPy/OpenBLAS, rho = 0.1 fixed: the per-iteration cost does not depend on it); each step "
-                               "times a bounded number of iterations of the full-size problem"},
-            "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
+            "ms_per_step": 1e3 * dt_tot / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "c64 (ComplexF32)", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "sample_rows": m_sub, "iterations_timed_per_step": iters,
+                       "iterations_per_s_on_the_sample": k_tot / dt_tot, "scaled_by": scale_to_full,
+                       "ms_per_step_is": "the measured time of one step on the SAMPLE (iterations_timed_per_step iterations of the "
+                                         f"{m_sub}-row system), not a synthesised full-size figure",
+                       "matrix_generation_s": t_gen,
+                       "note": "Julia is not installed in this image; the reference arm is the float32-faithful oracle port of "
+                               "src/FISTA.jl:139-185 with the lazy two-gemv normal operator on OpenBLAS (the BLAS family Julia ships)"},
+            "cgnr": {"value": kc / dtc * scale_to_full, "unit": "iterations/s", "iterations_timed": kc},
+            "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
 def run_b200(args):
+    import ctypes as C
     import rls_b200 as rls
+    capi = rls._capi
     rank, world, local = rls.dist.env_rank()
     multi = world > 1
     if multi:
@@ -148,31 +204,7 @@ def run_b200(args):
     ctx = rls.B200Context.default(local)
     if multi:
         rls.dist.init_comm(ctx, rank, world)
-    m_global = M * world
-    scale = 1.0 / np.sqrt(m_global)
-    A = rls.B200Matrix.philox(np.float32, M, N_COLS, seed=SEED, scale=scale, row_offset=rank * M, m_global=m_global, ctx=ctx)
-    # b = A x_true + noise, generated on the device (shard rows of the global b)
-    xt = rls.B200Vector(ctx, np.float32, N_COLS).fill_philox(SEED, stream=11, dist=0)
-    xt_h = xt.to_numpy()
-    xt_h[np.arange(N_COLS) % 100 != 0] = 0                       # 1 % non-zeros
-    xt.upload(xt_h)
-    b_dev = A.mul(xt)
-    noise = rls.B200Vector(ctx, np.float32, M).fill_philox(SEED, stream=12, dist=1, scale=1e-3, offset=rank * M)
-    b_host = (b_dev.to_numpy() + noise.to_numpy()).astype(np.float32)
-    b_dev.upload(b_host)
-    form = args.normal
-    AHA = rls.B200NormalOp(A, form=form)
-    # rho = 0.95 / lambda_max from 30 power iterations, fixed Philox start vector
-    b0 = rls.B200Vector(ctx, np.float32, N_COLS).fill_philox(SEED, stream=13, dist=1)
-    lam_max = AHA.power_iterations(b0, rtol=1e-3, maxiter=30)
-    rho = np.float32(0.95 / lam_max)
-    S = rls.FISTA(A, AHA=AHA, reg=rls.L1Regularization(LAMBDA), iterations=ITERS, rho=rho, relTol=0.0)
-    import ctypes as C
-    capi = rls._capi
-    it = C.c_int32()
-
-    def solve_dev():
-        capi.call("rls_solver_solve", S._handle, b_dev.handle, None, C.byref(it), C.byref(S._scalars))
+    dt = np.dtype(np.complex64)
 
     def barrier():
         ctx.sync()
@@ -193,84 +225,187 @@ def run_b200(args):
             ms = float(t[0])
         return ms
 
-    for _ in range(max(args.warmup, 3)):
-        solve_dev()
+    def sparse_truth(c, n, stream):
+        xt = rls.B200Vector(c, dt, n).fill_philox(SEED, stream=stream, dist=0)
+        h = xt.to_numpy()
+        h[np.arange(n) % 100 != 0] = 0                         # 1 % non-zeros
+        xt.upload(h)
+        return xt
+
+    # ---- parity twin (N > 1): the sharded solve against the same system on ONE GPU -------------------------------
+    parity = None
+    if multi:
+        lo, hi = rls.dist.row_range(TWIN_M, rank, world, align=4)
+        sc = 1.0 / np.sqrt(TWIN_M)
+        At = rls.B200Matrix.philox(dt, hi - lo, N_COLS, seed=SEED + 1, scale=sc, row_offset=lo, m_global=TWIN_M, ctx=ctx)
+        xt = sparse_truth(ctx, N_COLS, 21)
+        bt = At.mul(xt).to_numpy()
+        rho_t = np.float32(0.05)
+        xs_f = rls.solve_(rls.FISTA(At, reg=rls.L1Regularization(LAMBDA), iterations=20, rho=rho_t, relTol=0.0), bt)
+        xs_c = rls.solve_(rls.CGNR(At, reg=rls.L2Regularization(LAMBDA), iterations=10, relTol=0.0), bt)
+        parts = [None] * world
+        dist.all_gather_object(parts, bt)
+        if rank == 0:
+            solo = rls.B200Context(local)                      # second context on the same GPU, no communicator
+            Af = rls.B200Matrix.philox(dt, TWIN_M, N_COLS, seed=SEED + 1, scale=sc, ctx=solo)
+            bf = np.concatenate(parts)
+            x1_f = rls.solve_(rls.FISTA(Af, reg=rls.L1Regularization(LAMBDA), iterations=20, rho=rho_t, relTol=0.0), bf)
+            x1_c = rls.solve_(rls.CGNR(Af, reg=rls.L2Regularization(LAMBDA), iterations=10, relTol=0.0), bf)
+            rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+            parity = {"twin": f"{TWIN_M}x{N_COLS} ComplexF32, row-sharded over {world} GPUs vs the same system on one GPU",
+                      "fista_l1_20_iterations_rel_l2": rel(xs_f, x1_f), "cgnr_10_iterations_rel_l2": rel(xs_c, x1_c), "tolerance": 1e-5}
+            del Af
+            assert parity["fista_l1_20_iterations_rel_l2"] <= 1e-5 and parity["cgnr_10_iterations_rel_l2"] <= 1e-5, \
+                f"row-sharded solve departs from the single-GPU solve: {parity}"
+        del At
+
+    # ---- the workload: this rank's row block of the global system, generated on the device -------------------------
+    lo, hi = rls.dist.row_range(M_GLOBAL, rank, world, align=4)
+    m_loc = hi - lo
+    scale = 1.0 / np.sqrt(M_GLOBAL)
+    A = rls.B200Matrix.philox(dt, m_loc, N_COLS, seed=SEED, scale=scale, row_offset=lo, m_global=M_GLOBAL, ctx=ctx)
+    xt = sparse_truth(ctx, N_COLS, 11)
+    b_dev = A.mul(xt)
+    noise = rls.B200Vector(ctx, dt, m_loc).fill_philox(SEED, stream=12, dist=1, scale=1e-3, offset=lo)
+    b_host = (b_dev.to_numpy() + noise.to_numpy()).astype(np.complex64)
+    b_dev.upload(b_host)
+    AHA = rls.B200NormalOp(A, form=args.normal)
+    b0 = rls.B200Vector(ctx, dt, N_COLS).fill_philox(SEED, stream=13, dist=1)
+    lam_max = AHA.power_iterations(b0, rtol=1e-3, maxiter=10)
+    rho = np.float32(0.95 / lam_max)
+    S = rls.FISTA(A, AHA=AHA, reg=rls.L1Regularization(LAMBDA), iterations=FISTA_ITERS, rho=rho, relTol=0.0)
+    Sc = rls.CGNR(A, AHA=AHA, reg=rls.L2Regularization(LAMBDA), iterations=CGNR_ITERS, relTol=0.0)
+    it = C.c_int32()
+
+    def solve_dev(solver):
+        capi.call("rls_solver_solve", solver._handle, b_dev.handle, None, C.byref(it), C.byref(solver._scalars))
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        solve_dev(S)
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ctx.launch_count()
-    ms = timed(solve_dev, args.steps)
+    ms = timed(lambda: solve_dev(S), args.steps)
     launches = ctx.launch_count() - l0
-    assert it.value == ITERS
-    its_per_s = args.steps * ITERS / (ms * 1e-3)
+    assert it.value == FISTA_ITERS
+    its_per_s = args.steps * FISTA_ITERS / (ms * 1e-3)
+    x_fista = S._vec("x").to_numpy()
+    assert np.all(np.isfinite(x_fista)) and np.linalg.norm(x_fista) > 0
 
-    # e2e: the user's call — host b in, host x out, every step
+    # e2e: the user's call — host b (this rank's rows) in, host x out, every step
     x_host = None
+
     def solve_host():
         nonlocal x_host
         x_host = rls.solve_(S, b_host)
     for _ in range(2):
         solve_host()
     ms_e2e = timed(solve_host, args.steps)
+    e2e_its = args.steps * FISTA_ITERS / (ms_e2e * 1e-3)
+    assert np.array_equal(x_host, x_fista), "host-buffer solve and device-buffer solve differ"
+
+    # CGNR on the same system
+    for _ in range(2):
+        solve_dev(Sc)
+    ms_c = timed(lambda: solve_dev(Sc), args.steps)
+    assert it.value == CGNR_ITERS
+    cgnr_its = args.steps * CGNR_ITERS / (ms_c * 1e-3)
     sampler.stop_flag.set()
     sampler.join(timeout=2)
-    e2e_its = args.steps * ITERS / (ms_e2e * 1e-3)
+    clocks = sampler.summary()
 
-    # roofline of the dominant kernel: the normal-operator apply, timed alone on its stream
+    # roofline of the dominant kernel: the one-pass normal-operator apply on this rank's shard, timed alone on its stream
     xv = S._vec("x")
-    res = rls.B200Vector(ctx, np.float32, N_COLS)
-    reps = 40
-    for _ in range(5):
+    res = rls.B200Vector(ctx, dt, N_COLS)
+    reps = 20
+    for _ in range(3):
         AHA.apply(xv, res)
     ms_k = timed(lambda: AHA.apply(xv, res), reps) / reps
-    alg_bytes = M * N_COLS * 4
     peak, peak_src = measured_peaks()
+    alg_bytes = m_loc * N_COLS * 8
     achieved = alg_bytes / (ms_k * 1e-3) / 1e9
+    total_bytes = M_GLOBAL * N_COLS * 8
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                tr = json.load(f)
-                traffic = tr.get(f"{AHA.form}/{A.layout}", tr.get(AHA.form) if A.layout == "col" else None)
+                per_byte = json.load(f).get("rowstream_complex_dram_bytes_per_algorithmic_byte")
+            traffic = int(per_byte * alg_bytes) if per_byte else None
         except Exception:
             traffic = None
-    clocks = sampler.summary()
+
+    # secondary: round 1's line — FISTA-L1 on one Float32 16384 x 65536 shard per GPU (weak scaling)
+    secondary = None
+    if not args.no_secondary:
+        m2 = 16384
+        A2 = rls.B200Matrix.philox(np.float32, m2, N_COLS, seed=SEED, scale=1.0 / np.sqrt(m2 * world), row_offset=rank * m2,
+                                   m_global=m2 * world, ctx=ctx)
+        x2 = rls.B200Vector(ctx, np.float32, N_COLS).fill_philox(SEED, stream=11, dist=0)
+        h2 = x2.to_numpy(); h2[np.arange(N_COLS) % 100 != 0] = 0; x2.upload(h2)
+        b2 = A2.mul(x2)
+        op2 = rls.B200NormalOp(A2, form=args.normal)
+        rho2 = np.float32(0.95 / op2.power_iterations(rls.B200Vector(ctx, np.float32, N_COLS).fill_philox(SEED, stream=13, dist=1), maxiter=30))
+        S2 = rls.FISTA(A2, AHA=op2, reg=rls.L1Regularization(LAMBDA), iterations=200, rho=rho2, relTol=0.0)
+        call2 = lambda: capi.call("rls_solver_solve", S2._handle, b2.handle, None, C.byref(it), C.byref(S2._scalars))
+        for _ in range(3):
+            call2()
+        ms2 = timed(call2, 5)
+        secondary = {"workload": "C2 shard per GPU: FISTA-L1, Float32 16384x65536, 200 iterations per solve (weak scaling, "
+                                 "round-1 bench line)", "shard_iterations_per_s_per_gpu": 5 * 200 / (ms2 * 1e-3),
+                     "ms_per_iteration": ms2 / 5 / 200, "frac_of_measured_hbm": m2 * N_COLS * 4 / (ms2 / 5 / 200 * 1e-3) / 1e9 / peak,
+                     "normal_operator": op2.describe()}
+        del S2, op2, A2
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        m_sub = M
-        v0, _, _ = cpu_sample(iters=5, m_sub=m_sub)
-        v, k, dt = cpu_sample(iters=int(max(20, min(300, round(v0 * 12.0)))), m_sub=m_sub)      # ~12 s of CPU work
-        cpu = {"value": v, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"{k} FISTA-L1 iterations of the oracle loop (NumPy/OpenBLAS) on the full {m_sub}x{N_COLS} system in "
-                         f"{dt:.1f} s; restated reference, Julia is not installed"}
+        m_sub = 4096
+        cpu_problem(m_sub)
+        k0, dt0 = cpu_step("fista", m_sub, 4)
+        k, dts = cpu_step("fista", m_sub, int(max(20, min(400, round(k0 / dt0 * 12.0)))))      # ~12 s of CPU work
+        threads = blas_threads()
+        cpu = {"value": k / dts * m_sub / M_GLOBAL, "unit": "iterations/s", "cores": threads, "kind": "port",
+               "sample": f"{k} FISTA-L1 iterations of the oracle loop (NumPy + OpenBLAS cgemv pair, {threads} BLAS threads on "
+                         f"{os.cpu_count()} host cores) in {dts:.1f} s on rows 0..{m_sub - 1} of the same Philox matrix "
+                         f"({m_sub}x{N_COLS} ComplexF32); iterations/s scaled by {m_sub}/{M_GLOBAL} to the full system (DRAM-bound, "
+                         "linear in m); restated reference — Julia is not installed"}
     if rank == 0:
+        ms_it = ms / args.steps / FISTA_ITERS
+        ms_it_c = ms_c / args.steps / CGNR_ITERS
         line = {
             "metric": METRIC,
-            "value": its_per_s * world, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "normal_operator": AHA.form, "iterations_per_step": ITERS,
-                       "parallelism": "single GPU" if world == 1 else f"row-sharded x{world}: (16384*{world})x65536, one "
-                                      "NCCL allreduce of the 65536-vector per iteration; value = shard-iterations/s",
-                       "l2": "inputs (4.3 GB per GPU) are far larger than L2; no flush needed",
-                       "ms_per_iteration": ms / args.steps / ITERS,
-                       "in_step_gbs": alg_bytes * ITERS * args.steps / (ms * 1e-3) / 1e9},
-            "e2e": {"value": e2e_its * world, "unit": "iterations/s", "h2d_bytes_per_step": int(b_host.nbytes),
-                    "d2h_bytes_per_step": int(x_host.nbytes)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
-                         "traffic": traffic, "kernel": f"normal operator A'(A x) [{AHA.describe()}]",
+            "value": its_per_s, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "c64 (ComplexF32)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "normal_operator": AHA.form, "iterations_per_step": FISTA_ITERS,
+                       "parallelism": "single GPU (all 137.4 GB in one B200)" if world == 1 else
+                                      f"row-sharded x{world}: {m_loc} rows per GPU, one NCCL all-reduce of the 65536-vector per "
+                                      "iteration, epilogues replicated",
+                       "l2": f"inputs ({alg_bytes / 1e9:.1f} GB per GPU) are far larger than L2; no flush needed",
+                       "ms_per_iteration": ms_it,
+                       "frac_of_aggregate_measured_hbm": total_bytes / (ms_it * 1e-3) / 1e9 / (peak * world),
+                       "frac_of_aggregate_nominal_8000": total_bytes / (ms_it * 1e-3) / 1e9 / (8000.0 * world)},
+            "cgnr": {"value": cgnr_its, "unit": "iterations/s", "iterations_per_step": CGNR_ITERS, "ms_per_iteration": ms_it_c,
+                     "frac_of_aggregate_measured_hbm": total_bytes / (ms_it_c * 1e-3) / 1e9 / (peak * world)},
+            "e2e": {"value": e2e_its, "unit": "iterations/s", "h2d_bytes_per_step": int(b_host.nbytes) * world,
+                    "d2h_bytes_per_step": int(x_host.nbytes) * world,
+                    "note": "rls.solve_(solver, b_host) per step on every rank: pinned staging + H2D of the rank's rows of b, "
+                            "D2H of x"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_nominal_8000": achieved / 8000.0, "traffic": traffic,
+                         "kernel": f"normal operator A'(A x) on this rank's rows [{AHA.describe()}]",
                          "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                         "matrix_layout": A.layout,
-                         "ms_per_iteration_in_solve": ms / args.steps / ITERS,
-                         "note": "one launch = one normal-operator apply, scored against a single read of A (m*n*4 B); timed right "
-                                 "after the solves, i.e. at the clocks the power cap allows under sustained load (the cluster kernel on 120 "
-                                 "SMs is clock-sensitive: 0.58-0.60 ms at 1.9 GHz, up to 0.68 ms at 1.7 GHz); "
-                                 "onepass/rowmajor = cluster kernel that sweeps A once (+ a tiny partial-sum kernel); "
-                                 "twopass = gemv_n + gemv_c, two sweeps"},
+                         "matrix_layout": A.layout, "ms_per_iteration_in_solve": ms_it,
+                         "note": "one launch = one normal-operator apply on the rank's row block, scored against a single read of "
+                                 "it (rows x 65536 x 8 B), timed alone right after the solves (the clocks the power cap allows); "
+                                 "per iteration a solve adds the epilogue kernel(s) and, at N > 1, the all-reduce"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if parity is not None:
+            line["parity"] = parity
+        if secondary is not None:
+            line["secondary_c2"] = secondary
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -287,6 +422,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--normal", default="auto", choices=["auto", "twopass", "onepass"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -97,6 +97,14 @@ struct rls_mat_s {
 
 static inline size_t rls_elem_size(int32_t dtype) { return dtype == RLS_C32 ? 8 : 4; }
 
+// NVTX ranges (header-only NVTX3: a no-op unless a tool is attached): one range per phase of the reference's call
+// stack — init!, iterate, solve!, the normal-operator apply, the Gram build, a Kaczmarz sweep — so a timeline of
+// nsys / ncu --nvtx shows the solver structure above the kernels (SURVEY §5 tracing hook).
+struct RlsNvtxRange {
+  explicit RlsNvtxRange(const char* name);
+  ~RlsNvtxRange();
+};
+
 // RAII device guard: every entry point runs on its context's device
 struct RlsDeviceGuard {
   int prev = -1;

@@ -1,6 +1,7 @@
 // rls_context.cu — contexts, device vectors / matrices, Philox synthetic data,
 // BLAS-1 style reductions, timers and the NCCL communicator (dlopen'ed, so the
 // single-GPU path has no NCCL dependency).
+#include <nvtx3/nvToolsExt.h>
 #include <dlfcn.h>
 #include <stdarg.h>
 
@@ -23,6 +24,9 @@ extern "C" const char* rls_last_error(void) { return g_err; }
 
 struct TraceRec { const char* name; cudaEvent_t a, b; };
 static std::vector<TraceRec> g_trace;
+RlsNvtxRange::RlsNvtxRange(const char* name) { nvtxRangePushA(name); }
+RlsNvtxRange::~RlsNvtxRange() { nvtxRangePop(); }
+
 bool rls_trace_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("RLS_TRACE_EVENTS"); on = (e && atoi(e) != 0) ? 1 : 0; }

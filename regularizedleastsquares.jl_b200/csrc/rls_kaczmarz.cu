@@ -1112,6 +1112,7 @@ static int32_t kz_sweep_impl(rls_kaczmarz_s* K) {
 extern "C" int32_t rls_kaczmarz_sweep(rls_kaczmarz_t K) {
   RLS_CHECK_ARG(K, "NULL argument");
   RLS_CHECK_ARG(K->initialised, "Kaczmarz sweep before init");
+  RlsNvtxRange nvtx("rls: Kaczmarz iterate (one sweep over the rows)");
   RlsDeviceGuard g(K->ctx->device);
   if (K->persistent && K->nblk > 0) {
     rls_ctx_s* c = K->ctx;

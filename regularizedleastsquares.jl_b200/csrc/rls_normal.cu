@@ -439,6 +439,7 @@ static int32_t alloc_onepass_ws(rls_normal_s* op) {
 }
 
 static int32_t build_gram(rls_normal_s* op) {
+  RlsNvtxRange nvtx("rls: A'*A (Gram build)");
   rls_mat_s* A = op->A;
   rls_ctx_s* c = op->ctx;
   RLS_TRY(rls_mat_create_layout(c, A->dtype, A->n, A->n, nullptr, A->n, RLS_LAYOUT_COLMAJOR, &op->G));
@@ -621,6 +622,7 @@ __global__ void gated_copy_kernel(float* __restrict__ dst, const float* __restri
 }
 
 int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const int* gate) {
+  RlsNvtxRange nvtx("rls: mul!(res, AHA, x)");
   rls_ctx_s* c = op->ctx;
   if (op->form == RLS_NORMAL_GRAM) return rls_gemv_n_raw(op->G, x, res, gate);  // G already summed over ranks
   // row-sharded: kernels write this rank's partial into gpart, one sum-allreduce of the

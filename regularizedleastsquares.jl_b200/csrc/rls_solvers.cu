@@ -791,11 +791,18 @@ static int32_t init_lane_t(rls_solver_s* s, Lane& L, const void* b_dev, int64_t 
 }
 
 // ---------------------------------- iterate -------------------------------------------
+// ADMM / SplitBregman: one iteration is 1 + iterationsCG (+1 for the Bregman update) operator applies with elementwise
+// work between them.  admm_segment enqueues the kernels of segment `seg` and returns the apply that must run before
+// segment seg + 1 (none after the last segment).  The single-RHS path executes that apply at once; the multi-RHS driver
+// (MultiThreading.jl:45-78 batches any solver) collects the K pending applies of a segment and runs them as ONE batched
+// apply — two tensor-core GEMMs that read A once each — with the per-column device gates (done / cgi_gate / sb_outer_gate).
+struct PendingApply { const void* x; void* out; const int* gate; };
+static int admm_segment_count(const rls_solver_desc& d) { return d.iterations_cg + 2 + (d.kind == RLS_SPLITBREGMAN ? 1 : 0); }
+
+// out += Σ ρ_i (Φ_i'Φ_i v): the part of the composite operator AHA + Σ ρ Φ'Φ (ADMM.jl:141-159) that is not AHA
 template <typename T>
-static int32_t composite_apply(rls_solver_s* s, Lane& L, const T* v, T* out, const int* gate, bool fuse_identity_later) {
-  // out = AHA v ; then out = ρ_i (Φ_i'Φ_i v) + out term by term   (ADMM.jl:141-159)
+static int32_t composite_extras(rls_solver_s* s, Lane& L, const T* v, T* out, const int* gate, bool fuse_identity_later) {
   rls_ctx_s* c = s->ctx;
-  RLS_TRY(rls_normal_apply_raw(s->AHA, v, out, gate));
   if (fuse_identity_later) return RLS_OK;
   const int g = ew_grid(c, s->n);
   for (int i = 0; i < s->desc.n_reg; ++i) {
@@ -807,6 +814,112 @@ static int32_t composite_apply(rls_solver_s* s, Lane& L, const T* v, T* out, con
       c->launches++;
     }
   }
+  return RLS_OK;
+}
+
+template <typename T>
+static int32_t admm_segment(rls_solver_s* s, Lane& L, int seg, PendingApply* pa) {
+  rls_ctx_s* c = s->ctx;
+  cudaStream_t st = c->stream;
+  const int64_t n = s->n;
+  const int g = ew_grid(c, n);
+  DevState* S = L.dS;
+  const int* gate = &S->done;
+  const int* cgate = &S->cgi_gate;
+  double* part = c->red_partials;
+  unsigned* tick = c->red_ticket;
+  const int k = s->desc.n_reg;
+  const int ncg = s->desc.iterations_cg;
+  bool all_identity = true;
+  for (int i = 0; i < k; ++i) all_identity &= (s->desc.reg[i].trafo == RLS_TRAFO_IDENTITY);
+  T* beta = P<T>(L.v[V_BETA]);
+  // after the apply of segment 0 (c = AHA x): the rest of the composite operator, then r = β - c, ‖r‖ -> CG scalars
+  auto after_first_apply = [&]() -> int32_t {
+    RLS_TRY(composite_extras<T>(s, L, P<T>(L.v[V_X]), P<T>(L.v[V_CGC]), gate, false));
+    admm_cg_init_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_CGR]), beta, P<T>(L.v[V_CGC]), n, S, part, tick);
+    c->launches++;
+    return RLS_OK;
+  };
+  // after the apply of a CG step (c = AHA u): α = res² / (u·c), x += α u, r -= α c, ‖r‖
+  auto after_cg_apply = [&]() -> int32_t {
+    RLS_TRY(composite_extras<T>(s, L, P<T>(L.v[V_CGU]), P<T>(L.v[V_CGC]), cgate, all_identity));
+    admm_cg_dot_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_CGU]), P<T>(L.v[V_CGC]), n, S, all_identity ? k : 0, part, tick);
+    admm_cg_xr_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_CGR]), P<T>(L.v[V_CGU]), P<T>(L.v[V_CGC]), n, S, part, tick);
+    c->launches += 2;
+    return RLS_OK;
+  };
+  if (seg == 0) {
+    scalar_kernel<<<1, 32, 0, st>>>(S, STEP_ADMM_ITER_BEGIN, 0, gate);
+    c->launches++;
+    // 1. β = A'b + Σ ρ Φ'(z - u)
+    for (int i = 0; i < k; ++i) {
+      if (s->desc.reg[i].trafo == RLS_TRAFO_IDENTITY) {
+        admm_beta_identity_kernel<T><<<g, EB, 0, st>>>(beta, P<T>(L.v[V_BETAY]), P<T>(L.v[V_TZ0 + i]), P<T>(L.v[V_TU0 + i]), n, S, i, i == 0);
+        c->launches++;
+      } else {
+        if (i == 0) { copy_kernel<T><<<g, EB, 0, st>>>(beta, P<T>(L.v[V_BETAY]), n, gate); c->launches++; }
+        RLS_TRY(rls_grad_t_axpy_launch(c, s->dtype, L.v[V_TZ0 + i]->d, beta, beta, 0.f, &S->a_rho[i], 1.f, s->geom[i], gate));
+        RLS_TRY(rls_grad_t_axpy_launch(c, s->dtype, L.v[V_TU0 + i]->d, beta, beta, 0.f, &S->a_rho[i], -1.f, s->geom[i], gate));
+      }
+    }
+    if (k == 0) { copy_kernel<T><<<g, EB, 0, st>>>(beta, P<T>(L.v[V_BETAY]), n, gate); c->launches++; }
+    copy_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_XOLD]), P<T>(L.v[V_X]), n, gate);                    // xᵒˡᵈ = x   :243
+    // cg!(x, AHA + Σ ρ Φ'Φ, β)   :244  — warm start: r = β - (AHA + ...) x
+    fill_gated_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_CGU]), T{}, n, gate);
+    c->launches += 2;
+    *pa = PendingApply{L.v[V_X]->d, L.v[V_CGC]->d, gate};
+  } else if (seg <= ncg) {
+    if (seg == 1) RLS_TRY(after_first_apply());
+    else RLS_TRY(after_cg_apply());
+    admm_cg_u_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_CGU]), P<T>(L.v[V_CGR]), n, S);               // u = r + β u
+    c->launches++;
+    *pa = PendingApply{L.v[V_CGU]->d, L.v[V_CGC]->d, cgate};
+  } else if (seg == ncg + 1) {
+    if (ncg == 0) RLS_TRY(after_first_apply());
+    else RLS_TRY(after_cg_apply());
+    RLS_TRY(rls_proj_launch(c, s->dtype, L.v[V_X]->d, n, s->desc.proj_mask, gate));                 // :246-248
+    // 2./3. z, u, residuals per term
+    swap_roles(s, L); L.enq_swaps++;                                                                 // z <-> zᵒˡᵈ  :253-255
+    for (int i = 0; i < k; ++i) {
+      const rls_reg_desc& ri = s->desc.reg[i];
+      T* z = P<T>(L.v[V_TZ0 + i]); T* zo = P<T>(L.v[V_TZOLD0 + i]); T* u = P<T>(L.v[V_TU0 + i]); T* uo = P<T>(L.v[V_TUOLD0 + i]);
+      if (ri.trafo == RLS_TRAFO_IDENTITY) {
+        if (rls_reg_is_elementwise(ri.kind)) {
+          admm_term_identity_kernel<T, 0><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_XOLD]), z, zo, u, uo, n, S, i, ri.kind, part, tick);
+          c->launches++;
+        } else {
+          admm_term_identity_kernel<T, 1><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_XOLD]), z, zo, u, uo, n, S, i, ri.kind, part, tick);
+          RLS_TRY(rls_prox_launch(c, s->dtype, z, n, &ri, 0.f, &S->a_thr[i], gate, &s->tv));
+          admm_term_identity_kernel<T, 2><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_XOLD]), z, zo, u, uo, n, S, i, ri.kind, part, tick);
+          c->launches += 2;
+        }
+      } else {
+        RLS_TRY(rls_admm_term_gradient(c, s->dtype, L.v[V_X]->d, L.v[V_XOLD]->d, z, zo, u, uo, s->geom[i], S, i, ri.kind));
+      }
+      if (s->desc.vary_rho != RLS_VARY_RHO_NONE) {
+        admm_scale_u_kernel<T><<<ew_grid(c, s->rows[i]), EB, 0, st>>>(u, s->rows[i], S, i);
+        c->launches++;
+      }
+    }
+    scalar_kernel<<<1, 32, 0, st>>>(S, STEP_ADMM_ITER_END, 0, gate);
+    c->launches++;
+    // SplitBregman: Bregman update, gated on the device flag set by ITER_END (converged || iteration >= iterationsInner)
+    if (s->desc.kind == RLS_SPLITBREGMAN) *pa = PendingApply{L.v[V_X]->d, L.v[V_CGC]->d, &S->sb_outer_gate};
+  } else {
+    const int* ogate = &S->sb_outer_gate;
+    sb_outer_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_BETAY]), P<T>(L.v[V_Y]), P<T>(L.v[V_CGC]), n, S);
+    for (int i = 0; i < k; ++i) {
+      if (s->desc.reg[i].trafo == RLS_TRAFO_GRADIENT) {                 // z = Φx ; u = 0   :261-262
+        RLS_TRY(rls_grad_fwd_launch(c, s->dtype, L.v[V_X]->d, L.v[V_TZ0 + i]->d, s->geom[i], ogate));
+        fill_gated_kernel<T><<<ew_grid(c, s->rows[i]), EB, 0, st>>>(P<T>(L.v[V_TU0 + i]), T{}, s->rows[i], ogate);
+      } else {
+        sb_reset_term_kernel<T><<<ew_grid(c, s->rows[i]), EB, 0, st>>>(P<T>(L.v[V_TZ0 + i]), P<T>(L.v[V_TU0 + i]), P<T>(L.v[V_X]), s->rows[i], S);
+      }
+    }
+    scalar_kernel<<<1, 32, 0, st>>>(S, STEP_SB_FINISH, 0, gate);
+    c->launches += 2 + k;
+  }
+  RLS_CUDA(cudaGetLastError());
   return RLS_OK;
 }
 
@@ -905,80 +1018,12 @@ static int32_t enqueue_iteration_t(rls_solver_s* s, Lane& L, int phase = IT_ALL)
     }
     case RLS_SPLITBREGMAN:
     case RLS_ADMM: {
-      const int k = s->desc.n_reg;
-      bool all_identity = true;
-      for (int i = 0; i < k; ++i) all_identity &= (s->desc.reg[i].trafo == RLS_TRAFO_IDENTITY);
-      scalar_kernel<<<1, 32, 0, st>>>(S, STEP_ADMM_ITER_BEGIN, 0, gate);
-      c->launches++;
-      // 1. β = A'b + Σ ρ Φ'(z - u)
-      T* beta = P<T>(L.v[V_BETA]);
-      for (int i = 0; i < k; ++i) {
-        if (s->desc.reg[i].trafo == RLS_TRAFO_IDENTITY) {
-          admm_beta_identity_kernel<T><<<g, EB, 0, st>>>(beta, P<T>(L.v[V_BETAY]), P<T>(L.v[V_TZ0 + i]), P<T>(L.v[V_TU0 + i]), n, S, i, i == 0);
-          c->launches++;
-        } else {
-          if (i == 0) { copy_kernel<T><<<g, EB, 0, st>>>(beta, P<T>(L.v[V_BETAY]), n, gate); c->launches++; }
-          RLS_TRY(rls_grad_t_axpy_launch(c, s->dtype, L.v[V_TZ0 + i]->d, beta, beta, 0.f, &S->a_rho[i], 1.f, s->geom[i], gate));
-          RLS_TRY(rls_grad_t_axpy_launch(c, s->dtype, L.v[V_TU0 + i]->d, beta, beta, 0.f, &S->a_rho[i], -1.f, s->geom[i], gate));
-        }
-      }
-      if (k == 0) { copy_kernel<T><<<g, EB, 0, st>>>(beta, P<T>(L.v[V_BETAY]), n, gate); c->launches++; }
-      copy_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_XOLD]), P<T>(L.v[V_X]), n, gate);                    // xᵒˡᵈ = x   :243
-      // cg!(x, AHA + Σ ρ Φ'Φ, β)   :244
-      fill_gated_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_CGU]), T{}, n, gate);
-      c->launches += 2;
-      RLS_TRY(composite_apply<T>(s, L, P<T>(L.v[V_X]), P<T>(L.v[V_CGC]), gate, false));
-      admm_cg_init_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_CGR]), beta, P<T>(L.v[V_CGC]), n, S, part, tick);
-      c->launches++;
-      const int* cgate = &S->cgi_gate;
-      for (int it = 0; it < s->desc.iterations_cg; ++it) {
-        admm_cg_u_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_CGU]), P<T>(L.v[V_CGR]), n, S);
-        RLS_TRY(composite_apply<T>(s, L, P<T>(L.v[V_CGU]), P<T>(L.v[V_CGC]), cgate, all_identity));
-        admm_cg_dot_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_CGU]), P<T>(L.v[V_CGC]), n, S, all_identity ? k : 0, part, tick);
-        admm_cg_xr_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_CGR]), P<T>(L.v[V_CGU]), P<T>(L.v[V_CGC]), n, S, part, tick);
-        c->launches += 3;
-      }
-      RLS_TRY(rls_proj_launch(c, s->dtype, L.v[V_X]->d, n, s->desc.proj_mask, gate));                 // :246-248
-      // 2./3. z, u, residuals per term
-      swap_roles(s, L); L.enq_swaps++;                                                                 // z <-> zᵒˡᵈ  :253-255
-      for (int i = 0; i < k; ++i) {
-        const rls_reg_desc& ri = s->desc.reg[i];
-        T* z = P<T>(L.v[V_TZ0 + i]); T* zo = P<T>(L.v[V_TZOLD0 + i]); T* u = P<T>(L.v[V_TU0 + i]); T* uo = P<T>(L.v[V_TUOLD0 + i]);
-        if (ri.trafo == RLS_TRAFO_IDENTITY) {
-          if (rls_reg_is_elementwise(ri.kind)) {
-            admm_term_identity_kernel<T, 0><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_XOLD]), z, zo, u, uo, n, S, i, ri.kind, part, tick);
-            c->launches++;
-          } else {
-            admm_term_identity_kernel<T, 1><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_XOLD]), z, zo, u, uo, n, S, i, ri.kind, part, tick);
-            RLS_TRY(rls_prox_launch(c, s->dtype, z, n, &ri, 0.f, &S->a_thr[i], gate, &s->tv));
-            admm_term_identity_kernel<T, 2><<<g, EB, 0, st>>>(P<T>(L.v[V_X]), P<T>(L.v[V_XOLD]), z, zo, u, uo, n, S, i, ri.kind, part, tick);
-            c->launches += 2;
-          }
-        } else {
-          RLS_TRY(rls_admm_term_gradient(c, s->dtype, L.v[V_X]->d, L.v[V_XOLD]->d, z, zo, u, uo, s->geom[i], S, i, ri.kind));
-        }
-        if (s->desc.vary_rho != RLS_VARY_RHO_NONE) {
-          admm_scale_u_kernel<T><<<ew_grid(c, s->rows[i]), EB, 0, st>>>(u, s->rows[i], S, i);
-          c->launches++;
-        }
-      }
-      scalar_kernel<<<1, 32, 0, st>>>(S, STEP_ADMM_ITER_END, 0, gate);
-      c->launches++;
-      if (s->desc.kind == RLS_SPLITBREGMAN) {
-        // Bregman update, gated on the device flag set by ITER_END (converged || iteration >= iterationsInner)
-        const int* ogate = &S->sb_outer_gate;
-        RLS_TRY(rls_normal_apply_raw(s->AHA, L.v[V_X]->d, L.v[V_CGC]->d, ogate));
-        sb_outer_kernel<T><<<g, EB, 0, st>>>(P<T>(L.v[V_BETAY]), P<T>(L.v[V_Y]), P<T>(L.v[V_CGC]), n, S);
-        for (int i = 0; i < k; ++i) {
-          if (s->desc.reg[i].trafo == RLS_TRAFO_GRADIENT) {                 // z = Φx ; u = 0   :261-262
-            RLS_TRY(rls_grad_fwd_launch(c, s->dtype, L.v[V_X]->d, L.v[V_TZ0 + i]->d, s->geom[i], ogate));
-            fill_gated_kernel<T><<<ew_grid(c, s->rows[i]), EB, 0, st>>>(P<T>(L.v[V_TU0 + i]), T{}, s->rows[i], ogate);
-          } else {
-            sb_reset_term_kernel<T><<<ew_grid(c, s->rows[i]), EB, 0, st>>>(P<T>(L.v[V_TZ0 + i]), P<T>(L.v[V_TU0 + i]), P<T>(L.v[V_X]), s->rows[i], S);
-          }
-        }
-        scalar_kernel<<<1, 32, 0, st>>>(S, STEP_SB_FINISH, 0, gate);
-        c->launches += 2 + k;
+      // the iteration as a chain of segments, each ending in one operator apply (admm_segment below)
+      const int nseg = admm_segment_count(s->desc);
+      for (int seg = 0; seg < nseg; ++seg) {
+        PendingApply pa{nullptr, nullptr, nullptr};
+        RLS_TRY(admm_segment<T>(s, L, seg, &pa));
+        if (pa.x) RLS_TRY(rls_normal_apply_raw(s->AHA, pa.x, pa.out, pa.gate));
       }
       break;
     }
@@ -1144,6 +1189,7 @@ extern "C" int32_t rls_solver_init(rls_solver_t s, rls_vec_t b, rls_vec_t x0) {
   if (s->A) RLS_CHECK_ARG(b->len == s->A->m, "init!: b has %lld elements, A has %lld rows", (long long)b->len, (long long)s->A->m);
   else RLS_CHECK_ARG(b->len == s->n, "init!: with AHA only, b must be A'b of length %lld", (long long)s->n);
   if (x0) RLS_CHECK_ARG(x0->len == s->n && x0->dtype == s->dtype, "init!: x0 shape/dtype mismatch");
+  RlsNvtxRange nvtx("rls: init!");
   RlsDeviceGuard g(s->ctx->device);
   if (s->lanes.size() != 1) {
     for (size_t k = 1; k < s->lanes.size(); ++k) free_lane(s->lanes[k]);
@@ -1156,6 +1202,7 @@ extern "C" int32_t rls_solver_init(rls_solver_t s, rls_vec_t b, rls_vec_t x0) {
 
 extern "C" int32_t rls_solver_iterate(rls_solver_t s, int32_t* advanced, rls_solver_scalars* scalars) {
   RLS_CHECK_ARG(s && advanced, "NULL argument");
+  RlsNvtxRange nvtx("rls: iterate");
   RlsDeviceGuard g(s->ctx->device);
   Lane& L = s->lanes[0];
   if (L.hS->done) {
@@ -1193,6 +1240,7 @@ static int32_t solve_lane_async(rls_solver_s* s, Lane& L, const void* b, int64_t
 // iteration (the `for _ in enumerate(solver)` loop of solve!, RegularizedLeastSquares.jl:112-114)
 extern "C" int32_t rls_solver_run(rls_solver_t s, int32_t* iterations_done, rls_solver_scalars* scalars) {
   RLS_CHECK_ARG(s, "NULL argument");
+  RlsNvtxRange nvtx("rls: solve! (iterate until done)");
   RlsDeviceGuard g(s->ctx->device);
   Lane& L = s->lanes[0];
   if (!L.hS->done) RLS_TRY(run_lane_async(s, L, s->desc.kind == RLS_SPLITBREGMAN ? L.hS->sb_total : L.hS->iteration));
@@ -1212,6 +1260,7 @@ extern "C" int32_t rls_solver_solve(rls_solver_t s, rls_vec_t b, rls_vec_t x0, i
   if (s->A) RLS_CHECK_ARG(b->len == s->A->m, "solve!: b has %lld elements, A has %lld rows", (long long)b->len, (long long)s->A->m);
   else RLS_CHECK_ARG(b->len == s->n, "solve!: with AHA only, b must be A'b of length %lld", (long long)s->n);
   if (x0) RLS_CHECK_ARG(x0->len == s->n && x0->dtype == s->dtype, "solve!: x0 shape/dtype mismatch");
+  RlsNvtxRange nvtx("rls: solve!");
   RlsDeviceGuard g(s->ctx->device);
   if (s->lanes.size() != 1) {
     for (size_t k = 1; k < s->lanes.size(); ++k) free_lane(s->lanes[k]);
@@ -1241,6 +1290,7 @@ extern "C" int32_t rls_solver_solve_host(rls_solver_t s, const void* b_host, int
                                          int32_t* iterations_done, rls_solver_scalars* scalars) {
   RLS_CHECK_ARG(s && b_host && x_host, "NULL argument");
   RLS_CHECK_ARG(x_len == s->n, "solve!: x buffer has %lld elements, expected %lld", (long long)x_len, (long long)s->n);
+  RlsNvtxRange nvtx("rls: solve! (host buffers)");
   RlsDeviceGuard g(s->ctx->device);
   const size_t es = rls_elem_size(s->dtype);
   if (!s->b_dev || s->b_dev->len != b_len) {
@@ -1317,6 +1367,7 @@ extern "C" int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_hos
   RLS_CHECK_ARG(K >= 1, "K must be >= 1");
   const int64_t blen = s->A ? s->A->m : s->n;
   RLS_CHECK_ARG(ldb >= blen && ldx >= s->n, "leading dimensions too small");
+  RlsNvtxRange nvtx("rls: solve! (multi-RHS)");
   RlsDeviceGuard g(s->ctx->device);
   const size_t es = rls_elem_size(s->dtype);
   // RLS_TRACE_BATCH=1: wall time of the phases (with a stream sync at every phase boundary)
@@ -1353,13 +1404,29 @@ extern "C" int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_hos
     if (status != RLS_OK) break;
     const auto t2 = now();
     const int cap = iteration_cap(s->desc, s->n);
-    // one apply per iteration (FISTA / POGM / OptISTA / CGNR): the K applies of a batched iteration go through
-    // rls_normal_apply_batch_raw — two tensor-core GEMMs reading A once each when A is row-major — between the
-    // per-column pre and post kernels.  ADMM (1 + n_cg applies with data-dependent gates) keeps the per-column loop.
-    const bool split = K > 1 && !admm_like(s->desc.kind);
+    // the K applies of a batched iteration go through rls_normal_apply_batch_raw — two tensor-core GEMMs reading A once
+    // each when A is row-major — between the per-column pre and post kernels: one apply per iteration for FISTA / POGM /
+    // OptISTA / CGNR, 1 + n_cg (+1) applies with per-column device gates for ADMM / SplitBregman.
+    const bool split = K > 1;
     for (int it = 0; it < cap && status == RLS_OK; ++it) {
       if (!split) {
         for (int k = 0; k < K && status == RLS_OK; ++k) status = enqueue_iteration(s, s->lanes[k]);
+        continue;
+      }
+      if (admm_like(s->desc.kind)) {
+        // segment by segment: the K pending applies of a segment (AHA x, or AHA u of one inner CG step, each with its
+        // column's device gate) run as one batched apply
+        const int nseg = admm_segment_count(s->desc);
+        for (int seg = 0; seg < nseg && status == RLS_OK; ++seg) {
+          s->batch_x.clear(); s->batch_res.clear(); s->batch_gate.clear();
+          for (int k = 0; k < K && status == RLS_OK; ++k) {
+            PendingApply pa{nullptr, nullptr, nullptr};
+            status = s->dtype == RLS_C32 ? admm_segment<float2>(s, s->lanes[k], seg, &pa) : admm_segment<float>(s, s->lanes[k], seg, &pa);
+            if (pa.x) { s->batch_x.push_back(pa.x); s->batch_res.push_back(pa.out); s->batch_gate.push_back(pa.gate); }
+          }
+          if (status == RLS_OK && !s->batch_x.empty())
+            status = rls_normal_apply_batch_raw(s->AHA, K, s->batch_x.data(), s->batch_res.data(), s->batch_gate.data());
+        }
         continue;
       }
       s->batch_x.clear(); s->batch_res.clear(); s->batch_gate.clear();

@@ -1,11 +1,14 @@
 """Per-iterate parity of the CUDA solvers against the oracle (rel-L2 <= 1e-5, Float32 /
 ComplexF32 — the tolerance BASELINE.json's north_star states), identical iteration counts
-and stopping decisions, through the C ABI."""
+and stopping decisions, through the C ABI.  No tolerance above 1e-5 is used against the Float32 oracle: where an iterate
+can exceed it because of the oracle's own Float32 BLAS rounding (CG-steered solvers, long accelerated runs), the test
+carries a Float64 run of the oracle and the iterate must be as close to it as the Float32 oracle is
+(util.stepwise_vs_fp64 / assert_close_or_fp64)."""
 import numpy as np
 import pytest
 
 import oracle as O
-from util import rel, rand_matrix, rand_vector, sparse_truth
+from util import rel, rand_matrix, rand_vector, sparse_truth, up64, to64, stepwise_vs_fp64, assert_close_or_fp64
 
 pytestmark = pytest.mark.gpu
 
@@ -68,9 +71,9 @@ def test_fista_forms_whole_solve(rls, ctx, dtype, form):
     x = rls.solve_(S, b)
     xr = R.solve(b)
     assert S.iteration == R.iteration == 100
-    # 100 thresholded iterations amplify the summation-order rounding of x0 = A'b (1e-7) about a hundredfold;
-    # the per-iterate bound 1e-5 is checked by the stepwise tests, the end-to-end bound here is 2e-5
-    assert rel(x, xr) < 2 * TOL
+    # 100 thresholded iterations amplify the summation-order rounding of x0 = A'b (1e-7) about a hundredfold
+    assert_close_or_fp64(x, xr, lambda: O.FISTA(up64(A), reg=O.L1Regularization(float(lam)), iterations=100, rho=float(rho),
+                                                  relTol=0.0).solve(up64(b)), what="100 iterations")
     assert abs(S.state.rel_res_norm - R.rel_res_norm) <= 1e-4 * abs(R.rel_res_norm)
     # whole-solve fast path == init!/iterate loop with a callback
     trace = []
@@ -86,8 +89,8 @@ def test_cgnr_per_iterate(rls, ctx, dtype, lam):
     regs = lambda M: M.L2Regularization(lam)
     S = rls.CGNR(A, reg=regs(rls), iterations=30, relTol=0.0, normal="twopass")
     R = O.CGNR(A, reg=regs(O), iterations=30, relTol=0.0)
-    stepwise(S, R, b, 30, tol=5e-5)          # CG steering scalars amplify rounding (SURVEY 7 hard part 2)
-    assert rel(S.x, R.x) < 5e-5
+    R64 = O.CGNR(up64(A), reg=to64(regs(O)), iterations=30, relTol=0.0)
+    stepwise_vs_fp64(S, R, R64, b, 30)       # CG steering scalars amplify rounding (SURVEY 7 hard part 2)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -106,13 +109,11 @@ def test_cgnr_c1_shape_and_stop(rls, ctx, dtype):
     b = (A @ xt).astype(dtype)
     S = rls.CGNR(A, reg=rls.L2Regularization(lam), iterations=50, relTol=0.0)
     R = O.CGNR(A, reg=O.L2Regularization(lam), iterations=50, relTol=0.0)
-    S.init_(b); R.init(b)
-    for k in range(2):
-        assert S.iterate() and R.iterate()
-        assert rel(S.x, R.x) < 5e-4, f"iterate {k + 1}"
+    R64 = O.CGNR(up64(A), reg=O.L2Regularization(float(lam)), iterations=50, relTol=0.0)
+    stepwise_vs_fp64(S, R, R64, b, 50)
     x = rls.solve_(S, b)
-    assert S.iteration == 50
-    assert rel(A @ x, b) < 1e-3
+    assert S.iteration == R.iteration
+    assert rel(A @ x, b) <= max(1e-3, 2 * rel(A @ R.x, b))
     # (b) centred entries: stopping decision and solution
     Ac = (A - (0.5 + 0.5j if np.dtype(dtype).kind == "c" else 0.5)).astype(dtype)
     b = (Ac @ xt).astype(dtype)
@@ -121,10 +122,12 @@ def test_cgnr_c1_shape_and_stop(rls, ctx, dtype):
     x = rls.solve_(S, b); xr = R.solve(b)
     assert 0 < R.iteration < 50
     assert S.iteration == R.iteration, "identical iteration counts / stopping decisions"
-    assert rel(x, xr) < 2e-5
+    assert_close_or_fp64(x, xr, lambda: O.CGNR(up64(Ac), reg=O.L2Regularization(float(lam)), iterations=R.iteration,
+                                               relTol=0.0).solve(up64(b)), what="centred system")
     S = rls.CGNR(Ac, reg=rls.L2Regularization(lam), iterations=8, relTol=0.0)
     R = O.CGNR(Ac, reg=O.L2Regularization(lam), iterations=8, relTol=0.0)
-    stepwise(S, R, b, 8, tol=5e-5)
+    R64 = O.CGNR(up64(Ac), reg=O.L2Regularization(float(lam)), iterations=8, relTol=0.0)
+    stepwise_vs_fp64(S, R, R64, b, 8)
     # (c) iteration cap min(iterations, n) (CGNR.jl:185) and projections at termination only
     S = rls.CGNR(A[:, :8].copy(), reg=[rls.L2Regularization(lam), rls.PositiveRegularization()], iterations=50, relTol=0.0)
     R = O.CGNR(A[:, :8].copy(), reg=[O.L2Regularization(lam), O.PositiveRegularization()], iterations=50, relTol=0.0)
@@ -164,8 +167,8 @@ def test_proxgrad_other_regs(rls, ctx, solver, regname):
           "TV": lambda M: M.TVRegularization(np.float32(5e-3), shape=(32, 24))}[regname]
     S = getattr(rls, solver)(A, reg=mk(rls), iterations=25, rho=rho, relTol=0.0, normal="twopass")
     R = getattr(O, solver)(A, reg=mk(O), iterations=25, rho=rho, relTol=0.0)
-    what = "x"
-    stepwise(S, R, b, 25, what=what, tol=2e-5)
+    R64 = getattr(O, solver)(up64(A), reg=to64(mk(O)), iterations=25, rho=float(rho), relTol=0.0)
+    stepwise_vs_fp64(S, R, R64, b, 25)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -192,16 +195,15 @@ def test_admm(rls, ctx, dtype, variant):
     k1.update(mk(rls)); k2.update(mk(O))
     S = rls.ADMM(A, normal="twopass", **k1)
     R = O.ADMM(A, **k2)
-    S.init_(b); R.init(b)
-    for k in range(15):
-        a1, a2 = S.iterate(), R.iterate()
-        assert a1 == a2 == True
+    R64 = O.ADMM(up64(A), **to64(k2))
+
+    def each(k):
         assert S._scalars.cg_iterations_last == R.cg_iters[-1], f"inner CG count differs at outer {k}"
-        assert rel(S.x, R.x) < 5e-5, f"outer {k}"
+    stepwise_vs_fp64(S, R, R64, b, 15, each=each)
+    assert S.iteration == 15
     conv = S.convergence()
     assert np.allclose(conv["primal"], R.rk, rtol=2e-3)
     assert np.allclose(conv["dual"], R.sk, rtol=2e-3)
-    assert S.iterate() is False and R.iterate() is False
 
 
 def test_admm_docstring_kat_float32(rls, ctx):
@@ -217,12 +219,13 @@ def test_admm_docstring_kat_float32(rls, ctx):
 
 
 @pytest.mark.parametrize("solver", ["FISTA", "CGNR", "ADMM", "POGM", "OptISTA", "SplitBregman"])
-@pytest.mark.parametrize("tensor_cores", [True, False])
-def test_multi_rhs(rls, ctx, solver, tensor_cores, monkeypatch):
+@pytest.mark.parametrize("tensor_cores,layout", [(True, "row"), (True, "col"), (False, "row")])
+def test_multi_rhs(rls, ctx, solver, tensor_cores, layout, monkeypatch):
     """test/testMultiThreading.jl: batched == sequential, and a vector solve still works afterwards.
-    With the tensor-core GEMM path (two tcgen05 GEMMs per batched iteration instead of K applies) the columns
-    agree with the sequential solves to the per-iterate parity bound; with RLS_BATCH_TENSOR_CORES=0 (K single
-    applies) they are bit-identical."""
+    On a row-major A the K applies of a batched iteration (for ADMM / SplitBregman: of every segment — AHA x and each
+    inner CG step, with the per-column device gates) are two tcgen05 GEMMs; the columns then agree with the sequential
+    solves to the per-iterate parity bound.  With RLS_BATCH_TENSOR_CORES=0 or a column-major A (K single applies) they are
+    bit-identical."""
     monkeypatch.setenv("RLS_BATCH_TENSOR_CORES", "1" if tensor_cores else "0")
     monkeypatch.setenv("RLS_BATCH_MIN_K", "2")      # the GEMM path normally starts at 8 columns
     dtype = np.complex64
@@ -230,17 +233,32 @@ def test_multi_rhs(rls, ctx, solver, tensor_cores, monkeypatch):
     X = np.stack([sparse_truth(dtype, 96, 300 + k, every=7) for k in range(5)], axis=1)
     B = (A @ X).astype(dtype)
     kw = dict(iterations=30)
+    okw = dict(iterations=30)
     if solver in ("FISTA", "POGM", "OptISTA"):
         kw.update(rho=rho_for(A), reg=rls.L1Regularization(np.float32(1e-4)))
+        okw.update(rho=rho_for(A), reg=O.L1Regularization(np.float32(1e-4)))
     if solver == "SplitBregman":
         kw.update(iterations=3, iterationsInner=5)
-    S = rls.createLinearSolver(getattr(rls, solver), A, **kw)
+        okw.update(iterations=3, iterationsInner=5)
+    Ad = rls.B200Matrix.from_numpy(A, ctx, layout=layout)
+    S = rls.createLinearSolver(getattr(rls, solver), Ad, **kw)
     Xb = rls.solve_(S, B)
     Xs = np.stack([rls.solve_(S, B[:, k].copy()) for k in range(5)], axis=1)
-    if tensor_cores and solver not in ("ADMM", "SplitBregman"):
-        tol = 5e-5 if solver == "CGNR" else TOL
-        assert max(rel(Xb[:, k], Xs[:, k]) for k in range(5)) < tol
-        assert S.batch_iterations == [S.iteration] * 5 or solver == "CGNR"
+    if tensor_cores and layout == "row":
+        assert not np.array_equal(Xb, Xs), "the batched solve was meant to take the tensor-core GEMM path"
+        for k in range(5):
+            e = rel(Xb[:, k], Xs[:, k])
+            if e < TOL:
+                continue
+            # CG-steered solvers amplify the GEMM's summation order: the batched column must then be at least as close
+            # to the Float64 recurrence as the reference's own Float32 arithmetic is
+            assert solver in ("CGNR", "ADMM", "SplitBregman"), (solver, k, e)
+            x32 = getattr(O, solver)(A, **okw).solve(B[:, k].copy())
+            okw64 = {kk: (float(v) if isinstance(v, np.floating) else v) for kk, v in okw.items()}
+            x64 = getattr(O, solver)(up64(A), **okw64).solve(up64(B[:, k]))
+            assert rel(Xb[:, k], x64) <= rel(x32, x64), (solver, k, e, rel(Xb[:, k], x64), rel(x32, x64))
+        if solver in ("FISTA", "POGM", "OptISTA"):
+            assert S.batch_iterations == [S.iteration] * 5
     else:
         assert np.array_equal(Xb, Xs)
     xv = rls.solve_(S, B[:, 0].copy())
@@ -261,7 +279,8 @@ def test_measurement_based_normalization(rls, ctx):
         S = getattr(rls, name)(A, iterations=20, normalizeReg=rls.MeasurementBasedNormalization(), **kw1)
         R = getattr(O, name)(A, iterations=20, normalizeReg=O.MeasurementBasedNormalization(), **kw2)
         x = rls.solve_(S, b); xr = R.solve(b)
-        assert rel(x, xr) < 5e-5, name
+        assert_close_or_fp64(x, xr, lambda: getattr(O, name)(up64(A), iterations=20, normalizeReg=O.MeasurementBasedNormalization(),
+                                                             **to64(kw2)).solve(up64(b)), what=name)
     S = rls.FISTA(A, iterations=20, rho=rho, reg=rls.L1Regularization(np.float32(1e-2)),
                   normalizeReg=rls.SystemMatrixBasedNormalization())
     R = O.FISTA(A, iterations=20, rho=rho, reg=O.L1Regularization(np.float32(1e-2)),
@@ -286,7 +305,9 @@ def test_measurement_based_normalization_non_elementwise_prox(rls, ctx, solver, 
     for scale in (1.0, 37.0, 0.02):            # the factor ‖A'b‖₁/n changes from solve to solve
         bs = (b * np.float32(scale)).astype(dtype)
         x = rls.solve_(S, bs); xr = R.solve(bs)
-        assert rel(x, xr) < 2e-5, (solver, regname, scale)
+        assert_close_or_fp64(x, xr, lambda: getattr(O, solver)(up64(A), iterations=15, rho=float(rho), relTol=0.0, reg=to64(mk(O)),
+                                                               normalizeReg=O.MeasurementBasedNormalization()).solve(up64(bs)),
+                             what=f"{solver} {regname} scale {scale}")
 
 
 def test_power_iterations_and_default_rho(rls, ctx):
@@ -366,12 +387,13 @@ def test_row_major_per_iterate(rls, ctx, dtype, solver, kw):
     if solver == "CGNR":
         S = rls.CGNR(Ad, reg=rls.L2Regularization(np.float32(1e-3)), iterations=20, relTol=0.0)
         R = O.CGNR(A, reg=O.L2Regularization(np.float32(1e-3)), iterations=20, relTol=0.0)
-        stepwise(S, R, b, 20, tol=5e-5)
+        R64 = O.CGNR(up64(A), reg=O.L2Regularization(float(np.float32(1e-3))), iterations=20, relTol=0.0)
+        stepwise_vs_fp64(S, R, R64, b, 20)
         return
     rho = rho_for(A)
     lam = np.float32(2e-2)
     S = getattr(rls, solver)(Ad, reg=rls.L1Regularization(lam), iterations=40, rho=rho, relTol=0.0, **kw)
-    assert S.AHA.form == "onepass" and "rowmajor" in S.AHA.describe()
+    assert S.AHA.form == "onepass" and "rowstream" in S.AHA.describe()
     R = getattr(O, solver)(A, reg=O.L1Regularization(lam), iterations=40, rho=rho, relTol=0.0, **kw)
     stepwise(S, R, b, 40)
 
@@ -389,7 +411,8 @@ def test_row_major_fista_split_epilogue_and_projections(rls, ctx, regname, monke
           "L1+Positive": lambda M: [M.L1Regularization(np.float32(1e-2)), M.PositiveRegularization()]}[regname]
     S = rls.FISTA(Ad, reg=mk(rls), iterations=25, rho=rho, relTol=0.0, restart="gradient")
     R = O.FISTA(A, reg=mk(O), iterations=25, rho=rho, relTol=0.0, restart="gradient")
-    stepwise(S, R, b, 25, tol=2e-5)
+    R64 = O.FISTA(up64(A), reg=to64(mk(O)), iterations=25, rho=float(rho), relTol=0.0, restart="gradient")
+    stepwise_vs_fp64(S, R, R64, b, 25)
     x_fused = rls.solve_(S, b)
     monkeypatch.setenv("RLS_FUSE_ITERATION", "0")
     x_chain = rls.solve_(S, b)
@@ -421,23 +444,31 @@ def test_split_bregman(rls, ctx, dtype, case):
         mk = lambda M: dict(reg=M.L21Regularization(np.float32(5e-3), slices=8))
     S = rls.SplitBregman(A, **mk(rls), **kw)
     R = O.SplitBregman(A, **mk(O), **kw)
-    S.init_(b); R.init(b)
+    R64 = O.SplitBregman(up64(A), **to64(mk(O)), **to64(kw))
+    S.init_(b); R.init(b); R64.init(up64(b))
     steps = 0
     while True:
         a1, a2 = S.iterate(), R.iterate()
+        a3 = R64.iterate()
         assert a1 == a2, f"stopping decision differs after {steps} iterations: gpu={a1} oracle={a2}"
         if not a1:
             break
         steps += 1
         assert S.iteration == R.iteration and S.iter_cnt == R.iter_cnt, (steps, S.iteration, R.iteration, S.iter_cnt, R.iter_cnt)
-        assert rel(S.x, R.x) < 5e-5, f"iteration {steps}: rel-L2 {rel(S.x, R.x):.3e}"
+        # the Float64 run is only a yardstick while it walks the same path (same inner / outer counters)
+        if a3 and R64.iteration == R.iteration and R64.iter_cnt == R.iter_cnt:
+            assert_close_or_fp64(S.x, R.x, lambda: R64.x, what=f"iteration {steps}")
+        else:
+            assert rel(S.x, R.x) < TOL, f"iteration {steps}: rel-L2 {rel(S.x, R.x):.3e}"
         assert S._scalars.cg_iterations_last == R.cg_iters[-1]
     assert steps == R.total_iterations and steps > 0
     if case == "l1_stops_early":
         assert steps < 4 * 25
-    # whole-solve fast path (iterations enqueued back to back, device-side gating of the Bregman updates)
+    # whole-solve fast path (iterations enqueued back to back, device-side gating of the Bregman updates): the same
+    # kernels in the same order as the init!/iterate loop above
+    x_step = S.x.copy()
     x = rls.solve_(S, b)
-    assert rel(x, O.solve_(R, b)) < 5e-5
+    assert np.array_equal(x, x_step)
     assert S.iter_cnt == R.iter_cnt
 
 
