@@ -249,8 +249,8 @@ def run_b200(args):
             solo = rls.B200Context(local)                      # second context on the same GPU, no communicator
             Af = rls.B200Matrix.philox(dt, TWIN_M, N_COLS, seed=SEED + 1, scale=sc, ctx=solo)
             bf = np.concatenate(parts)
-            x1_f = rls.solve_(rls.FISTA(Af, reg=rls.L1Regularization(LAMBDA), iterations=20, rho=rho_t, relTol=0.0), bf)
-            x1_c = rls.solve_(rls.CGNR(Af, reg=rls.L2Regularization(LAMBDA), iterations=10, relTol=0.0), bf)
+            x1_f = rls.solve_(rls.FISTA(Af, reg=rls.L1Regularization(LAMBDA), iterations=20, rho=rho_t, relTol=0.0, ctx=solo), bf)
+            x1_c = rls.solve_(rls.CGNR(Af, reg=rls.L2Regularization(LAMBDA), iterations=10, relTol=0.0, ctx=solo), bf)
             rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
             parity = {"twin": f"{TWIN_M}x{N_COLS} ComplexF32, row-sharded over {world} GPUs vs the same system on one GPU",
                       "fista_l1_20_iterations_rel_l2": rel(xs_f, x1_f), "cgnr_10_iterations_rel_l2": rel(xs_c, x1_c), "tolerance": 1e-5}

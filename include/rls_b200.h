@@ -157,6 +157,10 @@ int32_t rls_mat_layout(rls_mat_t A, int32_t* layout);
 int32_t rls_mat_wrap_device(rls_ctx_t ctx, int32_t dtype, int64_t m, int64_t n, void* dev, int64_t ld,
                             rls_mat_t* out);
 int32_t rls_mat_destroy(rls_mat_t A);
+/* a copy of A in the other device layout, made on the device (one tiled-transpose launch, ~2 x bytes(A) of HBM traffic):
+ * how an adopted column-major CuArray (rls_mat_wrap_device — Julia's Matrix layout, src/FISTA.jl:57 takes A as it is
+ * stored) reaches the one-pass row kernels: wrap, re-layout, drop the wrapper */
+int32_t rls_mat_relayout(rls_mat_t A, int32_t layout, rls_mat_t* out);
 int32_t rls_mat_shape(rls_mat_t A, int64_t* m, int64_t* n, int32_t* dtype);
 int32_t rls_mat_upload(rls_mat_t A, const void* host, int64_t ld);
 int32_t rls_mat_download(rls_mat_t A, void* host, int64_t ld);

@@ -423,6 +423,15 @@ def reg_norm(reg, x, lam=None):
 # ----------------------------------------------------------------------------
 # operators
 # ----------------------------------------------------------------------------
+def adjoint_mul(A, y):
+    """mul!(x, adjoint(A), y) = BLAS gemv('C'): A' y without materialising conj(A).  For complex A NumPy's
+    `A.conj().T @ y` first writes a conjugated copy of the whole matrix; conj(Aᵀ conj(y)) is the same sum term by term
+    (conjugation is exact) through the transposed gemv on A itself — what Julia's BLAS call does."""
+    if np.iscomplexobj(A):
+        return np.conj(A.T @ np.conj(y))
+    return A.T @ y
+
+
 class NormalOp:
     """AHA.  mode='lazy': A'(A x) as two gemv (LinearOperatorCollection.normalOperator);
     mode='gram': the materialised A'*A the reference builds by default for a dense
@@ -440,7 +449,7 @@ class NormalOp:
     def apply(self, x):
         if self.mode == "gram":
             return self.G @ x
-        return self.A.conj().T @ (self.A @ x)
+        return adjoint_mul(self.A, self.A @ x)
 
 
 def _make_normal(A, AHA, normal):
@@ -515,7 +524,7 @@ class _Base:
     def _adjoint_b(self, b):
         if self.A is None:
             return np.array(b, dtype=self.T, copy=True)
-        return (self.A.conj().T @ b).astype(self.T, copy=False)
+        return adjoint_mul(self.A, b).astype(self.T, copy=False)
 
     def solve(self, b, callbacks=None, **kw):
         """solve!(solver, b; callbacks) RegularizedLeastSquares.jl:103-117 (vector b) and

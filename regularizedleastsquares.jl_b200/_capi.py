@@ -103,6 +103,7 @@ SIGNATURES = {
     "rls_mat_layout": [_P, _PI32],
     "rls_mat_wrap_device": [_P, _I32, _I64, _I64, _P, _I64, _PP],
     "rls_mat_destroy": [_P],
+    "rls_mat_relayout": [_P, _I32, _PP],
     "rls_mat_shape": [_P, _PI64, _PI64, _PI32],
     "rls_mat_upload": [_P, _P, _I64],
     "rls_mat_download": [_P, _P, _I64],

@@ -244,6 +244,19 @@ class B200Matrix:
         capi.call("rls_mat_download", self.handle, out.ctypes.data_as(C.c_void_p), self.m)
         return out
 
+    def relayout(self, layout):
+        """A copy in the other device layout, made on the device (tiled transpose at HBM speed)."""
+        B = object.__new__(B200Matrix)
+        B.ctx, B.dtype, B.m, B.n = self.ctx, self.dtype, self.m, self.n
+        h = C.c_void_p()
+        capi.call("rls_mat_relayout", self.handle, _LAYOUTS[layout], C.byref(h))
+        B.handle = h
+        B._fin = weakref.finalize(B, capi.load().rls_mat_destroy, h)
+        lay = C.c_int32()
+        capi.call("rls_mat_layout", h, C.byref(lay))
+        B.layout = _LAYOUT_NAMES[lay.value]
+        return B
+
     def frob2(self):
         out = C.c_double()
         capi.call("rls_mat_frob2", self.handle, C.byref(out))

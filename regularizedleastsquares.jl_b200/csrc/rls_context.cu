@@ -828,3 +828,34 @@ extern "C" int32_t rls_mat_frob2(rls_mat_t A, double* out) {
   *out = s;
   return RLS_OK;
 }
+
+extern "C" int32_t rls_mat_relayout(rls_mat_t A, int32_t layout, rls_mat_t* out) {
+  RLS_CHECK_ARG(A && out, "NULL argument");
+  RLS_CHECK_ARG(layout == RLS_LAYOUT_ROWMAJOR || layout == RLS_LAYOUT_COLMAJOR, "relayout: layout must be row- or column-major");
+  rls_ctx_s* c = A->ctx;
+  RlsDeviceGuard g(c->device);
+  RlsNvtxRange nvtx("rls: device re-layout of A");
+  rls_mat_s* B = nullptr;
+  RLS_TRY(rls_mat_create_layout(c, A->dtype, A->m, A->n, nullptr, A->m, layout, &B));
+  const size_t es = rls_elem_size(A->dtype);
+  if (A->m > 0 && A->n > 0) {
+    if (B->layout == A->layout) {
+      const int64_t rows = A->layout == RLS_LAYOUT_ROWMAJOR ? A->m : A->n, width = A->layout == RLS_LAYOUT_ROWMAJOR ? A->n : A->m;
+      cudaError_t e = cudaMemcpy2DAsync(B->d, (size_t)B->ld * es, A->d, (size_t)A->ld * es, (size_t)width * es, (size_t)rows,
+                                        cudaMemcpyDeviceToDevice, c->stream);
+      if (e != cudaSuccess) { rls_mat_destroy(B); rls_set_error("relayout: %s", cudaGetErrorString(e)); return RLS_ERR_CUDA; }
+    } else if (A->layout == RLS_LAYOUT_COLMAJOR) {
+      // in(r = column j, c = row i) at j*ld + i  ->  out at i*ldB + j
+      if (A->dtype == RLS_C32) launch_transpose<float2>(c, A->d, A->ld, B->d, B->ld, A->n, A->m);
+      else launch_transpose<float>(c, A->d, A->ld, B->d, B->ld, A->n, A->m);
+    } else {
+      // in(r = row i, c = column j) at i*ld + j  ->  out at j*ldB + i
+      if (A->dtype == RLS_C32) launch_transpose<float2>(c, A->d, A->ld, B->d, B->ld, A->m, A->n);
+      else launch_transpose<float>(c, A->d, A->ld, B->d, B->ld, A->m, A->n);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { rls_mat_destroy(B); rls_set_error("relayout: %s", cudaGetErrorString(e)); return RLS_ERR_CUDA; }
+  }
+  *out = B;
+  return RLS_OK;
+}

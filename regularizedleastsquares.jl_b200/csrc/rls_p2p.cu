@@ -54,12 +54,12 @@ __global__ void __launch_bounds__(P2P_THREADS) p2p_allreduce_kernel(PeerTable pe
   const int nf4 = (nf + 3) >> 2;  // cap is a multiple of 4 and the partial buffers are padded: whole float4s
   // 1. this rank's vector
   for (int i = blockIdx.x * P2P_THREADS + threadIdx.x; i < nf4; i += gridDim.x * P2P_THREADS) {
-    float4 s = __ldcg(reinterpret_cast<const float4*>(src) + i);
-    for (int k = 1; k < nsrc; ++k) {
+    double sx = 0.0, sy = 0.0, sz = 0.0, sw = 0.0;   // Float64, index order: the same sum as rowpass_finish_kernel
+    for (int k = 0; k < nsrc; ++k) {
       const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (size_t)k * sstride) + i);
-      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      sx += (double)t.x; sy += (double)t.y; sz += (double)t.z; sw += (double)t.w;
     }
-    reinterpret_cast<float4*>(slot)[i] = s;
+    reinterpret_cast<float4*>(slot)[i] = make_float4((float)sx, (float)sy, (float)sz, (float)sw);
   }
   // 2. publish (the barrier orders the block's stores before thread 0's system-scope fence: fences are cumulative)
   __syncthreads();

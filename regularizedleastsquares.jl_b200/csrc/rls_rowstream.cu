@@ -29,6 +29,11 @@
 // the optimum: more outstanding bulk copies lower the DRAM efficiency).
 // 20 warps (5 per scheduler) leave 96 registers per thread: 2 rows x 4 float4 of A + x + g = 64.
 // Every sum has a fixed order: results are deterministic run to run and identical in all CTAs.
+// Accuracy: a thread folds up to tens of thousands of rows into its g accumulators (262144 x 65536 on one GPU: 37449 rows
+// per cluster); a plain Float32 chain of that length loses ~sqrt(rows) ulps.  Every RS_FLUSH rows the Float32 accumulators
+// are therefore flushed into a Float64 copy of the slice in shared memory (owner-thread only: no synchronisation), and
+// the per-cluster partials are added in Float64 by the finish / epilogue kernels, so g carries the rounding of a 64-term
+// Float32 sum, not of a 37449-term one.
 //
 // What did not work (profiles/r02_rowstream_design.txt): exchanging through L2 with {tag,value} words so that
 // groups need not be clusters and 144-148 SMs stream — an L2 round trip under a saturated HBM stream costs
@@ -50,6 +55,7 @@ constexpr int RS_THREADS = (RS_CW + RS_SW) * 32;
 constexpr int RS_MAXG = 16;                  // CTAs per group (G * FPE <= 32: one lane per posted word)
 constexpr int RS_NSLOT = 4;                  // exchange slots (rows in flight between the CTAs of a cluster: <= 3)
 constexpr int RS_XROW = RS_MAXG * 2;         // floats per exchange slot: [component][rank]
+constexpr int RS_FLUSH = 64;                 // rows folded into the Float32 accumulators between two flushes into Float64
 enum { RS_NORMAL = 0, RS_GEMV_N = 1, RS_GEMV_C = 2 };
 
 struct RowstreamArgs {
@@ -120,7 +126,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rowstream_kernel(RowstreamArgs 
   float* xbuf = reinterpret_cast<float*>(xbar + RS_NSLOT);                  // [RS_NSLOT][RS_XROW]  (16-byte aligned)
   float* wpart = xbuf + RS_NSLOT * RS_XROW;                                 // [2][component][16 warps] (two-stage exchange)
   float* ysm = wpart + 2 * 32;                                              // [2][2]
-  volatile int* s_abort = reinterpret_cast<volatile int*>(ysm + 2 * 2);
+  double* g2 = reinterpret_cast<double*>(ysm + 2 * 2 + 4);                   // [W] Float64 second-level accumulators (8-byte aligned)
+  volatile int* s_abort = reinterpret_cast<volatile int*>(g2 + W);
 
   const int nf_pad = (p.nf + 3) & ~3;
   const int col0 = rank * W;
@@ -160,6 +167,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rowstream_kernel(RowstreamArgs 
       const int q4 = 4 * (tid + v * RS_CT);
       valid[v] = FULL || q4 < slice;
       g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE != RS_GEMV_N && valid[v]) {
+        reinterpret_cast<double2*>(g2 + q4)[0] = make_double2(0.0, 0.0);
+        reinterpret_cast<double2*>(g2 + q4)[1] = make_double2(0.0, 0.0);
+      }
       xr[v] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (MODE != RS_GEMV_C && valid[v]) {
         const int c = col0 + q4;
@@ -188,6 +199,19 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rowstream_kernel(RowstreamArgs 
         }
       }
     }
+    // second-level accumulation: g (Float32, at most RS_FLUSH rows) -> g2 (Float64, shared memory, this thread's entries)
+    auto flush = [&]() {
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (valid[v]) {
+          double2* q = reinterpret_cast<double2*>(g2 + 4 * (tid + v * RS_CT));
+          double2 d0 = q[0], d1 = q[1];
+          d0.x += (double)g[v].x; d0.y += (double)g[v].y; d1.x += (double)g[v].z; d1.y += (double)g[v].w;
+          q[0] = d0; q[1] = d1;
+          g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    int nfold = 0;
     int s = 0;
     unsigned phase = 0;
     if (MODE == RS_GEMV_C) {
@@ -205,6 +229,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rowstream_kernel(RowstreamArgs 
         __syncwarp();
         if (lane == 0) mbar_arrive(&ebar[s]);
         if (++s == NS) { s = 0; phase ^= 1u; }
+        if (++nfold == RS_FLUSH) { flush(); nfold = 0; }
       }
     } else {
       float4 a[2][V];
@@ -250,6 +275,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rowstream_kernel(RowstreamArgs 
               const float yr = ysm[uj * 2], yi = ysm[uj * 2 + FPE - 1];
 #pragma unroll
               for (int v = 0; v < V; ++v) axpy_conj<FPE>(g[v], a[uj][v], yr, yi);
+              if (++nfold == RS_FLUSH) { flush(); nfold = 0; }
             }
           }
         }
@@ -259,7 +285,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rowstream_kernel(RowstreamArgs 
       float* out = p.gpart + (size_t)grp * p.gstride + col0;
 #pragma unroll
       for (int v = 0; v < V; ++v)
-        if (valid[v]) *reinterpret_cast<float4*>(out + 4 * (tid + v * RS_CT)) = g[v];
+        if (valid[v]) {
+          const double2* q = reinterpret_cast<const double2*>(g2 + 4 * (tid + v * RS_CT));
+          const double2 d0 = q[0], d1 = q[1];
+          *reinterpret_cast<float4*>(out + 4 * (tid + v * RS_CT)) =
+              make_float4((float)(d0.x + (double)g[v].x), (float)(d0.y + (double)g[v].y), (float)(d1.x + (double)g[v].z), (float)(d1.y + (double)g[v].w));
+        }
     }
   } else if (warp == RS_CW) {
     // =========================== service warp A ===========================
@@ -322,25 +353,25 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rowstream_kernel(RowstreamArgs 
   cluster_sync_all();  // nobody leaves while a peer may still post into its shared memory
 }
 
-// res[j] = sum over the groups of gpart[k][j], fixed order
+// res[j] = sum over the groups of gpart[k][j], fixed order, accumulated in Float64
 __global__ void __launch_bounds__(256) rowpass_finish_kernel(const float* __restrict__ gpart, int64_t gstride, int ncl, int nf,
                                                             float* __restrict__ res, const int* gate) {
   pdl_prologue();
   if (gate && *gate) return;
   const int nf4 = nf >> 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf4; i += gridDim.x * blockDim.x) {
-    float4 s = __ldcg(reinterpret_cast<const float4*>(gpart) + i);
-    for (int k = 1; k < ncl; ++k) {
+    double sx = 0.0, sy = 0.0, sz = 0.0, sw = 0.0;   // Float64: the sum of the partials adds no rounding of its own
+    for (int k = 0; k < ncl; ++k) {
       const float4 t = __ldcg(reinterpret_cast<const float4*>(gpart + (size_t)k * gstride) + i);
-      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      sx += (double)t.x; sy += (double)t.y; sz += (double)t.z; sw += (double)t.w;
     }
-    reinterpret_cast<float4*>(res)[i] = s;
+    reinterpret_cast<float4*>(res)[i] = make_float4((float)sx, (float)sy, (float)sz, (float)sw);
   }
   if (blockIdx.x == 0 && threadIdx.x < (nf & 3)) {
     const int j = (nf4 << 2) + threadIdx.x;
-    float s = 0.f;
-    for (int k = 0; k < ncl; ++k) s += __ldcg(gpart + (size_t)k * gstride + j);
-    res[j] = s;
+    double s = 0.0;
+    for (int k = 0; k < ncl; ++k) s += (double)__ldcg(gpart + (size_t)k * gstride + j);
+    res[j] = (float)s;
   }
 }
 
@@ -394,7 +425,7 @@ void rls_rowpass_plan_destroy(RowPlan* p) {
 
 static size_t rowstream_smem(int NS, int W) {
   const size_t b = (size_t)NS * W * 4 + (size_t)(2 * NS + 4 + RS_NSLOT) * 8;  // ring, barriers (even count: 16-byte aligned)
-  return b + (size_t)(RS_NSLOT * RS_XROW + 2 * 32 + 2 * 2) * 4 + 16;
+  return b + (size_t)(RS_NSLOT * RS_XROW + 2 * 32 + 2 * 2 + 4) * 4 + (size_t)W * 8 + 16;
 }
 
 int32_t rls_rowpass_plan_create(rls_ctx_s* c, rls_mat_s* A, RowPlan** out) {

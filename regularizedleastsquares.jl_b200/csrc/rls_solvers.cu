@@ -72,17 +72,17 @@ __global__ void __launch_bounds__(EB) fista_momentum_kernel(T* __restrict__ x, c
 // sum of the per-cluster partials of a deferred one-pass apply, in rowpass_finish_kernel's order
 template <typename T> __device__ __forceinline__ T sum_partials(const NormalPartials& np, int64_t i);
 template <> __device__ __forceinline__ float sum_partials<float>(const NormalPartials& np, int64_t i) {
-  float s = __ldcg(np.gpart + i);
-  for (int k = 1; k < np.ncl; ++k) s += __ldcg(np.gpart + (size_t)k * np.gstride + i);
-  return s;
+  double s = 0.0;   // Float64 accumulation, index order: bit-identical to rowpass_finish_kernel
+  for (int k = 0; k < np.ncl; ++k) s += (double)__ldcg(np.gpart + (size_t)k * np.gstride + i);
+  return (float)s;
 }
 template <> __device__ __forceinline__ float2 sum_partials<float2>(const NormalPartials& np, int64_t i) {
-  float2 s = __ldcg(reinterpret_cast<const float2*>(np.gpart) + i);
-  for (int k = 1; k < np.ncl; ++k) {
+  double sx = 0.0, sy = 0.0;
+  for (int k = 0; k < np.ncl; ++k) {
     const float2 t = __ldcg(reinterpret_cast<const float2*>(np.gpart + (size_t)k * np.gstride) + i);
-    s.x += t.x; s.y += t.y;
+    sx += (double)t.x; sy += (double)t.y;
   }
-  return s;
+  return make_float2((float)sx, (float)sy);
 }
 
 // PART 0: everything; PART 1: up to the gradient step (a non-elementwise prox follows);

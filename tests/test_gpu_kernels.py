@@ -293,3 +293,19 @@ def test_degenerate_shapes(rls, ctx, dtype, layout, shape):
             continue
         g = rls.B200NormalOp(Ad, form=form).apply(xd).to_numpy()
         assert np.allclose(g, A64.conj().T @ (A64 @ x), atol=1e-5), form
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("m,n", [(1, 1), (33, 70), (257, 1024), (100, 4099)])
+def test_device_relayout(rls, ctx, dtype, m, n):
+    """rls_mat_relayout: an adopted column-major matrix (Julia's layout) becomes the row-major layout of the one-pass
+    kernels on the device, and back — the very same entries, the very same operator results."""
+    A, _ = rand_matrix(dtype, m, n, 611)
+    Ac = rls.B200Matrix.from_numpy(A, ctx, layout="col")
+    Ar = Ac.relayout("row")
+    assert Ar.layout == "row" and np.array_equal(Ar.to_numpy(), A)
+    assert np.array_equal(Ar.relayout("col").to_numpy(), A)
+    assert np.array_equal(Ac.relayout("col").to_numpy(), A)          # same layout: a plain copy
+    x = rls.B200Vector.from_numpy(rand_vector(dtype, n, 612), ctx)
+    ref = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx, layout="row"), form="onepass").apply(x).to_numpy()
+    assert np.array_equal(rls.B200NormalOp(Ar, form="onepass").apply(x).to_numpy(), ref)

@@ -110,7 +110,9 @@ def test_cgnr_c1_shape_and_stop(rls, ctx, dtype):
     S = rls.CGNR(A, reg=rls.L2Regularization(lam), iterations=50, relTol=0.0)
     R = O.CGNR(A, reg=O.L2Regularization(lam), iterations=50, relTol=0.0)
     R64 = O.CGNR(up64(A), reg=O.L2Regularization(float(lam)), iterations=50, relTol=0.0)
-    stepwise_vs_fp64(S, R, R64, b, 50)
+    # in this chaotic regime the distance of EITHER Float32 run to the Float64 recurrence grows by an order of magnitude
+    # every few iterations: a factor 4 between the two is less than one iteration's growth
+    stepwise_vs_fp64(S, R, R64, b, 50, slack=4.0)
     x = rls.solve_(S, b)
     assert S.iteration == R.iteration
     assert rel(A @ x, b) <= max(1e-3, 2 * rel(A @ R.x, b))

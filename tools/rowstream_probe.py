@@ -103,6 +103,28 @@ if __name__ == "__main__":
         for (m, n, dt) in [(16384, 65536, np.float32), (8192, 65536, np.complex64), (16384, 16384, np.complex64), (65536, 16384, np.float32),
                            (131072, 8192, np.float32)]:
             timeit(m, n, dt)
+    if "relayout" in what:
+        # what it costs to bring a matrix into the row-major device layout: from the host (staged 64 MB column blocks +
+        # tiled transpose, PCIe-bound) and from an adopted column-major device array (rls_mat_relayout, HBM-bound)
+        m, n = 16384, 65536
+        Ac = rls.B200Matrix.philox(np.float32, m, n, seed=1, scale=1.0 / np.sqrt(m), ctx=ctx, layout="col")
+        for _ in range(2):
+            Ar = Ac.relayout("row"); del Ar
+        ctx.sync()
+        ctx.timer_start()
+        Ar = Ac.relayout("row")
+        ms = ctx.timer_stop()
+        print(f"device re-layout col -> row, Float32 {m}x{n} (4.3 GB): {ms:.3f} ms = {2 * m * n * 4 / ms / 1e6:.0f} GB/s of read+write "
+              f"= {ms / 0.582:.1f} one-pass applies", flush=True)
+        host = Ac.to_numpy()
+        del Ac
+        t0 = time.perf_counter()
+        Ah = rls.B200Matrix.from_numpy(host, ctx=ctx, layout="row")
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        print(f"host (pageable, column-major) -> device row-major, same matrix: {dt:.2f} s = {m * n * 4 / dt / 1e9:.1f} GB/s", flush=True)
+        assert np.array_equal(Ah.to_numpy()[:64], host[:64]) and np.array_equal(Ar.to_numpy()[:64], host[:64])
+        del Ah, Ar, host
     if "sustained" in what:
         sustained(16384, 65536, np.float32, 5.0, "C2 shape")
         sustained(8192, 65536, np.complex64, 5.0, "C5 shard shape")
