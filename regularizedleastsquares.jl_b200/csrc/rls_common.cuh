@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -75,6 +76,10 @@ struct rls_ctx_s {
   int64_t peer_cap = 0;
   int* peer_abort = nullptr;
   bool peer_ready = false;
+  // Handles are freed by garbage collectors (Julia finalizers, Python weakrefs) in ARBITRARY order: every object that
+  // points to a context / matrix / operator holds a reference, and rls_*_destroy only drops the caller's one — the
+  // memory goes when the last holder has gone.
+  std::atomic<int> refs{1};
 };
 
 struct rls_vec_s {
@@ -93,6 +98,7 @@ struct rls_mat_s {
   bool owned;
   int32_t layout = RLS_LAYOUT_COLMAJOR;
   struct RowPlan* rowplan = nullptr;  // row-major matrices: kernel plan shared by gemv / normal operator
+  std::atomic<int> refs{1};           // the creator + every operator / solver built on it
 };
 
 static inline size_t rls_elem_size(int32_t dtype) { return dtype == RLS_C32 ? 8 : 4; }
@@ -120,6 +126,12 @@ struct RlsDeviceGuard {
   int target = -1;
 };
 
+void rls_ctx_retain(rls_ctx_s* c);
+void rls_ctx_release(rls_ctx_s* c);     // frees the context when the last reference goes
+void rls_mat_retain(rls_mat_s* A);
+void rls_mat_release(rls_mat_s* A);
+void rls_normal_retain(rls_normal_t op);
+void rls_normal_release(rls_normal_t op);
 int32_t rls_ensure_gemv_scratch(rls_ctx_s* ctx, size_t bytes);
 // diagnostic switches read from the environment (re-read on every call: tests flip them between solves; a getenv
 // costs ~100 ns against >= 0.3 ms per normal-operator apply)

@@ -144,8 +144,15 @@ extern "C" int32_t rls_ctx_create(int32_t device, rls_ctx_t* out) {
 typedef int (*nccl_destroy_fn)(void*);
 static void* g_nccl_lib = nullptr;
 
+void rls_ctx_retain(rls_ctx_s* c) { if (c) c->refs.fetch_add(1); }
+
 extern "C" int32_t rls_ctx_destroy(rls_ctx_t c) {
   if (!c) return RLS_OK;
+  rls_ctx_release(c);   // vectors / matrices / operators / solvers still alive keep the context until they go
+  return RLS_OK;
+}
+
+static int32_t ctx_free(rls_ctx_s* c) {
   RlsDeviceGuard g(c->device);
   rls_ctx_peer_release(c);
   cudaStreamSynchronize(c->stream);
@@ -165,6 +172,10 @@ extern "C" int32_t rls_ctx_destroy(rls_ctx_t c) {
   cudaStreamDestroy(c->stream);
   delete c;
   return RLS_OK;
+}
+
+void rls_ctx_release(rls_ctx_s* c) {
+  if (c && c->refs.fetch_sub(1) == 1) ctx_free(c);
 }
 
 extern "C" int32_t rls_ctx_sync(rls_ctx_t c) {
@@ -369,6 +380,7 @@ int32_t rls_vec_create_internal(rls_ctx_s* ctx, int32_t dtype, int64_t len, rls_
     return RLS_ERR_NOMEM;
   }
   cudaMemsetAsync(v->d, 0, bytes, ctx->stream);
+  rls_ctx_retain(ctx);
   *out = v;
   return RLS_OK;
 }
@@ -384,7 +396,9 @@ extern "C" int32_t rls_vec_destroy(rls_vec_t v) {
     cudaStreamSynchronize(v->ctx->stream);
     cudaFree(v->d);
   }
+  rls_ctx_s* c = v->ctx;
   delete v;
+  rls_ctx_release(c);
   return RLS_OK;
 }
 
@@ -641,11 +655,13 @@ extern "C" int32_t rls_mat_create_layout(rls_ctx_t ctx, int32_t dtype, int64_t m
   int64_t dld = ((fast + vec - 1) / vec) * vec;
   if (dld == 0) dld = vec;
   rls_mat_s* A = new rls_mat_s{ctx, dtype, m, n, dld, nullptr, true};
+  rls_ctx_retain(ctx);
   A->layout = layout;
   size_t bytes = (size_t)dld * (size_t)(slow > 0 ? slow : 1) * rls_elem_size(dtype);
   cudaError_t e = cudaMalloc(&A->d, bytes);
   if (e != cudaSuccess) {
     delete A;
+    rls_ctx_release(ctx);
     rls_set_error("cudaMalloc(%zu) for %lldx%lld matrix failed: %s", bytes, (long long)m, (long long)n, cudaGetErrorString(e));
     return RLS_ERR_NOMEM;
   }
@@ -685,16 +701,27 @@ extern "C" int32_t rls_mat_wrap_device(rls_ctx_t ctx, int32_t dtype, int64_t m, 
   RLS_CHECK_ARG(dtype == RLS_F32 || dtype == RLS_C32, "unsupported dtype %d", dtype);
   RLS_CHECK_ARG(m >= 0 && n >= 0 && ld >= m, "bad shape");
   *out = new rls_mat_s{ctx, dtype, m, n, ld, dev, false};
+  rls_ctx_retain(ctx);
   return RLS_OK;
 }
 
+void rls_mat_retain(rls_mat_s* A) { if (A) A->refs.fetch_add(1); }
+
+void rls_mat_release(rls_mat_s* A) {
+  if (!A || A->refs.fetch_sub(1) != 1) return;
+  rls_ctx_s* c = A->ctx;
+  {
+    RlsDeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (A->rowplan) rls_rowpass_plan_destroy(A->rowplan);
+    if (A->owned && A->d) cudaFree(A->d);
+    delete A;
+  }
+  rls_ctx_release(c);
+}
+
 extern "C" int32_t rls_mat_destroy(rls_mat_t A) {
-  if (!A) return RLS_OK;
-  RlsDeviceGuard g(A->ctx->device);
-  cudaStreamSynchronize(A->ctx->stream);
-  if (A->rowplan) rls_rowpass_plan_destroy(A->rowplan);
-  if (A->owned && A->d) cudaFree(A->d);
-  delete A;
+  rls_mat_release(A);   // operators / solvers built on A keep it until they go
   return RLS_OK;
 }
 

@@ -864,7 +864,11 @@ void kz_free(rls_kaczmarz_s* K) {
   if (K->x) rls_vec_destroy(K->x);
   if (K->vl) rls_vec_destroy(K->vl);
   if (K->u) rls_vec_destroy(K->u);
+  rls_ctx_s* c = K->ctx;
+  rls_mat_s* A = K->A;
   delete K;
+  rls_mat_release(A);   // taken in rls_kaczmarz_create: handles are freed by garbage collectors in arbitrary order
+  rls_ctx_release(c);
 }
 
 }  // namespace
@@ -951,6 +955,8 @@ extern "C" int32_t rls_kaczmarz_create(rls_mat_t A, int32_t block_rows, rls_kacz
   RLS_CHECK_ARG(R == 64 || R == 128 || R == 192 || R == 256, "Kaczmarz: block_rows must be 64, 128, 192 or 256 (got %d)", R);
   rls_kaczmarz_s* K = new rls_kaczmarz_s();
   K->ctx = c; K->A = A; K->fpe = fpe; K->R = R;
+  rls_ctx_retain(c);
+  rls_mat_retain(A);
   const int64_t nfl = A->n * fpe, ldf = A->ld * fpe;
   K->vec4 = (nfl % 4 == 0) && (ldf % 4 == 0) && (((uintptr_t)A->d) % 16 == 0);
   const int nf = K->vec4 ? 4 : fpe;

@@ -351,6 +351,7 @@ struct rls_normal_s {
   void* ws_mem = nullptr;
   int op_grid = 0, op_lpc = 0, op_maxc = 0, op_cpw = 0, op_lag = 2, op_hint = 1;
   unsigned tag_next = 1;
+  std::atomic<int> refs{1};   // the creator + every solver that borrows the operator
 };
 
 typedef void (*onepass_fn)(OnepassArgs);
@@ -515,6 +516,8 @@ extern "C" int32_t rls_normal_create(rls_mat_t A, int32_t form, rls_normal_t* ou
     }
   }
   op->form = form;
+  rls_mat_retain(A);          // from here on rls_normal_destroy / release undoes everything
+  rls_ctx_retain(op->ctx);
   if (form == RLS_NORMAL_GRAM) {
     int32_t s = build_gram(op);
     if (s != RLS_OK) { rls_normal_destroy(op); return s; }
@@ -526,17 +529,31 @@ extern "C" int32_t rls_normal_create(rls_mat_t A, int32_t form, rls_normal_t* ou
   return RLS_OK;
 }
 
+void rls_normal_retain(rls_normal_t op) { if (op) op->refs.fetch_add(1); }
+
+void rls_normal_release(rls_normal_t op) {
+  if (!op || op->refs.fetch_sub(1) != 1) return;
+  rls_ctx_s* c = op->ctx;
+  rls_mat_s* A = op->A;
+  rls_mat_s* Gborrowed = (op->G && !op->own_G) ? op->G : nullptr;
+  {
+    RlsDeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (op->ytmp) rls_vec_destroy(op->ytmp);
+    if (op->gpart) rls_vec_destroy(op->gpart);
+    if (op->G && op->own_G) rls_mat_destroy(op->G);
+    if (op->ws_mem) cudaFree(op->ws_mem);
+    if (op->tma) rls_tma_plan_destroy(op->tma);
+    if (op->tc) rls_tc_batch_destroy(op->tc);
+    delete op;
+  }
+  rls_mat_release(A);
+  rls_mat_release(Gborrowed);
+  rls_ctx_release(c);
+}
+
 extern "C" int32_t rls_normal_destroy(rls_normal_t op) {
-  if (!op) return RLS_OK;
-  RlsDeviceGuard g(op->ctx->device);
-  cudaStreamSynchronize(op->ctx->stream);
-  if (op->ytmp) rls_vec_destroy(op->ytmp);
-  if (op->gpart) rls_vec_destroy(op->gpart);
-  if (op->G && op->own_G) rls_mat_destroy(op->G);
-  if (op->ws_mem) cudaFree(op->ws_mem);
-  if (op->tma) rls_tma_plan_destroy(op->tma);
-  if (op->tc) rls_tc_batch_destroy(op->tc);
-  delete op;
+  rls_normal_release(op);   // solvers that borrow the operator keep it until they go
   return RLS_OK;
 }
 
@@ -575,6 +592,8 @@ extern "C" int32_t rls_normal_from_gram(rls_mat_t G, rls_normal_t* out) {
   op->form = RLS_NORMAL_GRAM;
   op->n_ = G->n;
   op->dtype_ = G->dtype;
+  rls_mat_retain(G);
+  rls_ctx_retain(op->ctx);
   *out = op;
   return RLS_OK;
 }

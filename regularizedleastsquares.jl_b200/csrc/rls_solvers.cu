@@ -1119,6 +1119,10 @@ extern "C" int32_t rls_solver_create(rls_mat_t A, rls_normal_t AHA, const rls_so
     if (st != RLS_OK) { delete s; return st; }
     s->own_AHA = true;
   }
+  // the solver keeps what it points to alive: handles are freed by garbage collectors in arbitrary order
+  rls_ctx_retain(ctx);
+  rls_mat_retain(A);
+  if (!s->own_AHA) rls_normal_retain(s->AHA);
   rls_normal_shape(s->AHA, &s->n, &s->dtype);
   if (A && (A->n != s->n || A->dtype != s->dtype)) {
     rls_solver_destroy(s);
@@ -1156,8 +1160,12 @@ extern "C" int32_t rls_solver_destroy(rls_solver_t s) {
   if (s->b_dev) rls_vec_destroy(s->b_dev);
   if (s->pin_b) cudaFreeHost(s->pin_b);
   if (s->pin_x) cudaFreeHost(s->pin_x);
-  if (s->own_AHA && s->AHA) rls_normal_destroy(s->AHA);
+  rls_ctx_s* c = s->ctx;
+  rls_mat_s* A = s->A;
+  rls_normal_release(s->AHA);   // own or borrowed: one reference either way
   delete s;
+  rls_mat_release(A);
+  rls_ctx_release(c);
   return RLS_OK;
 }
 

@@ -309,3 +309,26 @@ def test_device_relayout(rls, ctx, dtype, m, n):
     x = rls.B200Vector.from_numpy(rand_vector(dtype, n, 612), ctx)
     ref = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx, layout="row"), form="onepass").apply(x).to_numpy()
     assert np.array_equal(rls.B200NormalOp(Ar, form="onepass").apply(x).to_numpy(), ref)
+
+
+def test_handles_may_be_destroyed_in_any_order(rls):
+    """Garbage collectors (Julia finalizers, Python weakrefs) free handles in arbitrary order: the library counts
+    references, so destroying the context, the matrix and the operator BEFORE the solver that uses them is harmless —
+    the solver keeps working and the memory goes with the last holder."""
+    import oracle as O
+    c = rls.B200Context(0)
+    A, _ = rand_matrix(np.float32, 96, 160, 71)
+    b = rand_vector(np.float32, 96, 72)
+    Ad = rls.B200Matrix.from_numpy(A, c, layout="row")
+    op = rls.B200NormalOp(Ad, form="onepass")
+    S = rls.FISTA(Ad, AHA=op, reg=rls.L1Regularization(np.float32(1e-2)), iterations=10, rho=np.float32(0.05), relTol=0.0, ctx=c)
+    K = rls.Kaczmarz(Ad, reg=rls.L2Regularization(np.float32(1e-2)), iterations=2)
+    x_before = rls.solve_(S, b)
+    for obj in (c, Ad, op):          # rls_ctx_destroy, rls_mat_destroy, rls_normal_destroy — now, in the worst order
+        obj._fin()
+    x_after = rls.solve_(S, b)
+    assert np.array_equal(x_before, x_after)
+    xr = O.FISTA(A, reg=O.L1Regularization(np.float32(1e-2)), iterations=10, rho=np.float32(0.05), relTol=0.0).solve(b)
+    assert rel(x_after, xr) < 1e-5
+    assert np.all(np.isfinite(rls.solve_(K, b)))
+    S._fin(); K._fin()
