@@ -335,6 +335,30 @@ int32_t rls_kaczmarz_describe(rls_kaczmarz_t K, char* buf, int32_t len);
 /* diagnostics: 0 = block Gram matrices, 1 = dot partials of the last block, 2 = alpha of the last block, 3 = denominators */
 int32_t rls_kaczmarz_debug(rls_kaczmarz_t K, int32_t which, float* host, int64_t nfloats);
 
+/* ---- single-process multi-device ("multi-GPU handled inside one call") --------------------------------
+ * What createLinearSolver(FISTA, A; ...) + solve!(solver, b) (src/RegularizedLeastSquares.jl:288-294, :103-117) bind
+ * when the host is ONE process and the system is larger than one GPU: a group of devices with one NCCL communicator
+ * (ncclCommInitAll), a matrix row-partitioned over them, and a solve! that takes the whole b and returns x.  Inside a
+ * call one host thread per device runs the single-context entry points above (NCCL thread-per-rank). */
+typedef struct rls_group_s* rls_group_t;
+typedef struct rls_gmat_s* rls_gmat_t;
+typedef struct rls_gsolver_s* rls_gsolver_t;
+int32_t rls_group_create(int32_t ndev, const int32_t* dev_ids /* NULL: devices 0..ndev-1 */, rls_group_t* out);
+int32_t rls_group_destroy(rls_group_t g);
+int32_t rls_group_size(rls_group_t g, int32_t* ndev);
+int32_t rls_group_ctx(rls_group_t g, int32_t i, rls_ctx_t* ctx);                       /* borrowed */
+/* A (m x n): column-major host matrix (Julia Matrix), or host = NULL and rls_group_mat_fill_philox; contiguous row
+ * blocks (multiples of 4 rows), device layout chosen per block like rls_mat_create */
+int32_t rls_group_mat_create(rls_group_t g, int32_t dtype, int64_t m, int64_t n, const void* host, int64_t ld, rls_gmat_t* out);
+int32_t rls_group_mat_fill_philox(rls_gmat_t A, uint64_t seed, int32_t dist, float scale);
+int32_t rls_group_mat_part(rls_gmat_t A, int32_t i, rls_mat_t* part /* borrowed */, int64_t* row_lo, int64_t* row_hi);
+int32_t rls_group_mat_destroy(rls_gmat_t A);
+int32_t rls_group_solver_create(rls_gmat_t A, int32_t normal_form, const rls_solver_desc* desc, rls_gsolver_t* out);
+int32_t rls_group_solver_destroy(rls_gsolver_t s);
+/* solve!(solver, b): host b (m elements) in, host x (n elements) out; fails if the replicas are not bit-identical */
+int32_t rls_group_solver_solve_host(rls_gsolver_t s, const void* b_host, int64_t b_len, void* x_host, int64_t x_len,
+                                    int32_t* iterations_done, rls_solver_scalars* scalars);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ from . import _capi
 _capi.load()   # fail loudly if the CUDA library has not been built
 
 from ._capi import RlsError  # noqa: E402
-from .arrays import B200Context, B200Matrix, B200NormalOp, B200Vector  # noqa: E402
+from .arrays import B200Context, B200Group, B200GroupMatrix, B200Matrix, B200NormalOp, B200Vector  # noqa: E402
 from .regularization import (AbstractParameterizedRegularization, AbstractProjectionRegularization,  # noqa: E402
                              AbstractRegularization, GradientOp, L1Regularization, L2Regularization,
                              L21Regularization, MeasurementBasedNormalization, NoNormalization,

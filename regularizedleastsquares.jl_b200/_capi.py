@@ -86,6 +86,17 @@ SIGNATURES = {
     "rls_ctx_allreduce_f64": [_P, _PF64, _I32],
     "rls_ctx_peer_export": [_P, _I64, _P],
     "rls_ctx_peer_import": [_P, _P, _I32],
+    "rls_group_create": [_I32, _PI32, _PP],
+    "rls_group_destroy": [_P],
+    "rls_group_size": [_P, _PI32],
+    "rls_group_ctx": [_P, _I32, _PP],
+    "rls_group_mat_create": [_P, _I32, _I64, _I64, _P, _I64, _PP],
+    "rls_group_mat_fill_philox": [_P, _U64, _I32, _F32],
+    "rls_group_mat_part": [_P, _I32, _PP, _PI64, _PI64],
+    "rls_group_mat_destroy": [_P],
+    "rls_group_solver_create": [_P, _I32, C.POINTER(SolverDesc), _PP],
+    "rls_group_solver_destroy": [_P],
+    "rls_group_solver_solve_host": [_P, _P, _I64, _P, _I64, _PI32, C.POINTER(SolverScalars)],
     "rls_vec_create": [_P, _I32, _I64, _PP],
     "rls_vec_destroy": [_P],
     "rls_vec_len": [_P, _PI64, _PI32],

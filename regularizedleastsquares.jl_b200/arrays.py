@@ -325,3 +325,67 @@ class B200NormalOp:
         lam = C.c_double()
         capi.call("rls_power_iterations", self.handle, b0.handle, float(rtol), int(maxiter), C.byref(lam))
         return lam.value
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# single-process multi-device: one Python / Julia process, the system row-partitioned over a group of GPUs
+# ------------------------------------------------------------------------------------------------------------------
+class B200Group:
+    """A group of devices with one NCCL communicator (ncclCommInitAll).  `B200GroupMatrix` row-partitions A over it and
+    createLinearSolver(FISTA, A_group; ...) / solve_(solver, b) then run the row-sharded solve inside ONE call."""
+    def __init__(self, ndev=None, devices=None):
+        if devices is None:
+            if ndev is None:
+                n = C.c_int32()
+                capi.call("rls_device_count", C.byref(n))
+                ndev = n.value
+            devices = list(range(int(ndev)))
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        capi.call("rls_group_create", len(self.devices), arr, C.byref(h))
+        self.handle = h
+        self._fin = weakref.finalize(self, capi.load().rls_group_destroy, h)
+
+    def __len__(self):
+        return len(self.devices)
+
+
+class B200GroupMatrix:
+    """Dense m x n system matrix in contiguous row blocks on the devices of a group (host side: column-major, as ever)."""
+    def __init__(self, group, dtype, m, n, host=None):
+        self.group = group
+        self.dtype = np.dtype(dtype)
+        self.m, self.n = int(m), int(n)
+        ptr = None
+        if host is not None:
+            host = np.asfortranarray(host, dtype=self.dtype)
+            assert host.shape == (self.m, self.n)
+            ptr = host.ctypes.data_as(C.c_void_p)
+        h = C.c_void_p()
+        capi.call("rls_group_mat_create", group.handle, dtype_code(dtype), self.m, self.n, ptr, self.m, C.byref(h))
+        self.handle = h
+        self._fin = weakref.finalize(self, capi.load().rls_group_mat_destroy, h)
+
+    @classmethod
+    def from_numpy(cls, A, group):
+        A = np.asarray(A)
+        return cls(group, A.dtype, A.shape[0], A.shape[1], host=A)
+
+    @classmethod
+    def philox(cls, group, dtype, m, n, seed, dist=capi.RLS_DIST_IH4, scale=1.0):
+        A = cls(group, dtype, m, n)
+        capi.call("rls_group_mat_fill_philox", A.handle, int(seed), int(dist), float(scale))
+        return A
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    def row_blocks(self):
+        out = []
+        for i in range(len(self.group)):
+            lo, hi = C.c_int64(), C.c_int64()
+            capi.call("rls_group_mat_part", self.handle, i, None, C.byref(lo), C.byref(hi))
+            out.append((lo.value, hi.value))
+        return out

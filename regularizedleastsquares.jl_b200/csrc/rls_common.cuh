@@ -140,6 +140,7 @@ bool rls_env_flag(const char* name, bool dflt);
 // internal (non-ABI) helpers used across translation units
 int32_t rls_vec_create_internal(rls_ctx_s* ctx, int32_t dtype, int64_t len, rls_vec_s** out);
 int32_t rls_allreduce_raw(rls_ctx_s* ctx, void* buf, int64_t nfloats);  // float sum-allreduce in place
+int32_t rls_comm_init_all(rls_ctx_s* const* ctxs, int n);                // ncclCommInitAll over the contexts of one process
 int32_t rls_allreduce_f64_host(rls_ctx_s* c, double* vals, int n);    // host doubles, sum over ranks in place
 bool rls_p2p_available(const rls_ctx_s* c, int64_t nfloats);
 int32_t rls_p2p_allreduce(rls_ctx_s* c, const float* src, int64_t sstride, int nsrc, int64_t nf, float* res, const int* gate);

@@ -317,6 +317,23 @@ extern "C" int32_t rls_ctx_comm_init(rls_ctx_t c, int32_t rank, int32_t nranks, 
   return RLS_OK;
 }
 
+// one communicator over the contexts of ONE process (rls_group.cu): ncclCommInitAll, rank i = contexts[i]
+int32_t rls_comm_init_all(rls_ctx_s* const* ctxs, int n) {
+  RLS_TRY(load_nccl());
+  typedef int (*nccl_init_all_fn)(void**, int, const int*);
+  nccl_init_all_fn init_all = (nccl_init_all_fn)dlsym(g_nccl_lib, "ncclCommInitAll");
+  RLS_CHECK_ARG(init_all, "libnccl has no ncclCommInitAll");
+  std::vector<void*> comms(n, nullptr);
+  std::vector<int> devs(n);
+  for (int i = 0; i < n; ++i) {
+    RLS_CHECK_ARG(!ctxs[i]->nccl_comm, "communicator already initialised");
+    devs[i] = ctxs[i]->device;
+  }
+  RLS_NCCL(init_all(comms.data(), n, devs.data()));
+  for (int i = 0; i < n; ++i) { ctxs[i]->nccl_comm = comms[i]; ctxs[i]->rank = i; ctxs[i]->nranks = n; }
+  return RLS_OK;
+}
+
 extern "C" int32_t rls_ctx_comm_info(rls_ctx_t c, int32_t* rank, int32_t* nranks) {
   RLS_CHECK_ARG(c, "ctx is NULL");
   if (rank) *rank = c->rank;

@@ -26,7 +26,7 @@ import warnings
 import numpy as np
 
 from . import _capi as capi
-from .arrays import B200Context, B200Matrix, B200NormalOp, B200Vector, dtype_code
+from .arrays import B200Context, B200Group, B200GroupMatrix, B200Matrix, B200NormalOp, B200Vector, dtype_code, _FORMS
 from .regularization import (AbstractProjectionRegularization, GradientOp, L1Regularization, L2Regularization,
                              MeasurementBasedNormalization, NoNormalization, NormalizedRegularization,
                              PositiveRegularization, RealRegularization, SystemMatrixBasedNormalization, findsink,
@@ -67,9 +67,23 @@ class SolverState:
 
 class AbstractLinearSolver:
     name = ""
+    _group = False          # True: A is a B200GroupMatrix (single-process multi-device)
 
     # ---------------- construction helpers ----------------
     def _setup(self, A, AHA, normal, ctx):
+        self._group = isinstance(A, B200GroupMatrix)
+        if self._group:
+            # single-process multi-device: the C library keeps one operator + solver per device behind ONE handle
+            if AHA is not None:
+                raise NotImplementedError("a device group builds its own (lazy) normal operator; AHA cannot be supplied")
+            self.ctx, self.A, self.AHA = None, A, None
+            self._normal_form = _FORMS[normal]
+            self.dtype, self.n = A.dtype, A.n
+            self._handle = None
+            self._scalars = capi.SolverScalars()
+            self._vec_cache = {}
+            self.state = SolverState(self)
+            return
         self.ctx = ctx if ctx is not None else (A.ctx if isinstance(A, B200Matrix) else B200Context.default())
         self.A = _as_matrix(A, self.ctx)
         if AHA is None:
@@ -93,6 +107,8 @@ class AbstractLinearSolver:
         nz = self.normalizeReg
         if isinstance(nz, NoNormalization):
             return regs
+        if self._group:
+            raise NotImplementedError("normalizeReg on a device group: normalise λ on the host or use one process per GPU")
         if isinstance(nz, MeasurementBasedNormalization):
             f = np.float32(1)
         elif isinstance(nz, SystemMatrixBasedNormalization):
@@ -108,11 +124,19 @@ class AbstractLinearSolver:
         return [normalize_reg(r, f) for r in regs]
 
     def _default_rho(self):
+        if self._group:
+            raise ValueError("a solver on a device group needs an explicit rho (the default runs power iterations on one context)")
         b0 = B200Vector(self.ctx, self.dtype, self.n).fill_philox(seed=0x5EED, stream=7, dist=capi.RLS_DIST_IH4)
         return np.float32(0.95 / self.AHA.power_iterations(b0))
 
     def _create(self, desc):
         h = C.c_void_p()
+        if self._group:
+            import weakref
+            capi.call("rls_group_solver_create", self.A.handle, self._normal_form, C.byref(desc), C.byref(h))
+            self._handle, self._desc = h, desc
+            self._fin = weakref.finalize(self, capi.load().rls_group_solver_destroy, h)
+            return
         capi.call("rls_solver_create", self.A.handle if self.A is not None else None, self.AHA.handle, C.byref(desc), C.byref(h))
         import weakref
         self._handle = h
@@ -204,6 +228,15 @@ class AbstractLinearSolver:
         """solve!(solver, b; x0, callbacks): RegularizedLeastSquares.jl:103-117; a matrix b runs the
         multi-right-hand-side path of MultiThreading.jl:30-80."""
         host_in = not isinstance(b, B200Vector)
+        if self._group:
+            if not host_in or np.ndim(b) != 1 or callbacks or not (np.isscalar(x0) and x0 == 0):
+                raise NotImplementedError("a solver on a device group takes one host vector b (no callbacks, x0 = 0)")
+            bh = np.ascontiguousarray(b, dtype=self.dtype).ravel()
+            xh = np.empty(self.n, self.dtype)
+            it = C.c_int32()
+            capi.call("rls_group_solver_solve_host", self._handle, bh.ctypes.data_as(C.c_void_p), bh.size,
+                      xh.ctypes.data_as(C.c_void_p), xh.size, C.byref(it), C.byref(self._scalars))
+            return xh
         if host_in and np.ndim(b) == 2:
             return self._solve_batch(np.asarray(b))
         cbs = [] if callbacks is None else (list(callbacks) if isinstance(callbacks, (list, tuple)) else [callbacks])
@@ -666,6 +699,15 @@ class Kaczmarz(AbstractLinearSolver):
 
     def solve_(self, b, x0=0, callbacks=None, scheduler=None):
         host_in = not isinstance(b, B200Vector)
+        if self._group:
+            if not host_in or np.ndim(b) != 1 or callbacks or not (np.isscalar(x0) and x0 == 0):
+                raise NotImplementedError("a solver on a device group takes one host vector b (no callbacks, x0 = 0)")
+            bh = np.ascontiguousarray(b, dtype=self.dtype).ravel()
+            xh = np.empty(self.n, self.dtype)
+            it = C.c_int32()
+            capi.call("rls_group_solver_solve_host", self._handle, bh.ctypes.data_as(C.c_void_p), bh.size,
+                      xh.ctypes.data_as(C.c_void_p), xh.size, C.byref(it), C.byref(self._scalars))
+            return xh
         if host_in and np.ndim(b) == 2:
             return np.stack([self.solve_(np.asarray(b)[:, k], x0=x0, callbacks=callbacks) for k in range(np.shape(b)[1])], axis=1)
         cbs = [] if callbacks is None else (list(callbacks) if isinstance(callbacks, (list, tuple)) else [callbacks])
