@@ -79,9 +79,10 @@ def test_c2_full_size_fista_l1_per_iterate(rls, ctx):
     R = O.FISTA(A, reg=O.L1Regularization(lam), iterations=its, rho=rho, relTol=0.0)
     R64 = O.FISTA(up64(A), reg=O.L1Regularization(float(lam)), iterations=its, rho=float(rho), relTol=0.0)
 
-    def each(k):                                      # ‖res‖_k / ‖x₀‖ (FISTA.jl:156); res = A'Ax - A'b cancels: same criterion as for x
-        g, r32, r64 = S._scalars.rel_res_norm, float(R.rel_res_norm), float(R64.rel_res_norm)
-        assert abs(g - r32) <= 1e-4 * r32 or abs(g - r64) <= 1.5 * abs(r32 - r64) + 1e-6 * r64, (k, g, r32, r64)
+    def each(k):
+        # ‖res‖_k / ‖A'b‖ (FISTA.jl:156).  res = A'A x - A'b is a difference of vectors ~200 x its own size late in the solve,
+        # so the bound is on the error of res relative to what is subtracted, i.e. absolute in this normalised quantity
+        assert abs(S._scalars.rel_res_norm - float(R.rel_res_norm)) <= 2e-5, (k, S._scalars.rel_res_norm, float(R.rel_res_norm))
     w = stepwise_vs_fp64(S, R, R64, b, its, each=each)
     assert S.iteration == R.iteration == its
     print(f"C2: worst per-iterate over {its} iterations gpu-o32 {w[0]:.2e}, gpu-o64 {w[1]:.2e}, o32-o64 {w[2]:.2e}; "
