@@ -316,9 +316,16 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rowstream_kernel(RowstreamArgs 
             t = (((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w))) +
                 (((q2.x + q2.y) + (q2.z + q2.w)) + ((q3.x + q3.y) + (q3.z + q3.w)));
           }
-          t = __shfl_sync(0xffffffffu, t, lane % FPE);
           const int slot = i & (RS_NSLOT - 1);
-          if (lane < G * FPE) dsmem_post(&xbuf[slot * RS_XROW + (lane % FPE) * RS_MAXG + rank], &xbar[slot], (unsigned)(lane / FPE), t);
+          if (G > 1) {
+            t = __shfl_sync(0xffffffffu, t, lane % FPE);
+            if (lane < G * FPE) dsmem_post(&xbuf[slot * RS_XROW + (lane % FPE) * RS_MAXG + rank], &xbar[slot], (unsigned)(lane / FPE), t);
+          } else {
+            // a cluster of one: plain shared-memory hand-over (st.async needs a peer CTA)
+            if (lane < FPE) xbuf[slot * RS_XROW + lane * RS_MAXG] = t;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xbar[slot]);
+          }
         }
         if (lane == 0 && i + NS < Q) issue(i + NS, s);
         if (++s == NS) s = 0;
@@ -329,7 +336,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) rowstream_kernel(RowstreamArgs 
     if (MODE != RS_GEMV_C) {
       for (int r = 0; r < Q; ++r) {
         const int slot = r & (RS_NSLOT - 1), u = r & 1;
-        if (lane == 0) mbar_expect_tx(&xbar[slot], (unsigned)(G * FPE) * 4u);
+        if (G > 1 && lane == 0) mbar_expect_tx(&xbar[slot], (unsigned)(G * FPE) * 4u);   // G == 1: warp A arrives
         mbar_wait(&xbar[slot], (unsigned)(r / RS_NSLOT) & 1u, s_abort, p.abort_flag);
         float yr = 0.f;
         if (lane < FPE) {

@@ -49,7 +49,7 @@ def test_device_group_inside_one_process(ndev):
         Ag = rls.B200GroupMatrix.from_numpy(A, G)
         blocks = Ag.row_blocks()
         assert blocks[0][0] == 0 and blocks[-1][1] == m and all(blocks[i][1] == blocks[i + 1][0] for i in range(ndev - 1))
-        A1 = rls.B200Matrix.from_numpy(A, layout="row")
+        A1 = rls.B200Matrix.from_numpy(A)                    # same layout choice (AUTO) as the blocks of the group
         cases = (("FISTA", dict(reg=rls.L1Regularization(np.float32(1e-2)), iterations=30, rho=rho, relTol=0.0),
                   dict(reg=O.L1Regularization(np.float32(1e-2)), iterations=30, rho=rho, relTol=0.0)),
                  ("CGNR", dict(reg=rls.L2Regularization(np.float32(1e-2)), iterations=10, relTol=0.0),
@@ -70,7 +70,7 @@ def test_device_group_inside_one_process(ndev):
         # Philox generation per row block reproduces the global matrix
         Ap = rls.B200GroupMatrix.philox(G, dtype, m, n, seed=5, scale=0.1)
         Sp = rls.FISTA(Ap, reg=rls.L1Regularization(np.float32(1e-2)), iterations=5, rho=np.float32(0.01), relTol=0.0)
-        S1 = rls.FISTA(rls.B200Matrix.philox(dtype, m, n, seed=5, scale=0.1, layout="row"), reg=rls.L1Regularization(np.float32(1e-2)),
+        S1 = rls.FISTA(rls.B200Matrix.philox(dtype, m, n, seed=5, scale=0.1), reg=rls.L1Regularization(np.float32(1e-2)),
                        iterations=5, rho=np.float32(0.01), relTol=0.0)
         xp, x1 = rls.solve_(Sp, b), rls.solve_(S1, b)
         assert np.array_equal(xp, x1) if ndev == 1 else rel(xp, x1) < 1e-5
