@@ -182,6 +182,9 @@ int32_t rls_tc_batch_adjoint(TcBatchPlan* p, const void* const* bs, void* const*
 int32_t rls_normal_adjoint_batch_raw(rls_normal_t op, int K, const void* const* bs, void* const* outs, bool* done);
 int32_t rls_tc_batch_debug(TcBatchPlan* p, int which, float* host, int64_t nfloats);
 int32_t rls_tc_gram(rls_mat_s* A, rls_mat_s* G);
+bool rls_tc_gram_batch_supported(const rls_mat_s* G, int K);
+int32_t rls_tc_gram_batch_create(rls_mat_s* G, int K, TcBatchPlan** out);
+int32_t rls_tc_gram_batch_apply(TcBatchPlan* p, const void* const* xs, void* const* outs, const int* const* gates);
 int32_t rls_normal_apply_batch_raw(rls_normal_t op, int K, const void* const* xs, void* const* outs, const int* const* gates);
 
 #ifdef __CUDACC__

@@ -686,7 +686,7 @@ int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const in
 }
 
 // res_k = AHA x_k for K right-hand sides.  Lazy forms on a row-major A: two tensor-core GEMMs that read A once
-// each (rls_tc.cu); otherwise K single applies.
+// each; Gram form: one tensor-core GEMM over G (rls_tc.cu); otherwise K single applies.
 int32_t rls_normal_apply_batch_raw(rls_normal_t op, int K, const void* const* xs, void* const* outs, const int* const* gates) {
   const bool want = rls_env_flag("RLS_BATCH_TENSOR_CORES", true);
   if (want && op->form != RLS_NORMAL_GRAM && op->A && rls_tc_batch_supported(op->A, K)) {
@@ -697,6 +697,16 @@ int32_t rls_normal_apply_batch_raw(rls_normal_t op, int K, const void* const* xs
       op->tc_K = K;
     }
     if (op->tc) return rls_tc_batch_apply(op->tc, xs, outs, gates);
+  }
+  // Gram form (the reference's default AHA): one GEMM over G instead of K gemvs that re-read G K times
+  if (want && op->form == RLS_NORMAL_GRAM && op->G && rls_env_flag("RLS_GRAM_BATCH_TENSOR_CORES", true) && rls_tc_gram_batch_supported(op->G, K)) {
+    if (op->tc && op->tc_K != K) { rls_tc_batch_destroy(op->tc); op->tc = nullptr; }
+    if (!op->tc) {
+      int32_t st = rls_tc_gram_batch_create(op->G, K, &op->tc);
+      if (st != RLS_OK) op->tc = nullptr;
+      op->tc_K = K;
+    }
+    if (op->tc) return rls_tc_gram_batch_apply(op->tc, xs, outs, gates);
   }
   for (int k = 0; k < K; ++k) RLS_TRY(rls_normal_apply_raw(op, xs[k], outs[k], gates ? gates[k] : nullptr));
   return RLS_OK;

@@ -363,7 +363,7 @@ __global__ void tc_pack_x_kernel(const __grid_constant__ PtrTable xs, int K, int
 // res_k[j] from P [nf][ldp]: complex (P[2j,2k] + P[2j+1,2k+1]) + i (P[2j,2k+1] - P[2j+1,2k]); real P[j,k].  Lane k is
 // skipped when its done() gate is set.
 __global__ void tc_unpack_g_kernel(const float* __restrict__ P, int64_t ldp, int K, int fpe, int64_t n, const __grid_constant__ PtrTable outs,
-                                   const __grid_constant__ PtrTable gates, int have_gates) {
+                                   const __grid_constant__ PtrTable gates, int have_gates, int conj_out) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
   const int k = threadIdx.x + blockIdx.y * blockDim.x;
   if (j >= n || k >= K) return;
@@ -374,16 +374,20 @@ __global__ void tc_unpack_g_kernel(const float* __restrict__ P, int64_t ldp, int
   } else {
     const float2 a = *reinterpret_cast<const float2*>(P + (2 * j) * ldp + 2 * k);
     const float2 b = *reinterpret_cast<const float2*>(P + (2 * j + 1) * ldp + 2 * k);
-    reinterpret_cast<float2*>(const_cast<void*>(outs.p[k]))[j] = make_float2(a.x + b.y, a.y - b.x);
+    const float im = a.y - b.x;
+    reinterpret_cast<float2*>(const_cast<void*>(outs.p[k]))[j] = make_float2(a.x + b.y, conj_out ? -im : im);
   }
 }
 // Y~ of mode T from K m-vectors (the batched back-projection A'B of init!): Y~[i][fpe*k + c] = b_k[i*fpe + c]
-__global__ void tc_pack_y_kernel(const __grid_constant__ PtrTable bs, int K, int fpe, int64_t m, float* __restrict__ Y, float* __restrict__ Ylo, int Npad) {
+// (conj_in: the imaginary parts change sign — the Gram form below feeds conj(x_k))
+__global__ void tc_pack_y_kernel(const __grid_constant__ PtrTable bs, int K, int fpe, int64_t m, float* __restrict__ Y, float* __restrict__ Ylo, int Npad,
+                                 int conj_in) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
   const int col = threadIdx.x + blockIdx.y * blockDim.x;  // float column of Y~
   if (i >= m || col >= Npad) return;
   const int k = col / fpe, c = col - k * fpe;
-  const float v = k < K ? reinterpret_cast<const float*>(bs.p[k])[i * fpe + c] : 0.f;
+  float v = k < K ? reinterpret_cast<const float*>(bs.p[k])[i * fpe + c] : 0.f;
+  if (conj_in && c == 1) v = -v;
   const float h = rna_tf32(v);
   Y[i * Npad + col] = h;
   Ylo[i * Npad + col] = rna_tf32(v - h);
@@ -463,6 +467,8 @@ int32_t tc_launch(rls_ctx_s* c, const CUtensorMap& mapA, const CUtensorMap& mapB
 struct TcBatchPlan {
   rls_ctx_s* ctx = nullptr;
   rls_mat_s* A = nullptr;
+  rls_mat_s view;         // Gram form: the column-major G seen as the row-major matrix M = G^T on the same memory
+  bool gram = false;
   int K = 0, fpe = 1, Npad = 0;
   int64_t nf = 0, ldx = 0;
   float* XT = nullptr;    // [Npad][ldx]   B^T of mode N, TF32 hi part
@@ -552,15 +558,16 @@ int32_t rls_tc_batch_apply(TcBatchPlan* p, const void* const* xs, void* const* o
   {
     dim3 block(32, 8);
     dim3 grid((unsigned)((A->n + 7) / 8), (unsigned)((K + 31) / 32));
-    tc_unpack_g_kernel<<<grid, block, 0, c->stream>>>(p->P, p->Npad, K, p->fpe, A->n, to, tg, gates ? 1 : 0);
+    tc_unpack_g_kernel<<<grid, block, 0, c->stream>>>(p->P, p->Npad, K, p->fpe, A->n, to, tg, gates ? 1 : 0, 0);
     c->launches++;
   }
   RLS_CUDA(cudaGetLastError());
   return RLS_OK;
 }
 
-// outs_k = A' b_k for K m-vectors (init!: mul!(x0, adjoint(A), b), FISTA.jl:114, CGNR.jl:132, ADMM.jl:198) as ONE mode-T GEMM
-int32_t rls_tc_batch_adjoint(TcBatchPlan* p, const void* const* bs, void* const* outs) {
+// outs_k = A' b_k for K m-vectors (init!: mul!(x0, adjoint(A), b), FISTA.jl:114, CGNR.jl:132, ADMM.jl:198) as ONE mode-T GEMM.
+// conj != 0: outs_k = conj(A' conj(b_k)) = A^T b_k (the Gram form); gates as in rls_tc_batch_apply.
+static int32_t tc_adjoint(TcBatchPlan* p, const void* const* bs, void* const* outs, const int* const* gates, int conj) {
   rls_ctx_s* c = p->ctx;
   rls_mat_s* A = p->A;
   const int K = p->K;
@@ -569,11 +576,11 @@ int32_t rls_tc_batch_adjoint(TcBatchPlan* p, const void* const* bs, void* const*
     return RLS_OK;
   }
   PtrTable tb{}, to{}, tg{};
-  for (int k = 0; k < K; ++k) { tb.p[k] = bs[k]; to.p[k] = outs[k]; }
+  for (int k = 0; k < K; ++k) { tb.p[k] = bs[k]; to.p[k] = outs[k]; tg.p[k] = gates ? gates[k] : nullptr; }
   {
     dim3 block(32, 8);
     dim3 grid((unsigned)((A->m + 7) / 8), (unsigned)((p->Npad + 31) / 32));
-    tc_pack_y_kernel<<<grid, block, 0, c->stream>>>(tb, K, p->fpe, A->m, p->Y, p->Ylo, p->Npad);
+    tc_pack_y_kernel<<<grid, block, 0, c->stream>>>(tb, K, p->fpe, A->m, p->Y, p->Ylo, p->Npad, conj);
     c->launches++;
   }
   TcArgs a{};
@@ -582,15 +589,73 @@ int32_t rls_tc_batch_adjoint(TcBatchPlan* p, const void* const* bs, void* const*
   a.b_presplit = 1;
   a.D = p->P; a.ldd = p->Npad; a.Mtot = p->nf; a.Nvalid = p->Npad; a.Ntot = p->Npad;
   RLS_TRY(tc_launch(c, p->mapAt, p->mapY, p->mapYlo, a, (int)((p->nf + TC_BM - 1) / TC_BM), 1));
-  if (c->nranks > 1) RLS_TRY(rls_allreduce_raw(c, p->P, p->nf * p->Npad));
+  if (c->nranks > 1 && !p->gram) RLS_TRY(rls_allreduce_raw(c, p->P, p->nf * p->Npad));  // G is already the sum over the ranks
   {
     dim3 block(32, 8);
     dim3 grid((unsigned)((A->n + 7) / 8), (unsigned)((K + 31) / 32));
-    tc_unpack_g_kernel<<<grid, block, 0, c->stream>>>(p->P, p->Npad, K, p->fpe, A->n, to, tg, 0);
+    tc_unpack_g_kernel<<<grid, block, 0, c->stream>>>(p->P, p->Npad, K, p->fpe, A->n, to, tg, gates ? 1 : 0, conj);
     c->launches++;
   }
   RLS_CUDA(cudaGetLastError());
   return RLS_OK;
+}
+int32_t rls_tc_batch_adjoint(TcBatchPlan* p, const void* const* bs, void* const* outs) {
+  if (p->gram) { rls_set_error("tensor-core batch plan of a Gram operator has no A"); return RLS_ERR_INVALID; }
+  return tc_adjoint(p, bs, outs, nullptr, 0);
+}
+
+// ------------------------------------------------------------------------------------
+// Gram form of the batched normal operator: res_k = G x_k, G = A'A dense n x n (the reference's DEFAULT AHA,
+// FISTA.jl:58 / CGNR.jl:49 / ADMM.jl:81, under MultiThreading.jl:45-78) as ONE GEMM that reads G once:
+// n^2 s bytes and 8 n^2 K flop (complex) per batched iteration against 2 m n s and 16 m n K for the A-form pair.
+// The column-major G is, on the same memory, the row-major matrix M = G^T, and
+//     (G x)_j = sum_i M[i][j] x_i = conj( sum_i conj(M[i][j]) conj(x_i) ) = conj( (M' conj(x))_j ),
+// i.e. the mode-T GEMM of the back-projection with the imaginary parts flipped on the way in and out — no
+// symmetry of G is assumed (a user-supplied AHA, FISTA.jl:55, is applied as given).
+// ------------------------------------------------------------------------------------
+bool rls_tc_gram_batch_supported(const rls_mat_s* G, int K) {
+  const char* mk = getenv("RLS_BATCH_MIN_K");
+  const int min_k = mk ? atoi(mk) : 8;
+  if (!G || G->layout != RLS_LAYOUT_COLMAJOR || G->m != G->n || K < 2 || K < min_k) return false;
+  const int fpe = G->dtype == RLS_C32 ? 2 : 1;
+  if (K * fpe > 128) return false;
+  if (((uintptr_t)G->d & 15) != 0 || (G->ld * fpe) % 4 != 0) return false;
+  if (G->n * (int64_t)fpe > 0x7fffffff) return false;
+  return G->ctx->cc_major == 10;
+}
+
+int32_t rls_tc_gram_batch_create(rls_mat_s* G, int K, TcBatchPlan** out) {
+  *out = nullptr;
+  if (!rls_tc_gram_batch_supported(G, K)) { rls_set_error("tensor-core Gram batch path: unsupported matrix / K"); return RLS_ERR_UNSUPPORTED; }
+  TcBatchPlan* p = new TcBatchPlan();
+  p->gram = true;
+  p->view.ctx = G->ctx; p->view.dtype = G->dtype; p->view.m = G->n; p->view.n = G->n; p->view.ld = G->ld; p->view.d = G->d;
+  p->view.owned = false; p->view.layout = RLS_LAYOUT_ROWMAJOR;
+  p->ctx = G->ctx; p->A = &p->view; p->K = K;
+  p->fpe = G->dtype == RLS_C32 ? 2 : 1;
+  p->nf = G->n * p->fpe;
+  p->Npad = ((K * p->fpe + 31) / 32) * 32;
+  p->ldx = 0;
+  bool ok = cudaMalloc(&p->Y, (size_t)std::max<int64_t>(G->n, 1) * p->Npad * 4) == cudaSuccess &&
+            cudaMalloc(&p->Ylo, (size_t)std::max<int64_t>(G->n, 1) * p->Npad * 4) == cudaSuccess &&
+            cudaMalloc(&p->P, (size_t)std::max<int64_t>(p->nf, 1) * p->Npad * 4) == cudaSuccess &&
+            cudaMalloc(&p->abort_flag, 4) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); rls_tc_batch_destroy(p); rls_set_error("tensor-core Gram batch path: out of device memory"); return RLS_ERR_NOMEM; }
+  cudaMemsetAsync(p->abort_flag, 0, 4, G->ctx->stream);
+  int32_t s = RLS_OK;
+  if (G->n > 0) {
+    s = make_map(&p->mapAt, (const float*)G->d, G->n, p->nf, G->ld * p->fpe, true);
+    if (s == RLS_OK) s = make_map(&p->mapY, p->Y, G->n, p->Npad, p->Npad, true);
+    if (s == RLS_OK) s = make_map(&p->mapYlo, p->Ylo, G->n, p->Npad, p->Npad, true);
+  }
+  if (s != RLS_OK) { rls_tc_batch_destroy(p); return s; }
+  *out = p;
+  return RLS_OK;
+}
+
+int32_t rls_tc_gram_batch_apply(TcBatchPlan* p, const void* const* xs, void* const* outs, const int* const* gates) {
+  if (!p->gram) { rls_set_error("not a Gram batch plan"); return RLS_ERR_INVALID; }
+  return tc_adjoint(p, xs, outs, gates, p->fpe == 2 ? 1 : 0);
 }
 
 int32_t rls_tc_check_abort(rls_ctx_s* c, int* abort_flag) {
@@ -603,6 +668,7 @@ int32_t rls_tc_check_abort(rls_ctx_s* c, int* abort_flag) {
 // diagnostics: copy an internal operand (0 = B^T of mode N, 1 = Y~, 2 = P) to the host
 int32_t rls_tc_batch_debug(TcBatchPlan* p, int which, float* host, int64_t nfloats) {
   const float* src = which == 0 ? p->XT : which == 1 ? p->Y : p->P;
+  if (!src) { rls_set_error("operand %d does not exist in this plan", which); return RLS_ERR_INVALID; }
   const int64_t have = which == 0 ? (int64_t)p->Npad * p->ldx : which == 1 ? p->A->m * (int64_t)p->Npad : p->nf * (int64_t)p->Npad;
   RLS_CUDA(cudaStreamSynchronize(p->ctx->stream));
   RLS_CUDA(cudaMemcpy(host, src, sizeof(float) * std::min(nfloats, have), cudaMemcpyDeviceToHost));

@@ -272,6 +272,36 @@ def test_gram_on_tensor_cores(rls, ctx, dtype, shape, monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape_k", [(256, 128, 32), (300, 200, 5), (700, 516, 64), (90, 1030, 17)])
+def test_gram_apply_batch_tensor_cores(rls, ctx, dtype, shape_k, monkeypatch):
+    """Gram form (the reference's default AHA = A'*A, FISTA.jl:58) under the multi-RHS driver: K columns G x_k as ONE
+    tcgen05 GEMM over G, against NumPy float64 and against the K single gemvs; a user-supplied non-Hermitian AHA
+    (FISTA.jl:55) is applied as given, not as its adjoint."""
+    monkeypatch.setenv("RLS_BATCH_MIN_K", "2")
+    m, n, K = shape_k
+    A, _ = rand_matrix(dtype, m, n, 81)
+    X = np.stack([rand_vector(dtype, n, 90 + k) for k in range(K)], axis=1)
+    xs = [rls.B200Vector.from_numpy(np.ascontiguousarray(X[:, k]), ctx) for k in range(K)]
+    op = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx, layout="row"), form="gram")
+    R = np.stack([o.to_numpy() for o in op.apply_batch(xs)], axis=1)
+    A64 = A.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
+    ref = (A64.conj().T @ A64) @ X
+    for k in range(K):
+        assert rel(R[:, k], ref[:, k]) < 1.5e-6, (k, rel(R[:, k], ref[:, k]))
+    monkeypatch.setenv("RLS_GRAM_BATCH_TENSOR_CORES", "0")
+    R1 = np.stack([o.to_numpy() for o in op.apply_batch(xs)], axis=1)        # K gemvs over G
+    assert np.array_equal(R1[:, 0], op.apply(xs[0]).to_numpy())
+    assert rel(R, R1) < 2e-6 and not np.array_equal(R, R1)                    # the tensor-core path really ran
+    monkeypatch.setenv("RLS_GRAM_BATCH_TENSOR_CORES", "1")
+    # AHA handed over as a matrix that is NOT Hermitian
+    H, _ = rand_matrix(dtype, n, n, 83)
+    oph = rls.B200NormalOp(G=rls.B200Matrix.from_numpy(H, ctx, layout="col"))
+    Rh = np.stack([o.to_numpy() for o in oph.apply_batch(xs)], axis=1)
+    refh = H.astype(A64.dtype) @ X
+    assert rel(Rh, refh) < 1.5e-6, rel(Rh, refh)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("shape", [(0, 5), (5, 0), (0, 0), (1, 1), (2, 3)])
 def test_degenerate_shapes(rls, ctx, dtype, layout, shape):

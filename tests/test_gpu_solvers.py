@@ -363,6 +363,42 @@ def test_multi_rhs_per_column_stopping(rls, ctx, dtype, monkeypatch):
     assert len(set(counts)) > 1, "the columns were meant to stop at different iterations"
 
 
+@pytest.mark.parametrize("solver", ["FISTA", "CGNR", "ADMM"])
+def test_multi_rhs_gram_form_on_tensor_cores(rls, ctx, solver, monkeypatch):
+    """The reference's DEFAULT normal operator is the materialised Gram matrix (FISTA.jl:58, CGNR.jl:49, ADMM.jl:81); under
+    the multi-RHS driver (MultiThreading.jl:45-78) its K applies G x_k per iteration run as ONE tcgen05 GEMM over G.
+    Columns agree with the sequential Gram-form solves to the parity bound (CG-steered solvers: Float64 criterion) and
+    keep their own iteration counts."""
+    monkeypatch.setenv("RLS_BATCH_MIN_K", "2")
+    dtype = np.complex64
+    m, n, K = 201, 96, 6
+    A, _, _ = problem(dtype, m, n)
+    X = np.stack([sparse_truth(dtype, n, 400 + k, every=5 + 3 * k) for k in range(K)], axis=1)
+    X[:, 4] *= np.float32(1e2)
+    B = (A @ X).astype(dtype)
+    kw, okw = dict(iterations=30), dict(iterations=30)
+    if solver == "FISTA":
+        kw.update(rho=rho_for(A), reg=rls.L1Regularization(np.float32(1e-4)), relTol=np.float32(1e-3))
+        okw.update(rho=rho_for(A), reg=O.L1Regularization(np.float32(1e-4)), relTol=np.float32(1e-3))
+    S = rls.createLinearSolver(getattr(rls, solver), rls.B200Matrix.from_numpy(A, ctx, layout="row"), normal="gram", **kw)
+    assert S.AHA.form == "gram"
+    Xb = rls.solve_(S, B)
+    counts = list(S.batch_iterations)
+    monkeypatch.setenv("RLS_GRAM_BATCH_TENSOR_CORES", "0")
+    Xg = rls.solve_(S, B)                                   # K gemvs over G per iteration
+    assert list(S.batch_iterations) == counts
+    assert not np.array_equal(Xb, Xg), "the batched solve was meant to take the tensor-core GEMM over G"
+    for k in range(K):
+        e = rel(Xb[:, k], Xg[:, k])
+        if e < TOL:
+            continue
+        assert solver in ("CGNR", "ADMM"), (solver, k, e)
+        x32 = getattr(O, solver)(A, **okw).solve(B[:, k].copy())
+        okw64 = {kk: (float(v) if isinstance(v, np.floating) else v) for kk, v in okw.items()}
+        x64 = getattr(O, solver)(up64(A), **okw64).solve(up64(B[:, k]))
+        assert rel(Xb[:, k], x64) <= rel(x32, x64), (solver, k, e, rel(Xb[:, k], x64), rel(x32, x64))
+
+
 def test_multi_rhs_more_columns_than_one_gemm_tile(rls, ctx):
     """K * 2 > 128 complex columns do not fit one 128-wide GEMM tile: the driver falls back to per-column applies."""
     dtype = np.complex64
