@@ -272,7 +272,7 @@ def test_gram_on_tensor_cores(rls, ctx, dtype, shape, monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape_k", [(256, 128, 32), (300, 200, 5), (700, 516, 64), (90, 1030, 17)])
+@pytest.mark.parametrize("shape_k", [(256, 128, 32), (300, 200, 5), (700, 516, 64), (90, 1032, 17)])   # Gram form: n % 4 == 0
 def test_gram_apply_batch_tensor_cores(rls, ctx, dtype, shape_k, monkeypatch):
     """Gram form (the reference's default AHA = A'*A, FISTA.jl:58) under the multi-RHS driver: K columns G x_k as ONE
     tcgen05 GEMM over G, against NumPy float64 and against the K single gemvs; a user-supplied non-Hermitian AHA
