@@ -48,8 +48,13 @@ enum { RLS_F32 = 0, RLS_C32 = 1 };
 /* ---- solver kinds: src/{FISTA,POGM,OptISTA,CGNR,ADMM,SplitBregman}.jl (Kaczmarz: rls_kaczmarz_*) */
 enum { RLS_FISTA = 0, RLS_POGM = 1, RLS_OPTISTA = 2, RLS_CGNR = 3, RLS_ADMM = 4, RLS_SPLITBREGMAN = 5 };
 
-/* ---- regularisation sinks: src/proximalMaps/Prox{L1,L2,L21,TV}.jl ------------ */
-enum { RLS_REG_NONE = 0, RLS_REG_L1 = 1, RLS_REG_L2 = 2, RLS_REG_L21 = 3, RLS_REG_TV = 4 };
+/* ---- regularisation sinks: src/proximalMaps/Prox{L1,L2,L21,TV,Nuclear,LLR}.jl -- */
+enum { RLS_REG_NONE = 0, RLS_REG_L1 = 1, RLS_REG_L2 = 2, RLS_REG_L21 = 3, RLS_REG_TV = 4,
+       RLS_REG_NUCLEAR = 5,  /* rls_reg_desc: svtShape in tv_shape[0..1], tv_ndims = 2                            */
+       RLS_REG_LLR = 6       /* rls_reg_desc: shape in tv_shape, blockSize in tv_dims, RLS_LLR_* flags in
+                                tv_iterations, seed of the randshift stream in slices                              */ };
+/* LLRRegularization keywords randshift / fullyOverlapping (ProxLLR.jl:15-16) */
+enum { RLS_LLR_RANDSHIFT = 1, RLS_LLR_OVERLAPPING = 2 };
 
 /* ---- projections: src/proximalMaps/Prox{Real,Positive}.jl (bit mask) --------- */
 enum { RLS_PROJ_REAL = 1, RLS_PROJ_POSITIVE = 2 };
@@ -206,6 +211,17 @@ int32_t rls_prox_tv(rls_vec_t x, float lambda, int32_t ndims, const int64_t* sha
                     const int32_t* dims_1based, int32_t iterations_tv);
 int32_t rls_prox_positive(rls_vec_t x);
 int32_t rls_prox_real(rls_vec_t x);
+/* Singular-value soft-thresholding, computed on the device as X·W with W from the Float64
+ * eigen-decomposition of the short side's Gram matrix (csrc/rls_svt.cu); the shorter side must be <= 32.
+ * prox!(::NuclearRegularization, x, λ), ProxNuclear.jl:27-32: x is the column-major rows x cols matrix (svtShape).
+ * prox!(::LLRRegularization, x, λ), ProxLLR.jl:36-90,163-199: x = image series shape x K; every blockSize patch is a
+ * (pixels x K) matrix; `shift` (NULL = 0) is the circular shift of the patch grid that `randshift` draws (:55), injected
+ * by the caller so that a result can be reproduced; fully_overlapping averages all blockSize shifts (needs
+ * shape % blockSize == 0: the reference's padded reshape fails otherwise, :170-176 with :50).  The reference's shortcut
+ * "λ >= sqrt(norm(X'X, Inf)) -> patch = 0" (:67-71, `norm` = largest |entry|) is kept. */
+int32_t rls_prox_nuclear(rls_vec_t x, float lambda, int64_t rows, int64_t cols);
+int32_t rls_prox_llr(rls_vec_t x, float lambda, int32_t ndims, const int64_t* shape, const int64_t* block_size,
+                     const int64_t* shift, int32_t fully_overlapping);
 /* GradientOp(T; shape, dims) forward / transpose (LinearOperatorCollection; ProxTV.jl:46, ADMM.jl:74) */
 int32_t rls_grad_rows(int32_t ndims, const int64_t* shape, int32_t ndirs, const int32_t* dims_1based, int64_t* rows);
 int32_t rls_grad_apply(rls_vec_t img, rls_vec_t out, int32_t ndims, const int64_t* shape, int32_t ndirs,

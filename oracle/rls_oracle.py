@@ -18,11 +18,13 @@ Third-party arithmetic restated from published sources (not vendored in
 """
 from __future__ import annotations
 
+import itertools
 import math
 import numpy as np
 
 __all__ = [
     "L1Regularization", "L2Regularization", "L21Regularization", "TVRegularization",
+    "NuclearRegularization", "LLRRegularization", "prox_nuclear", "prox_llr",
     "PositiveRegularization", "RealRegularization", "NormalizedRegularization",
     "NoNormalization", "MeasurementBasedNormalization", "SystemMatrixBasedNormalization",
     "prox_", "reg_norm", "lam_of", "grad_op", "grad_op_t", "grad_t_axpy", "grad_rows", "cg", "power_iterations",
@@ -133,6 +135,24 @@ class TVRegularization(_Param):
         self.dims = tuple(range(1, len(self.shape) + 1)) if dims is None else (
             (int(dims),) if np.isscalar(dims) else tuple(int(d) for d in dims))
         self.iterationsTV = int(iterationsTV)
+
+
+class NuclearRegularization(_Param):
+    """src/proximalMaps/ProxNuclear.jl:15-19"""
+    def __init__(self, lam, svtShape=()):
+        super().__init__(lam)
+        self.svtShape = tuple(int(v) for v in svtShape)
+
+
+class LLRRegularization(_Param):
+    """src/proximalMaps/ProxLLR.jl:20-29.  `shift` replaces the draw `rand(block_idx)` of randshift (:55) so that a
+    test can hand the same shift to both sides; None = no shift (randshift=false)."""
+    def __init__(self, lam, shape=(0,), blockSize=None, randshift=False, fullyOverlapping=False, L=1, shift=None):
+        super().__init__(lam)
+        self.shape = tuple(int(v) for v in shape)
+        self.blockSize = tuple(int(b) for b in blockSize) if blockSize is not None else (2,) * len(self.shape)
+        self.randshift, self.fullyOverlapping, self.L = bool(randshift), bool(fullyOverlapping), int(L)
+        self.shift = shift
 
 
 class PositiveRegularization:
@@ -379,6 +399,74 @@ def prox_tv_fgp(x, lam, shape, dims, iterationsTV=10):
     return x
 
 
+def prox_nuclear(x, lam, svtShape):
+    """ProxNuclear.jl:27-32: U,S,V = svd(reshape(x, svtShape)); prox!(L1Regularization, S, lam); x = vec(U*Diagonal(S)*V').
+    LAPACK gesdd in the element type, as Julia's `svd`."""
+    T = real_type(x.dtype)
+    X = x.reshape(svtShape, order="F")
+    U, S, Vh = np.linalg.svd(X, full_matrices=False)
+    S = prox_l1(S.astype(T), lam)
+    x[...] = ((U * S) @ Vh).astype(x.dtype).reshape(-1, order="F")
+    return x
+
+
+def _llr_non_overlapping(xs, lam, shape, blockSize):
+    """ProxLLR.jl:44-90 on the (already shifted) array xs of size shape x K, in place."""
+    T = real_type(xs.dtype)
+    lam = T(lam)
+    K = xs.shape[-1]
+    for origin in itertools.product(*[range(0, shape[d], blockSize[d]) for d in range(len(shape))][::-1]):
+        origin = origin[::-1]                                   # CartesianIndices iterate the first dimension fastest
+        # idx = idx_center .+ block_idx (1-based offsets 1..blockSize on 0-based centres), cut at the image border (:60-63)
+        sl = tuple(slice(origin[d], min(origin[d] + blockSize[d], shape[d])) for d in range(len(shape)))
+        blk = xs[sl]
+        X = np.zeros((int(np.prod(blockSize)), K), dtype=xs.dtype)
+        npx = int(np.prod(blk.shape[:-1]))
+        X[:npx, :] = blk.reshape((npx, K), order="F")
+        if np.any(X != 0):
+            G = (X.conj().T @ X).astype(xs.dtype)                # mul!(x2, x', x)
+            ub = np.sqrt(np.max(_hypot_abs(G)))                  # sqrt(norm(x2, Inf)): Julia's norm of a matrix = largest |entry|
+            if lam >= ub:
+                xs[sl] = 0
+            else:
+                U, S, Vh = np.linalg.svd(X, full_matrices=False)
+                S = prox_l1(S.astype(T), lam)
+                Vh = Vh * S[:, None]                             # SVDec.Vt .*= SVDec.S
+                X = (U @ Vh).astype(xs.dtype)
+                xs[sl] = X[:npx, :].reshape(blk.shape, order="F")
+    return xs
+
+
+def prox_llr(x, lam, shape, blockSize, shift=None, fullyOverlapping=False):
+    """ProxLLR.jl:36-38.  shift = the draw of `rand(block_idx)` (:55; None = randshift off).  ShiftedArrays.circshift is a
+    lazy view (writes go through to x); here: shift a copy, threshold, shift back."""
+    nd = len(shape)
+    K = x.size // int(np.prod(shape))
+    X = x.reshape(tuple(shape) + (K,), order="F")
+    sh = tuple(int(v) for v in shift) if shift is not None else (0,) * nd
+    ax = tuple(range(nd))
+    if not fullyOverlapping:
+        xs = np.roll(X, sh, axis=ax)                             # circshift(x, s): xs[i] = x[i - s]
+        _llr_non_overlapping(xs, lam, shape, blockSize)
+        x[...] = np.roll(xs, tuple(-v for v in sh), axis=ax).reshape(-1, order="F")
+        return x
+    # ProxLLR.jl:163-199; the padded branch (:170-173) reshapes the padded array with the unpadded shape inside the
+    # nested call (:50) and throws, so only shapes that are multiples of blockSize exist
+    if any(shape[d] % blockSize[d] for d in range(nd)):
+        raise ValueError("DimensionMismatch: fully overlapping LLR needs shape to be a multiple of blockSize")
+    xp = X.copy()
+    out = np.zeros_like(X)
+    for is_ in itertools.product(*[range(1, blockSize[d] + 1) for d in range(nd)][::-1]):
+        is_ = is_[::-1]
+        tot = tuple(is_[d] + sh[d] for d in range(nd))           # the nested call applies its own randshift on top (:55)
+        xs = np.roll(xp, tot, axis=ax)
+        _llr_non_overlapping(xs, lam, shape, blockSize)
+        out = out + np.roll(xs, tuple(-v for v in tot), axis=ax)
+    out = out / real_type(x.dtype)(int(np.prod(blockSize)))
+    x[...] = out.astype(x.dtype).reshape(-1, order="F")
+    return x
+
+
 def prox_(reg, x, lam=None):
     """prox!(reg, x[, lam]) dispatch: Regularization.jl:17,31; NestedRegularization.jl:26-29"""
     if isinstance(reg, type):
@@ -399,6 +487,10 @@ def prox_(reg, x, lam=None):
         return prox_l21(x, lam, reg.slices)
     if isinstance(reg, TVRegularization):
         return prox_tv_fgp(x, lam, reg.shape, reg.dims, reg.iterationsTV)
+    if isinstance(reg, NuclearRegularization):
+        return prox_nuclear(x, lam, reg.svtShape)
+    if isinstance(reg, LLRRegularization):
+        return prox_llr(x, lam, reg.shape, reg.blockSize, reg.shift, reg.fullyOverlapping)
     raise TypeError(reg)
 
 
@@ -417,6 +509,8 @@ def reg_norm(reg, x, lam=None):
         return lam * sum(_norm2(xv[j::L]) for j in range(L))
     if isinstance(reg0, TVRegularization):
         return lam * np.sum(_hypot_abs(grad_op(x, reg0.shape, reg0.dims)))
+    if isinstance(reg0, NuclearRegularization):                  # ProxNuclear.jl:39-42
+        return lam * np.sum(np.linalg.svd(x.reshape(reg0.svtShape, order="F"), compute_uv=False))
     raise TypeError(reg)
 
 

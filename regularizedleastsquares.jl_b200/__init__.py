@@ -21,7 +21,7 @@ from ._capi import RlsError  # noqa: E402
 from .arrays import B200Context, B200Group, B200GroupMatrix, B200Matrix, B200NormalOp, B200Vector  # noqa: E402
 from .regularization import (AbstractParameterizedRegularization, AbstractProjectionRegularization,  # noqa: E402
                              AbstractRegularization, GradientOp, L1Regularization, L2Regularization,
-                             L21Regularization, MeasurementBasedNormalization, NoNormalization,
+                             L21Regularization, LLRRegularization, MeasurementBasedNormalization, NoNormalization, NuclearRegularization,
                              NormalizedRegularization, PositiveRegularization, RealRegularization,
                              SystemMatrixBasedNormalization, TVRegularization, findsink, findsinks, lam, sink)
 from .prox import prox_  # noqa: E402

@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "librls_b200.so")
 RLS_OK = 0
 RLS_F32, RLS_C32 = 0, 1
 RLS_FISTA, RLS_POGM, RLS_OPTISTA, RLS_CGNR, RLS_ADMM, RLS_SPLITBREGMAN = 0, 1, 2, 3, 4, 5
-RLS_REG_NONE, RLS_REG_L1, RLS_REG_L2, RLS_REG_L21, RLS_REG_TV = 0, 1, 2, 3, 4
+RLS_REG_NONE, RLS_REG_L1, RLS_REG_L2, RLS_REG_L21, RLS_REG_TV, RLS_REG_NUCLEAR, RLS_REG_LLR = 0, 1, 2, 3, 4, 5, 6
+RLS_LLR_RANDSHIFT, RLS_LLR_OVERLAPPING = 1, 2
 RLS_PROJ_REAL, RLS_PROJ_POSITIVE = 1, 2
 RLS_NORMAL_TWOPASS, RLS_NORMAL_ONEPASS, RLS_NORMAL_GRAM, RLS_NORMAL_AUTO = 0, 1, 2, 3
 RLS_TRAFO_IDENTITY, RLS_TRAFO_GRADIENT = 0, 1
@@ -137,6 +138,8 @@ SIGNATURES = {
     "rls_prox_tv": [_P, _F32, _I32, _PI64, _I32, _PI32, _I32],
     "rls_prox_positive": [_P],
     "rls_prox_real": [_P],
+    "rls_prox_nuclear": [_P, _F32, _I64, _I64],
+    "rls_prox_llr": [_P, _F32, _I32, _PI64, _PI64, _PI64, _I32],
     "rls_grad_rows": [_I32, _PI64, _I32, _PI32, _PI64],
     "rls_grad_apply": [_P, _P, _I32, _PI64, _I32, _PI32],
     "rls_grad_apply_t": [_P, _P, _I32, _PI64, _I32, _PI32],

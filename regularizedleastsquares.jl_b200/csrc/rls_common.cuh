@@ -64,6 +64,10 @@ struct rls_ctx_s {
   void* gemv_scratch = nullptr;
   size_t gemv_scratch_bytes = 0;
   unsigned* gemv_tickets = nullptr;  // [4096]
+  // singular-value thresholding scratch (partial Gram matrices and the q x q maps W, rls_svt.cu), grown on demand
+  void* svt_scratch = nullptr;
+  size_t svt_scratch_bytes = 0;
+  uint64_t llr_calls = 0;            // LLR randshift: prox! calls so far (counter of the shift generator)
   // L2 flush
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;

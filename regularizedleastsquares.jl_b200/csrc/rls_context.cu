@@ -165,6 +165,7 @@ static int32_t ctx_free(rls_ctx_s* c) {
   cudaFree(c->red_out);
   cudaFreeHost(c->red_out_host);
   cudaFree(c->gemv_scratch);
+  cudaFree(c->svt_scratch);
   cudaFree(c->gemv_tickets);
   cudaFree(c->flush_buf);
   cudaEventDestroy(c->ev0);

@@ -263,6 +263,26 @@ int32_t rls_prox_launch(rls_ctx_s* c, int32_t dtype, void* x, int64_t n, const r
       }
       return s;
     }
+    case RLS_REG_NUCLEAR:
+      // svtShape travels in tv_shape[0..1] (ProxNuclear.jl:15-19)
+      return rls_prox_nuclear_launch(c, dtype, x, n, reg->tv_shape[0], reg->tv_shape[1], lam, lam_dev, gate);
+    case RLS_REG_LLR: {
+      // shape in tv_shape, blockSize in tv_dims, flags in tv_iterations (ProxLLR.jl:20-29).  randshift draws one shift of
+      // the patch grid per prox! call (:55); here from a counter-based generator seeded by reg->slices, so that a solve
+      // is reproducible (the reference uses the global RNG)
+      RLS_CHECK_ARG(reg->tv_ndims >= 1 && reg->tv_ndims <= RLS_MAX_TV_DIMS, "LLR: bad dimensionality %d", reg->tv_ndims);
+      int64_t block[RLS_MAX_TV_DIMS], shift[RLS_MAX_TV_DIMS];
+      for (int d = 0; d < reg->tv_ndims; ++d) { block[d] = reg->tv_dims[d]; shift[d] = 0; }
+      if (reg->tv_iterations & RLS_LLR_RANDSHIFT) {
+        uint64_t z = (uint64_t)reg->slices * 0x9E3779B97F4A7C15ull + (++c->llr_calls) * 0xBF58476D1CE4E5B9ull;
+        for (int d = 0; d < reg->tv_ndims; ++d) {
+          z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;   // splitmix64
+          shift[d] = 1 + (int64_t)(z % (uint64_t)(block[d] > 0 ? block[d] : 1));                             // rand(1:blockSize[d])
+        }
+      }
+      return rls_prox_llr_launch(c, dtype, x, n, reg->tv_ndims, reg->tv_shape, block, shift, (reg->tv_iterations & RLS_LLR_OVERLAPPING) ? 1 : 0,
+                                 lam, lam_dev, gate);
+    }
     default:
       rls_set_error("unknown regularization kind %d", reg->kind);
       return RLS_ERR_INVALID;

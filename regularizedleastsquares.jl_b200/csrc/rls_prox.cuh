@@ -127,6 +127,12 @@ void rls_tv_work_free(TvWork* w);
 // *lam_dev when lam_dev != NULL (device-resident thresholds of the whole-solve path).
 int32_t rls_prox_launch(rls_ctx_s* ctx, int32_t dtype, void* x, int64_t n, const rls_reg_desc* reg, float lam,
                         const float* lam_dev, const int* gate, TvWork* tv);
+// singular-value thresholding (rls_svt.cu): NuclearRegularization on the column-major rows x cols matrix, LLRRegularization
+// on the blockSize patches of an image series (shift = circular shift of the patch grid, may be NULL)
+int32_t rls_prox_nuclear_launch(rls_ctx_s* ctx, int32_t dtype, void* x, int64_t n, int64_t rows, int64_t cols, float lam, const float* lam_dev,
+                                const int* gate);
+int32_t rls_prox_llr_launch(rls_ctx_s* ctx, int32_t dtype, void* x, int64_t n, int32_t ndims, const int64_t* shape, const int64_t* block,
+                            const int64_t* shift, int fully_overlapping, float lam, const float* lam_dev, const int* gate);
 int32_t rls_proj_launch(rls_ctx_s* ctx, int32_t dtype, void* x, int64_t n, int proj_mask, const int* gate);
 // out[e] = (Phi x)[e]
 int32_t rls_grad_fwd_launch(rls_ctx_s* ctx, int32_t dtype, const void* x, void* out, const GradGeom& g, const int* gate);

@@ -1084,7 +1084,7 @@ static int32_t validate_desc(const rls_solver_desc* d) {
   }
   for (int i = 0; i < d->n_reg; ++i) {
     const rls_reg_desc& r = d->reg[i];
-    RLS_CHECK_ARG(r.kind >= RLS_REG_NONE && r.kind <= RLS_REG_TV, "unknown regularization kind %d", r.kind);
+    RLS_CHECK_ARG(r.kind >= RLS_REG_NONE && r.kind <= RLS_REG_LLR, "unknown regularization kind %d", r.kind);
     RLS_CHECK_ARG(r.trafo == RLS_TRAFO_IDENTITY || r.trafo == RLS_TRAFO_GRADIENT, "unknown regTrafo %d", r.trafo);
     if (r.trafo == RLS_TRAFO_GRADIENT) {
       RLS_CHECK_ARG(admm_like(d->kind), "regTrafo is an ADMM / SplitBregman keyword");

@@ -15,11 +15,11 @@ import numpy as np
 from . import _capi as capi
 from .arrays import B200Vector
 from .regularization import (AbstractProjectionRegularization, L1Regularization, L2Regularization, L21Regularization,
-                             NormalizedRegularization, PositiveRegularization, RealRegularization, TVRegularization,
-                             lam as lam_of, sink)
+                             LLRRegularization, NormalizedRegularization, NuclearRegularization, PositiveRegularization,
+                             RealRegularization, TVRegularization, lam as lam_of, sink)
 
 
-def _device_prox(reg, v, lam):
+def _device_prox(reg, v, lam, shift=None):
     s = sink(reg)
     if isinstance(s, PositiveRegularization):
         capi.call("rls_prox_positive", v.handle)
@@ -38,15 +38,21 @@ def _device_prox(reg, v, lam):
         shape = (C.c_int64 * len(s.shape))(*s.shape)
         dims = (C.c_int32 * max(1, len(s.dims)))(*s.dims)
         capi.call("rls_prox_tv", v.handle, lam, len(s.shape), shape, len(s.dims), dims, s.iterationsTV)
+    elif isinstance(s, NuclearRegularization):
+        capi.call("rls_prox_nuclear", v.handle, lam, s.svtShape[0], s.svtShape[1])
+    elif isinstance(s, LLRRegularization):
+        nd = len(s.shape)
+        capi.call("rls_prox_llr", v.handle, lam, nd, (C.c_int64 * nd)(*s.shape), (C.c_int64 * nd)(*s.blockSize),
+                  (C.c_int64 * nd)(*(shift if shift is not None else s.next_shift())), 1 if s.fullyOverlapping else 0)
     else:
         raise TypeError(f"prox! is not accelerated for {type(s).__name__} (no CPU fallback)")
 
 
-def prox_(reg, x, lam=None, **kwargs):
+def prox_(reg, x, lam=None, shift=None, **kwargs):
     """prox!(reg, x[, λ]; kwargs...) — in place, returns x.
 
     `reg` may be an instance, or a type (then `reg(λ; kwargs...)` is constructed first,
-    Regularization.jl:39,55)."""
+    Regularization.jl:39,55).  `shift` (LLRRegularization only) fixes the patch-grid shift that `randshift` would draw."""
     if isinstance(reg, type):
         if issubclass(reg, AbstractProjectionRegularization):
             reg = reg()
@@ -55,13 +61,13 @@ def prox_(reg, x, lam=None, **kwargs):
     if lam is None and not isinstance(sink(reg), AbstractProjectionRegularization):
         lam = lam_of(reg)
     if isinstance(x, B200Vector):
-        _device_prox(reg, x, lam)
+        _device_prox(reg, x, lam, shift)
         return x
     arr = np.asarray(x)
     if arr.dtype not in (np.float32, np.complex64):
         raise TypeError(f"prox!: Float32 / ComplexF32 only on this path, got {arr.dtype}")
     v = B200Vector.from_numpy(arr.ravel(order="F"))
-    _device_prox(reg, v, lam)
+    _device_prox(reg, v, lam, shift)
     out = v.to_numpy().reshape(arr.shape, order="F")
     if isinstance(x, np.ndarray):
         x[...] = out

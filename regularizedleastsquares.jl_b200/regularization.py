@@ -4,7 +4,8 @@ regularization term + normalisation scheme into the scalar λ handed to the libr
 
 Names, argument meaning and error behaviour follow the reference:
   L1Regularization(λ), L2Regularization(λ), L21Regularization(λ; slices),
-  TVRegularization(λ; shape, dims, iterationsTV), PositiveRegularization(), RealRegularization(),
+  TVRegularization(λ; shape, dims, iterationsTV), NuclearRegularization(λ; svtShape),
+  LLRRegularization(λ; shape, blockSize, randshift, fullyOverlapping), PositiveRegularization(), RealRegularization(),
   NormalizedRegularization(reg, factor), NoNormalization / MeasurementBasedNormalization /
   SystemMatrixBasedNormalization, λ(reg) -> lam(reg), sink(reg), findsink(s).
 """
@@ -69,6 +70,41 @@ class TVRegularization(AbstractParameterizedRegularization):
         self.iterationsTV = int(iterationsTV)
         if not 1 <= len(self.shape) <= capi.RLS_MAX_TV_DIMS:
             raise ValueError(f"TVRegularization: 1..{capi.RLS_MAX_TV_DIMS} dimensions supported")
+
+
+class NuclearRegularization(AbstractParameterizedRegularization):
+    """src/proximalMaps/ProxNuclear.jl:15-19: singular-value soft-thresholding of reshape(x, svtShape)"""
+    kind = capi.RLS_REG_NUCLEAR
+
+    def __init__(self, lam, svtShape=()):
+        super().__init__(lam)
+        self.svtShape = tuple(int(s) for s in svtShape)
+        if len(self.svtShape) != 2:
+            raise ValueError("NuclearRegularization: svtShape must be (rows, cols)")
+
+
+class LLRRegularization(AbstractParameterizedRegularization):
+    """src/proximalMaps/ProxLLR.jl:20-29: locally low rank — singular-value thresholding of every blockSize patch of an
+    image series.  `randshift` draws a new circular shift of the patch grid at every prox! call (:55); `seed` makes that
+    stream reproducible here (the reference uses the global RNG)."""
+    kind = capi.RLS_REG_LLR
+
+    def __init__(self, lam, shape=(0,), blockSize=None, randshift=True, fullyOverlapping=False, L=1, seed=0):
+        super().__init__(lam)
+        self.shape = tuple(int(s) for s in shape)
+        self.blockSize = tuple(int(b) for b in blockSize) if blockSize is not None else (2,) * len(self.shape)
+        if len(self.blockSize) != len(self.shape) or not 1 <= len(self.shape) <= capi.RLS_MAX_TV_DIMS:
+            raise ValueError(f"LLRRegularization: shape and blockSize need the same 1..{capi.RLS_MAX_TV_DIMS} dimensions")
+        self.randshift, self.fullyOverlapping, self.L, self.seed = bool(randshift), bool(fullyOverlapping), int(L), int(seed)
+        self._calls = 0
+
+    def next_shift(self):
+        """the shift of this prox! call: rand(CartesianIndices(blockSize)) (:55), zero when randshift is off"""
+        if not self.randshift:
+            return (0,) * len(self.shape)
+        self._calls += 1
+        rng = np.random.default_rng([self.seed, self._calls])
+        return tuple(int(rng.integers(1, b + 1)) for b in self.blockSize)
 
 
 class PositiveRegularization(AbstractProjectionRegularization):
@@ -155,6 +191,13 @@ def reg_desc(reg, rho=0.0, trafo=None):
     if isinstance(s, TVRegularization):
         geom = (s.shape, s.dims)
         d.tv_iterations = s.iterationsTV
+    if isinstance(s, NuclearRegularization):           # svtShape in tv_shape[0..1] (include/rls_b200.h)
+        d.tv_ndims = 2
+        d.tv_shape[0], d.tv_shape[1] = s.svtShape
+    if isinstance(s, LLRRegularization):               # shape / blockSize / flags / seed of the shift stream
+        geom = (s.shape, s.blockSize)
+        d.tv_iterations = (capi.RLS_LLR_RANDSHIFT if s.randshift else 0) | (capi.RLS_LLR_OVERLAPPING if s.fullyOverlapping else 0)
+        d.slices = s.seed
     if trafo is not None:
         d.trafo = capi.RLS_TRAFO_GRADIENT
         geom = (trafo.shape, trafo.dims)
