@@ -64,7 +64,8 @@ enum {
   RLS_NORMAL_TWOPASS = 0,   /* y = A x ; g = A' y      (2 sweeps over A)          */
   RLS_NORMAL_ONEPASS = 1,   /* fused panel kernel      (1 HBM sweep over A)       */
   RLS_NORMAL_GRAM = 2,      /* g = G x with G = A'A    (reference default form)   */
-  RLS_NORMAL_AUTO = 3
+  RLS_NORMAL_AUTO = 3,
+  RLS_NORMAL_MATRIXFREE = 4 /* reported by rls_normal_form for rls_normal_from_linop / rls_normal_from_callback */
 };
 
 /* ---- device storage layout of a system matrix ---------------------------------
@@ -90,6 +91,9 @@ typedef struct rls_ctx_s* rls_ctx_t;
 typedef struct rls_mat_s* rls_mat_t;
 typedef struct rls_vec_s* rls_vec_t;
 typedef struct rls_normal_s* rls_normal_t;
+typedef struct rls_linop_s* rls_linop_t;   /* matrix-free system operator (SamplingOp, FFTOp, products) */
+/* matrix-free AHA as a callback: enqueue res = AHA x on `cuda_stream` (x, res: DEVICE pointers to n elements); 0 = success */
+typedef int32_t (*rls_apply_fn)(void* user, const void* x_dev, void* res_dev, void* cuda_stream);
 typedef struct rls_solver_s* rls_solver_t;
 typedef struct rls_kaczmarz_s* rls_kaczmarz_t;
 
@@ -197,6 +201,23 @@ int32_t rls_normal_apply(rls_normal_t op, rls_vec_t x, rls_vec_t res);
 int32_t rls_normal_apply_batch(rls_normal_t op, int32_t K, const rls_vec_t* xs, const rls_vec_t* outs);
 /* diagnostics: internal operands of the last batched apply (0 = packed X, 1 = Y = A X, 2 = A' Y before unpacking) */
 int32_t rls_normal_batch_debug(rls_normal_t op, int32_t which, float* host, int64_t nfloats);
+/* ---- matrix-free operators ---------------------------------
+ * The documentation's examples use operators that are never stored: SamplingOp (examples/compressed_sensing.jl:23), FFTOp
+ * and products of them (LinearOperatorCollection).  A solver built on such an operator takes the AHA-only interface the
+ * reference already has (`createLinearSolver(S, A; AHA=...)`, solve!(solver, A'b)): the host computes A'b with
+ * rls_linop_mul_adjoint and creates the solver with A = NULL and AHA = rls_normal_from_linop(L).
+ * pattern_1based: Julia linear indices, no duplicates.  FFTOp: ComplexF32, y = fftshift(fft(ifftshift(x))) / sqrt(N) for
+ * shift != 0, unitary != 0 (cuFFT, loaded with dlopen on first use); its adjoint is the inverse transform.
+ * rls_normal_from_callback: AHA is the caller's function (a Julia @cfunction around any LinearOperator). */
+int32_t rls_linop_sampling_create(rls_ctx_t ctx, int32_t dtype, int64_t n, int64_t npattern, const int64_t* pattern_1based, rls_linop_t* out);
+int32_t rls_linop_fft_create(rls_ctx_t ctx, int32_t ndims, const int64_t* shape, int32_t shift, int32_t unitary, rls_linop_t* out);
+int32_t rls_linop_compose(rls_linop_t outer, rls_linop_t inner, rls_linop_t* out);   /* y = outer (inner x) */
+int32_t rls_linop_destroy(rls_linop_t L);
+int32_t rls_linop_shape(rls_linop_t L, int64_t* m, int64_t* n, int32_t* dtype);
+int32_t rls_linop_mul(rls_linop_t L, rls_vec_t x, rls_vec_t y);                      /* mul!(y, A, x)           */
+int32_t rls_linop_mul_adjoint(rls_linop_t L, rls_vec_t y, rls_vec_t x);              /* mul!(x, adjoint(A), y)  */
+int32_t rls_normal_from_linop(rls_linop_t L, rls_normal_t* out);                     /* normalOperator(A)       */
+int32_t rls_normal_from_callback(rls_ctx_t ctx, int32_t dtype, int64_t n, rls_apply_fn fn, void* user, rls_normal_t* out);
 /* power_iterations(AHA, b; rtol, maxiter) Utils.jl:262-287; b0 replaces the randn start vector */
 int32_t rls_power_iterations(rls_normal_t op, rls_vec_t b0, double rtol, int32_t maxiter, double* lambda_max);
 

@@ -24,6 +24,7 @@ from .regularization import (AbstractParameterizedRegularization, AbstractProjec
                              L21Regularization, LLRRegularization, MeasurementBasedNormalization, NoNormalization, NuclearRegularization,
                              NormalizedRegularization, PositiveRegularization, RealRegularization,
                              SystemMatrixBasedNormalization, TVRegularization, findsink, findsinks, lam, sink)
+from .operators import FFTOp, LinearOperator, SamplingOp  # noqa: E402
 from .prox import prox_  # noqa: E402
 from .solvers import (ADMM, CGNR, FISTA, POGM, Kaczmarz, OptISTA, SplitBregman, AbstractLinearSolver, createLinearSolver, init_, iterate,  # noqa: E402
                       linearSolverList, solve_, solverconvergence, solversolution, solverstate)

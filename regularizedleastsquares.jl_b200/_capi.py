@@ -18,7 +18,7 @@ RLS_FISTA, RLS_POGM, RLS_OPTISTA, RLS_CGNR, RLS_ADMM, RLS_SPLITBREGMAN = 0, 1, 2
 RLS_REG_NONE, RLS_REG_L1, RLS_REG_L2, RLS_REG_L21, RLS_REG_TV, RLS_REG_NUCLEAR, RLS_REG_LLR = 0, 1, 2, 3, 4, 5, 6
 RLS_LLR_RANDSHIFT, RLS_LLR_OVERLAPPING = 1, 2
 RLS_PROJ_REAL, RLS_PROJ_POSITIVE = 1, 2
-RLS_NORMAL_TWOPASS, RLS_NORMAL_ONEPASS, RLS_NORMAL_GRAM, RLS_NORMAL_AUTO = 0, 1, 2, 3
+RLS_NORMAL_TWOPASS, RLS_NORMAL_ONEPASS, RLS_NORMAL_GRAM, RLS_NORMAL_AUTO, RLS_NORMAL_MATRIXFREE = 0, 1, 2, 3, 4
 RLS_TRAFO_IDENTITY, RLS_TRAFO_GRADIENT = 0, 1
 RLS_VARY_RHO_NONE, RLS_VARY_RHO_BALANCE, RLS_VARY_RHO_PNP = 0, 1, 2
 RLS_DIST_UNIFORM01, RLS_DIST_IH4 = 0, 1
@@ -68,6 +68,8 @@ _P = C.c_void_p
 _I32, _I64, _U64, _F32, _F64 = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double
 _PI32, _PI64, _PF32, _PF64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(C.c_double)
 _PP = C.POINTER(C.c_void_p)
+# rls_apply_fn: int32 (*)(void* user, const void* x_dev, void* res_dev, void* cuda_stream)
+APPLY_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 
 # name -> argtypes ; every function returns int32 unless listed in _SPECIAL
 SIGNATURES = {
@@ -132,6 +134,15 @@ SIGNATURES = {
     "rls_normal_apply_batch": [_P, _I32, _PP, _PP],
     "rls_normal_batch_debug": [_P, _I32, _P, _I64],
     "rls_power_iterations": [_P, _P, _F64, _I32, _PF64],
+    "rls_linop_sampling_create": [_P, _I32, _I64, _I64, _PI64, _PP],
+    "rls_linop_fft_create": [_P, _I32, _PI64, _I32, _I32, _PP],
+    "rls_linop_compose": [_P, _P, _PP],
+    "rls_linop_destroy": [_P],
+    "rls_linop_shape": [_P, _PI64, _PI64, _PI32],
+    "rls_linop_mul": [_P, _P, _P],
+    "rls_linop_mul_adjoint": [_P, _P, _P],
+    "rls_normal_from_linop": [_P, _PP],
+    "rls_normal_from_callback": [_P, _I32, _I64, APPLY_FN, _P, _PP],
     "rls_prox_l1": [_P, _F32],
     "rls_prox_l2": [_P, _F32],
     "rls_prox_l21": [_P, _F32, _I64],

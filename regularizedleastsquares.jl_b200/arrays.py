@@ -277,14 +277,20 @@ class B200Matrix:
 
 _FORMS = {"twopass": capi.RLS_NORMAL_TWOPASS, "onepass": capi.RLS_NORMAL_ONEPASS, "gram": capi.RLS_NORMAL_GRAM,
           "auto": capi.RLS_NORMAL_AUTO, "lazy": capi.RLS_NORMAL_AUTO}
-_FORM_NAMES = {capi.RLS_NORMAL_TWOPASS: "twopass", capi.RLS_NORMAL_ONEPASS: "onepass", capi.RLS_NORMAL_GRAM: "gram"}
+_FORM_NAMES = {capi.RLS_NORMAL_TWOPASS: "twopass", capi.RLS_NORMAL_ONEPASS: "onepass", capi.RLS_NORMAL_GRAM: "gram",
+               capi.RLS_NORMAL_MATRIXFREE: "matrixfree"}
 
 
 class B200NormalOp:
-    """AHA: `normalOperator(A)` (lazy forms) or `A'*A` (Gram)."""
-    def __init__(self, A=None, form="auto", G=None):
+    """AHA: `normalOperator(A)` (lazy forms), `A'*A` (Gram), the normal operator of a matrix-free operator (`linop=`,
+    operators.py) or a callback working on device pointers (`from_callback`)."""
+    def __init__(self, A=None, form="auto", G=None, linop=None):
         h = C.c_void_p()
-        if G is not None:
+        if linop is not None:
+            self.A, self.G, self.linop = None, None, linop
+            capi.call("rls_normal_from_linop", linop.handle, C.byref(h))
+            self.ctx, self.dtype, self.n = linop.ctx, linop.dtype, linop.shape[1]
+        elif G is not None:
             self.A, self.G = None, G
             capi.call("rls_normal_from_gram", G.handle, C.byref(h))
             self.ctx, self.dtype, self.n = G.ctx, G.dtype, G.n
@@ -294,6 +300,31 @@ class B200NormalOp:
             self.ctx, self.dtype, self.n = A.ctx, A.dtype, A.n
         self.handle = h
         self._fin = weakref.finalize(self, capi.load().rls_normal_destroy, h)
+
+    @classmethod
+    def from_callback(cls, fn, dtype, n, ctx=None):
+        """AHA as a function fn(x_ptr, res_ptr, stream) -> status that enqueues res = AHA x on the CUDA stream `stream`
+        (device pointers as integers) — the hook a Julia `@cfunction` around any LinearOperator uses
+        (rls_normal_from_callback)."""
+        ctx = ctx if ctx is not None else B200Context.default()
+        self = cls.__new__(cls)
+
+        def tramp(_user, x, res, stream):
+            try:
+                r = fn(x, res, stream)
+                return int(r) if r is not None else 0
+            except Exception:          # an exception cannot cross the C frames
+                import traceback
+                traceback.print_exc()
+                return 1          # RLS_ERR_INVALID
+        self._cb = capi.APPLY_FN(tramp)
+        h = C.c_void_p()
+        capi.call("rls_normal_from_callback", ctx.handle, _DT[np.dtype(dtype)], int(n), self._cb, None, C.byref(h))
+        self.A, self.G = None, None
+        self.ctx, self.dtype, self.n = ctx, np.dtype(dtype), int(n)
+        self.handle = h
+        self._fin = weakref.finalize(self, capi.load().rls_normal_destroy, h)
+        return self
 
     @property
     def form(self):

@@ -9,7 +9,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-extended-lambda --expt-relaxed-constexpr -Xcompiler -fPIC -Xptxas -v"
 OBJS=""
 pids=()
-for f in rls_context rls_gemv rls_normal rls_normal_tma rls_rowstream rls_tc rls_p2p rls_prox rls_svt rls_kaczmarz rls_solvers rls_group; do
+for f in rls_context rls_gemv rls_normal rls_normal_tma rls_rowstream rls_tc rls_p2p rls_prox rls_svt rls_linop rls_kaczmarz rls_solvers rls_group; do
   if [ "$SRC/$f.cu" -nt "$HERE/build/$f.o" ] || [ -n "$(find "$SRC" "$HERE/../include" -name '*.cuh' -newer "$HERE/build/$f.o" -o -name '*.h' -newer "$HERE/build/$f.o" 2>/dev/null | head -1)" ] || [ ! -f "$HERE/build/$f.o" ]; then
     $NVCC $FLAGS -c "$SRC/$f.cu" -o "$HERE/build/$f.o" > "$HERE/build/$f.log" 2>&1 &
     pids+=($!)

@@ -153,6 +153,8 @@ void rls_ctx_peer_release(rls_ctx_s* c);
 int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const int* gate);
 int32_t rls_gemv_n_raw(rls_mat_s* A, const void* x, void* y, const int* gate);
 int32_t rls_gemv_c_raw(rls_mat_s* A, const void* y, void* g, const int* gate);
+int32_t rls_normal_from_function(rls_ctx_s* ctx, int32_t dtype, int64_t n, int32_t (*apply)(void*, const void*, void*, void*),
+                                 void (*release)(void*), void* user, const char* name, rls_normal_t* out);
 int32_t rls_normal_shape(rls_normal_t op, int64_t* n, int32_t* dtype);
 rls_ctx_s* rls_normal_ctx(rls_normal_t op);
 rls_mat_s* rls_normal_matrix(rls_normal_t op);

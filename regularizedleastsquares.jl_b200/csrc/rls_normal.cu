@@ -351,6 +351,13 @@ struct rls_normal_s {
   void* ws_mem = nullptr;
   int op_grid = 0, op_lpc = 0, op_maxc = 0, op_cpw = 0, op_lag = 2, op_hint = 1;
   unsigned tag_next = 1;
+  // matrix-free form (RLS_NORMAL_MATRIXFREE): res = AHA x through a function — a structured operator of rls_linop.cu or a
+  // caller-supplied callback working on device pointers on the context's stream
+  int32_t (*mf_apply)(void* user, const void* x, void* out, void* stream) = nullptr;
+  void (*mf_release)(void* user) = nullptr;   // drops what the operator holds on `user` when it goes
+  void* mf_user = nullptr;
+  rls_vec_s* mf_tmp = nullptr;                // n-vector: result of a gated apply before the gated copy
+  char mf_name[96] = {0};
   std::atomic<int> refs{1};   // the creator + every solver that borrows the operator
 };
 
@@ -545,6 +552,8 @@ void rls_normal_release(rls_normal_t op) {
     if (op->ws_mem) cudaFree(op->ws_mem);
     if (op->tma) rls_tma_plan_destroy(op->tma);
     if (op->tc) rls_tc_batch_destroy(op->tc);
+    if (op->mf_tmp) rls_vec_destroy(op->mf_tmp);
+    if (op->mf_release) op->mf_release(op->mf_user);
     delete op;
   }
   rls_mat_release(A);
@@ -560,7 +569,8 @@ extern "C" int32_t rls_normal_destroy(rls_normal_t op) {
 // human-readable description of the kernel plan behind this operator (diagnostics / bench config)
 extern "C" int32_t rls_normal_describe(rls_normal_t op, char* buf, int32_t len) {
   RLS_CHECK_ARG(op && buf && len > 0, "NULL argument");
-  if (op->form == RLS_NORMAL_ONEPASS && op->row) rls_rowpass_describe(op->row, buf, len);
+  if (op->form == RLS_NORMAL_MATRIXFREE) snprintf(buf, len, "matrix-free: %s", op->mf_name);
+  else if (op->form == RLS_NORMAL_ONEPASS && op->row) rls_rowpass_describe(op->row, buf, len);
   else if (op->row) snprintf(buf, len, "twopass/rowmajor: gemv_n + gemv_c (cluster kernels)");
   else if (op->form == RLS_NORMAL_ONEPASS && op->tma) rls_tma_describe(op->tma, buf, len);
   else if (op->form == RLS_NORMAL_ONEPASS)
@@ -596,6 +606,39 @@ extern "C" int32_t rls_normal_from_gram(rls_mat_t G, rls_normal_t* out) {
   rls_ctx_retain(op->ctx);
   *out = op;
   return RLS_OK;
+}
+
+// matrix-free AHA: apply(user, x, out, stream) must enqueue out = AHA x on `stream` (device pointers, n elements)
+int32_t rls_normal_from_function(rls_ctx_s* ctx, int32_t dtype, int64_t n, int32_t (*apply)(void*, const void*, void*, void*),
+                                 void (*release)(void*), void* user, const char* name, rls_normal_t* out) {
+  RLS_CHECK_ARG(ctx && apply && out && n >= 0, "bad argument");
+  RLS_CHECK_ARG(dtype == RLS_F32 || dtype == RLS_C32, "unsupported element type %d", dtype);
+  rls_normal_s* op = new rls_normal_s();
+  op->ctx = ctx;
+  op->A = nullptr;
+  op->ytmp = nullptr;
+  op->G = nullptr;
+  op->form = RLS_NORMAL_MATRIXFREE;
+  op->n_ = n;
+  op->dtype_ = dtype;
+  op->mf_apply = apply;
+  op->mf_release = release;
+  op->mf_user = user;
+  snprintf(op->mf_name, sizeof(op->mf_name), "%s", name ? name : "callback");
+  rls_ctx_retain(ctx);
+  RlsDeviceGuard g(ctx->device);
+  int32_t st = rls_vec_create_internal(ctx, dtype, n, &op->mf_tmp);
+  if (st != RLS_OK) { op->mf_release = nullptr; rls_normal_release(op); return st; }
+  *out = op;
+  return RLS_OK;
+}
+
+// createLinearSolver(S, A_matrix_free): AHA as a C callback (a Julia @cfunction around any LinearOperator — FFTW/CUFFT
+// plans, NFFT, Radon, ...: docs/src/literate/howto/normal_operator.jl, examples/computed_tomography.jl:23).  The callback
+// receives DEVICE pointers and the CUDA stream it must enqueue its work on; it returns 0 on success.
+extern "C" int32_t rls_normal_from_callback(rls_ctx_t ctx, int32_t dtype, int64_t n, rls_apply_fn fn, void* user, rls_normal_t* out) {
+  RLS_CHECK_ARG(ctx && fn && out, "NULL argument");
+  return rls_normal_from_function(ctx, dtype, n, fn, nullptr, user, "callback", out);
 }
 
 int32_t rls_normal_shape(rls_normal_t op, int64_t* n, int32_t* dtype) {
@@ -644,6 +687,22 @@ int32_t rls_normal_apply_raw(rls_normal_t op, const void* x, void* res, const in
   RlsNvtxRange nvtx("rls: mul!(res, AHA, x)");
   rls_ctx_s* c = op->ctx;
   if (op->form == RLS_NORMAL_GRAM) return rls_gemv_n_raw(op->G, x, res, gate);  // G already summed over ranks
+  if (op->form == RLS_NORMAL_MATRIXFREE) {
+    // the function knows nothing of the solver's done() gate: a gated apply lands in a scratch vector and is copied
+    // into res by a gated kernel, so a finished solve is never disturbed.  The operator is global (not row-sharded).
+    void* out = gate ? op->mf_tmp->d : res;
+    const int32_t st = op->mf_apply(op->mf_user, x, out, (void*)c->stream);
+    if (st != RLS_OK) {
+      if (st > RLS_ERR_NOMEM || st < 0) { rls_set_error("matrix-free normal operator: the callback returned %d", (int)st); return RLS_ERR_INVALID; }
+      return st;
+    }
+    if (gate) {
+      gated_copy_kernel<<<c->sm_count, 256, 0, c->stream>>>((float*)res, (const float*)out, op->n_ * (op->dtype_ == RLS_C32 ? 2 : 1), gate);
+      c->launches++;
+      RLS_CUDA(cudaGetLastError());
+    }
+    return RLS_OK;
+  }
   // row-sharded: kernels write this rank's partial into gpart, one sum-allreduce of the
   // n-vector over NVLink, then a (gated) copy into res.  A gated-off launch still joins the
   // collective so that ranks stay in lock-step, but never touches res.

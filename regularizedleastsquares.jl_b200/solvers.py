@@ -70,7 +70,16 @@ class AbstractLinearSolver:
     _group = False          # True: A is a B200GroupMatrix (single-process multi-device)
 
     # ---------------- construction helpers ----------------
+    _linop = None           # A is a matrix-free LinearOperator (operators.py): b is back-projected with it first
+
     def _setup(self, A, AHA, normal, ctx):
+        from .operators import LinearOperator
+        if isinstance(A, LinearOperator):
+            # matrix-free A: the solver runs on the lazy normal operator A'A through the AHA-only interface (FISTA.jl:55)
+            self._linop = A
+            AHA = A.normal() if AHA is None else AHA
+            ctx = A.ctx
+            A = None
         self._group = isinstance(A, B200GroupMatrix)
         if self._group:
             # single-process multi-device: the C library keeps one operator + solver per device behind ONE handle
@@ -196,6 +205,9 @@ class AbstractLinearSolver:
 
     # ---------------- the iterator protocol ----------------
     def _b_to_device(self, b):
+        if self._linop is not None and not getattr(self, "_in_linop_solve", False):
+            bd = b if isinstance(b, B200Vector) else B200Vector.from_numpy(np.ascontiguousarray(b, dtype=self.dtype), self.ctx)
+            return self._linop.tmul(bd)                     # init!(solver, b) on a matrix-free A: x0 = A'b
         if isinstance(b, B200Vector):
             return b
         b = np.ascontiguousarray(b, dtype=self.dtype)
@@ -228,6 +240,18 @@ class AbstractLinearSolver:
         """solve!(solver, b; x0, callbacks): RegularizedLeastSquares.jl:103-117; a matrix b runs the
         multi-right-hand-side path of MultiThreading.jl:30-80."""
         host_in = not isinstance(b, B200Vector)
+        if self._linop is not None and not getattr(self, "_in_linop_solve", False):
+            if isinstance(self.normalizeReg, MeasurementBasedNormalization):
+                raise NotImplementedError("MeasurementBasedNormalization with a matrix-free operator")
+            if host_in and np.ndim(b) != 1:
+                raise NotImplementedError("a matrix-free operator takes one right-hand side at a time")
+            bd = b if not host_in else B200Vector.from_numpy(np.ascontiguousarray(b, dtype=self.dtype), self.ctx)
+            self._in_linop_solve = True
+            try:
+                xv = self.solve_(self._linop.tmul(bd), x0=x0, callbacks=callbacks)     # solve!(solver, A'b)
+            finally:
+                self._in_linop_solve = False
+            return xv.to_numpy() if host_in else xv
         if self._group:
             if not host_in or np.ndim(b) != 1 or callbacks or not (np.isscalar(x0) and x0 == 0):
                 raise NotImplementedError("a solver on a device group takes one host vector b (no callbacks, x0 = 0)")
@@ -699,6 +723,18 @@ class Kaczmarz(AbstractLinearSolver):
 
     def solve_(self, b, x0=0, callbacks=None, scheduler=None):
         host_in = not isinstance(b, B200Vector)
+        if self._linop is not None and not getattr(self, "_in_linop_solve", False):
+            if isinstance(self.normalizeReg, MeasurementBasedNormalization):
+                raise NotImplementedError("MeasurementBasedNormalization with a matrix-free operator")
+            if host_in and np.ndim(b) != 1:
+                raise NotImplementedError("a matrix-free operator takes one right-hand side at a time")
+            bd = b if not host_in else B200Vector.from_numpy(np.ascontiguousarray(b, dtype=self.dtype), self.ctx)
+            self._in_linop_solve = True
+            try:
+                xv = self.solve_(self._linop.tmul(bd), x0=x0, callbacks=callbacks)     # solve!(solver, A'b)
+            finally:
+                self._in_linop_solve = False
+            return xv.to_numpy() if host_in else xv
         if self._group:
             if not host_in or np.ndim(b) != 1 or callbacks or not (np.isscalar(x0) and x0 == 0):
                 raise NotImplementedError("a solver on a device group takes one host vector b (no callbacks, x0 = 0)")
