@@ -32,7 +32,8 @@ end
 # ---- enums of include/rls_b200.h ----------------------------------------------------------------
 const RLS_F32, RLS_C32 = Int32(0), Int32(1)
 const RLS_FISTA, RLS_POGM, RLS_OPTISTA, RLS_CGNR, RLS_ADMM, RLS_SPLITBREGMAN = Int32.(0:5)
-const RLS_REG_NONE, RLS_REG_L1, RLS_REG_L2, RLS_REG_L21, RLS_REG_TV = Int32.(0:4)
+const RLS_REG_NONE, RLS_REG_L1, RLS_REG_L2, RLS_REG_L21, RLS_REG_TV, RLS_REG_NUCLEAR, RLS_REG_LLR = Int32.(0:6)
+const RLS_LLR_RANDSHIFT, RLS_LLR_OVERLAPPING = Int32(1), Int32(2)
 const RLS_PROJ_REAL, RLS_PROJ_POSITIVE = Int32(1), Int32(2)
 const RLS_NORMAL_AUTO = Int32(3)
 dtypecode(::Type{Float32}) = RLS_F32
@@ -158,14 +159,78 @@ function prox!(r::TVRegularization, x::B200Vector, λ::Float32)
   check(ccall((:rls_prox_tv, LIB), Int32, (Ptr{Cvoid}, Float32, Int32, Ptr{Int64}, Int32, Ptr{Int32}, Int32),
               x.handle, λ, length(shape), shape, length(dims), dims, r.iterationsTV)); x
 end
+# singular-value thresholding on the device (the reference moves GPU arrays to the CPU for these: ProxLLR.jl:7)
+function prox!(r::NuclearRegularization, x::B200Vector, λ::Float32)                 # ProxNuclear.jl:27-32
+  check(ccall((:rls_prox_nuclear, LIB), Int32, (Ptr{Cvoid}, Float32, Int64, Int64), x.handle, λ, r.svtShape[1], r.svtShape[2])); x
+end
+function prox!(r::LLRRegularization, x::B200Vector, λ::Float32)                     # ProxLLR.jl:36-38
+  shape = collect(Int64, r.shape); block = collect(Int64, r.blockSize)
+  shift = r.randshift ? Int64[rand(1:b) for b in block] : zeros(Int64, length(block))   # rand(block_idx), ProxLLR.jl:55
+  check(ccall((:rls_prox_llr, LIB), Int32, (Ptr{Cvoid}, Float32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int32),
+              x.handle, λ, length(shape), shape, block, shift, r.fullyOverlapping ? 1 : 0)); x
+end
 prox!(::PositiveRegularization, x::B200Vector) = (check(ccall((:rls_prox_positive, LIB), Int32, (Ptr{Cvoid},), x.handle)); x)
 prox!(::RealRegularization, x::B200Vector) = (check(ccall((:rls_prox_real, LIB), Int32, (Ptr{Cvoid},), x.handle)); x)
+
+# ---- matrix-free system operators (SamplingOp, FFTOp, products; compressed_sensing.jl:23) -------------
+mutable struct B200LinOp{T}
+  handle::Ptr{Cvoid}; m::Int; n::Int; keep::Any
+end
+function B200SamplingOp(::Type{T}; pattern::AbstractVector{<:Integer}, shape) where T
+  h = Ref{Ptr{Cvoid}}(); pat = collect(Int64, pattern)
+  check(ccall((:rls_linop_sampling_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Int64}, Ptr{Ptr{Cvoid}}),
+              default_ctx().handle, T <: Complex ? RLS_C32 : RLS_F32, prod(shape), length(pat), pat, h))
+  L = B200LinOp{T}(h[], length(pat), prod(shape), nothing)
+  finalizer(l -> ccall((:rls_linop_destroy, LIB), Int32, (Ptr{Cvoid},), l.handle), L)
+end
+function B200FFTOp(::Type{ComplexF32}; shape, shift::Bool = true, unitary::Bool = true)
+  h = Ref{Ptr{Cvoid}}(); shp = collect(Int64, shape)
+  check(ccall((:rls_linop_fft_create, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, Int32, Int32, Ptr{Ptr{Cvoid}}),
+              default_ctx().handle, length(shp), shp, shift, unitary, h))
+  L = B200LinOp{ComplexF32}(h[], prod(shape), prod(shape), nothing)
+  finalizer(l -> ccall((:rls_linop_destroy, LIB), Int32, (Ptr{Cvoid},), l.handle), L)
+end
+function Base.:*(A::B200LinOp{T}, B::B200LinOp{T}) where T                                 # ProdOp
+  h = Ref{Ptr{Cvoid}}()
+  check(ccall((:rls_linop_compose, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), A.handle, B.handle, h))
+  L = B200LinOp{T}(h[], A.m, B.n, (A, B))
+  finalizer(l -> ccall((:rls_linop_destroy, LIB), Int32, (Ptr{Cvoid},), l.handle), L)
+end
+LinearAlgebra.mul!(y::B200Vector, A::B200LinOp, x::B200Vector) =
+  (check(ccall((:rls_linop_mul, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), A.handle, x.handle, y.handle)); y)
+LinearAlgebra.mul!(x::B200Vector, At::Adjoint{T,B200LinOp{T}}, y::B200Vector) where T =
+  (check(ccall((:rls_linop_mul_adjoint, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), parent(At).handle, y.handle, x.handle)); x)
+# normalOperator(A) of a matrix-free A; createLinearSolver(S, A::B200LinOp; AHA = normalOperator(A)) then takes the AHA-only
+# path (rls_solver_create with A = C_NULL) and solve!(solver, A' * b)
+function LinearOperatorCollection.normalOperator(A::B200LinOp{T}) where T
+  h = Ref{Ptr{Cvoid}}()
+  check(ccall((:rls_normal_from_linop, LIB), Int32, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), A.handle, h))
+  B200NormalOp{T}(h[], A.n)
+end
+# any other LinearOperator (NFFT, Radon, wavelets on the GPU, ...): AHA as a @cfunction on device pointers + stream
+#   apply(user, x::Ptr{Cvoid}, res::Ptr{Cvoid}, stream::Ptr{Cvoid})::Int32 = (my_gpu_normal_op!(res, x, stream); Int32(0))
+#   fn = @cfunction(apply, Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}))
+function B200NormalOp(fn::Ptr{Cvoid}, ::Type{T}, n::Integer; user::Ptr{Cvoid} = C_NULL) where T
+  h = Ref{Ptr{Cvoid}}()
+  check(ccall((:rls_normal_from_callback, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
+              default_ctx().handle, T <: Complex ? RLS_C32 : RLS_F32, n, fn, user, h))
+  B200NormalOp{T}(h[], n)
+end
 
 # ---- solvers: one library-side solver object per Julia solver, keyed by objectid ---------------------
 regkind(::L1Regularization) = RLS_REG_L1; regkind(::L2Regularization) = RLS_REG_L2
 regkind(::L21Regularization) = RLS_REG_L21; regkind(::TVRegularization) = RLS_REG_TV
+regkind(::NuclearRegularization) = RLS_REG_NUCLEAR; regkind(::LLRRegularization) = RLS_REG_LLR
+pad4(T, v) = ntuple(i -> i <= length(v) ? T(collect(v)[i]) : T(0), 4)
 function regdesc(reg; rho = 0f0)
   s = sink(reg); l = λ(reg)
+  if s isa NuclearRegularization      # svtShape in tv_shape[1:2] (include/rls_b200.h, RLS_REG_NUCLEAR)
+    return RegDesc(RLS_REG_NUCLEAR, l isa Float64 ? 1 : 0, Float64(l), 1, 2, 0, pad4(Int64, s.svtShape), pad4(Int32, ()), 0, 0, Float32(rho), 0)
+  elseif s isa LLRRegularization      # shape / blockSize / flags / seed of the shift stream (RLS_REG_LLR)
+    flags = (s.randshift ? RLS_LLR_RANDSHIFT : Int32(0)) | (s.fullyOverlapping ? RLS_LLR_OVERLAPPING : Int32(0))
+    return RegDesc(RLS_REG_LLR, l isa Float64 ? 1 : 0, Float64(l), rand(Int64(1):Int64(2)^31), length(s.shape), length(s.blockSize),
+                   pad4(Int64, s.shape), pad4(Int32, s.blockSize), flags, 0, Float32(rho), 0)
+  end
   shape = s isa TVRegularization ? ntuple(i -> i <= length(s.shape) ? Int64(s.shape[i]) : Int64(0), 4) : ntuple(_ -> Int64(0), 4)
   dims = s isa TVRegularization ? ntuple(i -> i <= length(s.dims) ? Int32(collect(s.dims)[i]) : Int32(0), 4) : ntuple(_ -> Int32(0), 4)
   RegDesc(regkind(s), l isa Float64 ? 1 : 0, Float64(l), s isa L21Regularization ? s.slices : 1,

@@ -91,9 +91,11 @@ def test_solvers_on_undersampled_fourier_operator(rls, ctx, solver):
     lam = np.float32(1e-3)
     its = 60
     if solver == "CGNR":
-        kw, okw = dict(iterations=20, relTol=0.0), dict(iterations=20, relTol=0.0)
+        # the rows of a unitary DFT are orthonormal (A A' = I): CG converges in one step and the residual then decays to an
+        # exact Float32 zero (iteration 9 in the oracle), where `‖r‖/z0 <= relTol` stops at a rounding-dependent iteration
+        kw, okw = dict(iterations=4, relTol=0.0), dict(iterations=4, relTol=0.0)
         reg, oreg = rls.L2Regularization(lam), O.L2Regularization(lam)
-        its = 20
+        its = 4
     elif solver == "ADMM":
         kw, okw = dict(iterations=30, rho=0.1), dict(iterations=30, rho=0.1)
         reg, oreg = rls.L1Regularization(lam), O.L1Regularization(lam)
