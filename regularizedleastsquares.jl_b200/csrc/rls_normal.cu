@@ -347,6 +347,8 @@ struct rls_normal_s {
   bool gram_on_tensor_cores = false;
   TcBatchPlan* tc = nullptr;  // tensor-core plan of the multi-RHS apply (created on first use for a given K)
   int tc_K = 0;
+  TcBatchPlan* tc_adj = nullptr;  // Gram form: plan on A for the K back-projections A'b_k of a multi-RHS init! (tc runs on G)
+  int tc_adj_K = 0;
   OnepassWs ws{};
   void* ws_mem = nullptr;
   int op_grid = 0, op_lpc = 0, op_maxc = 0, op_cpw = 0, op_lag = 2, op_hint = 1;
@@ -552,6 +554,7 @@ void rls_normal_release(rls_normal_t op) {
     if (op->ws_mem) cudaFree(op->ws_mem);
     if (op->tma) rls_tma_plan_destroy(op->tma);
     if (op->tc) rls_tc_batch_destroy(op->tc);
+    if (op->tc_adj) rls_tc_batch_destroy(op->tc_adj);
     if (op->mf_tmp) rls_vec_destroy(op->mf_tmp);
     if (op->mf_release) op->mf_release(op->mf_user);
     delete op;
@@ -775,13 +778,16 @@ int32_t rls_normal_apply_batch_raw(rls_normal_t op, int K, const void* const* xs
 // *done = false leaves the back-projections to the caller (per-column gemv_c)
 int32_t rls_normal_adjoint_batch_raw(rls_normal_t op, int K, const void* const* bs, void* const* outs, bool* done) {
   *done = false;
-  if (!rls_env_flag("RLS_BATCH_TENSOR_CORES", true) || op->form == RLS_NORMAL_GRAM || !op->A || !rls_tc_batch_supported(op->A, K)) return RLS_OK;
-  if (op->tc && op->tc_K != K) { rls_tc_batch_destroy(op->tc); op->tc = nullptr; }
-  if (!op->tc) {
-    if (rls_tc_batch_create(op->A, K, &op->tc) != RLS_OK) { op->tc = nullptr; return RLS_OK; }
-    op->tc_K = K;
+  if (!rls_env_flag("RLS_BATCH_TENSOR_CORES", true) || !op->A || !rls_tc_batch_supported(op->A, K)) return RLS_OK;
+  // lazy forms share the plan of the batched apply; the Gram form's apply plan lives on G, so it keeps a second one on A
+  TcBatchPlan** plan = op->form == RLS_NORMAL_GRAM ? &op->tc_adj : &op->tc;
+  int* plan_K = op->form == RLS_NORMAL_GRAM ? &op->tc_adj_K : &op->tc_K;
+  if (*plan && *plan_K != K) { rls_tc_batch_destroy(*plan); *plan = nullptr; }
+  if (!*plan) {
+    if (rls_tc_batch_create(op->A, K, plan) != RLS_OK) { *plan = nullptr; return RLS_OK; }
+    *plan_K = K;
   }
-  RLS_TRY(rls_tc_batch_adjoint(op->tc, bs, outs));
+  RLS_TRY(rls_tc_batch_adjoint(*plan, bs, outs));
   *done = true;
   return RLS_OK;
 }
@@ -819,6 +825,8 @@ int32_t rls_normal_apply_deferred_raw(rls_normal_t op, const void* x, const floa
 
 int32_t rls_normal_check_abort(rls_normal_t op) {
   RLS_TRY(rls_p2p_check_abort(op->ctx));
+  if (op->tc) RLS_TRY(rls_tc_batch_check_abort(op->tc));          // multi-RHS plans: a timed-out barrier ends the GEMM, not the process
+  if (op->tc_adj) RLS_TRY(rls_tc_batch_check_abort(op->tc_adj));
   if (op->row) return rls_rowpass_check_abort(op->row);
   if (op->form != RLS_NORMAL_ONEPASS) return RLS_OK;
   if (op->tma) return rls_tma_check_abort(op->tma);

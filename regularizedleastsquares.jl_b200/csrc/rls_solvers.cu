@@ -1460,8 +1460,11 @@ extern "C" int32_t rls_solver_solve_batch_host(rls_solver_t s, const void* B_hos
       if (cudaMemcpyAsync((char*)X_host + (size_t)k * ldx * es, L.v[V_X]->d, s->n * es, cudaMemcpyDeviceToHost, s->ctx->stream) != cudaSuccess) status = RLS_ERR_CUDA;
     }
     if (status == RLS_OK && cudaStreamSynchronize(s->ctx->stream) != cudaSuccess) status = RLS_ERR_CUDA;
+    if (tr) fprintf(stderr, "[batch] K=%d: state download + D2H of X %.2f ms\n", K, ms_since(t3, now()));
   } while (0);
   if (status == RLS_ERR_CUDA) rls_set_error("CUDA error in batch solve: %s", cudaGetErrorString(cudaGetLastError()));
+  const auto t5 = now();
   rls_vec_destroy(Bd);
+  if (tr) fprintf(stderr, "[batch] K=%d: free of the device copy of B %.2f ms\n", K, ms_since(t5, now()));
   return status;
 }
