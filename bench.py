@@ -27,10 +27,35 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-if "--impl" in sys.argv and "reference" in sys.argv:
-    # torchrun exports OMP_NUM_THREADS=1 for N > 1: the CPU arm must use all host threads it can, and say how many
-    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-        os.environ[_k] = str(os.cpu_count() or 1)
+
+
+def host_threads():
+    """CPU threads this process may really use: the affinity mask, cut by a cgroup CPU quota when there is one (a BLAS pool
+    sized to os.cpu_count() inside a smaller quota runs SLOWER than one thread per granted core)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        if os.path.exists("/sys/fs/cgroup/cpu.max"):                                   # cgroup v2
+            with open("/sys/fs/cgroup/cpu.max") as f:
+                quota, period = f.read().split()[:2]
+        else:                                                                          # cgroup v1
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+                quota = f.read().strip()
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                period = f.read().strip()
+        if quota not in ("max", "-1"):
+            n = max(1, min(n, int(-(-int(quota) // int(period)))))
+    except Exception:
+        pass
+    return n
+
+
+# The CPU legs (reference arm, cpu_baseline) use every host thread they are granted and say how many: torchrun exports
+# OMP_NUM_THREADS=1 for N > 1, and an unset variable lets OpenBLAS size its pool to the machine instead of the quota.
+for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_k] = str(host_threads())
 
 import numpy as np  # noqa: E402
 
@@ -119,7 +144,7 @@ def cpu_problem(m_sub):
             idx = rows[:, None] + cols[None, :] * np.uint64(M_GLOBAL)
             A[:, j0:j0 + cols.size] = philox_values(SEED, idx, 0, 0, IH4, scale) + 1j * philox_values(SEED, idx, 0, 1, IH4, scale)
 
-        with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:   # NumPy releases the GIL inside the big array ops
+        with ThreadPoolExecutor(max_workers=host_threads()) as ex:   # NumPy releases the GIL inside the big array ops
             list(ex.map(fill, range(0, N_COLS, 128)))
         rng = np.random.default_rng(SEED)
         b = (rng.standard_normal(m_sub) + 1j * rng.standard_normal(m_sub)).astype(np.complex64)
@@ -148,7 +173,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return                                  # N > 1: rank 0 alone runs the CPU arm
-    cores = os.cpu_count()
+    cores = host_threads()
     m_sub = 4096                                # 2.1 GB of the 137.4 GB: the gemv pair is DRAM-bound, i.e. linear in m
     scale_to_full = m_sub / M_GLOBAL
     t_gen = time.perf_counter()
@@ -382,7 +407,7 @@ def run_b200(args):
         threads = blas_threads()
         cpu = {"value": k / dts * m_sub / M_GLOBAL, "unit": "iterations/s", "cores": threads, "kind": "port",
                "sample": f"{k} FISTA-L1 iterations of the oracle loop (NumPy + OpenBLAS cgemv pair, {threads} BLAS threads on "
-                         f"{os.cpu_count()} host cores) in {dts:.1f} s on rows 0..{m_sub - 1} of the same Philox matrix "
+                         f"{host_threads()} usable host cores of {os.cpu_count()}) in {dts:.1f} s on rows 0..{m_sub - 1} of the same Philox matrix "
                          f"({m_sub}x{N_COLS} ComplexF32); iterations/s scaled by {m_sub}/{M_GLOBAL} to the full system (DRAM-bound, "
                          "linear in m); restated reference — Julia is not installed"}
     if rank == 0:
