@@ -64,3 +64,29 @@ if want("kaczmarz"):
     Ad = rls.B200Matrix.from_numpy(A, ctx=ctx, layout="row")
     x = rls.solve_(rls.Kaczmarz(Ad, reg=rls.L2Regularization(np.float32(1e-2)), iterations=2), b)
     print("kaczmarz ok", flush=True)
+
+if want("svt"):
+    # singular-value thresholding (rls_svt.cu): both views (short side = columns / rows), q up to 64, LLR patches with a
+    # shift, border patches and the fully overlapping variant; Gram-form batched apply on the tensor cores
+    for dtype in (np.float32, np.complex64):
+        for shp in ((70, 9), (9, 70), (130, 64)):
+            x = rand_vector(dtype, shp[0] * shp[1], 50)
+            rls.prox_(rls.NuclearRegularization(np.float32(3.0), svtShape=shp), x.copy())
+        x = rand_vector(dtype, 9 * 7 * 5, 51)
+        rls.prox_(rls.LLRRegularization(np.float32(0.8), shape=(9, 7), blockSize=(4, 4), randshift=False), x.copy(), shift=(1, 3))
+        x = rand_vector(dtype, 8 * 8 * 70, 52)
+        rls.prox_(rls.LLRRegularization(np.float32(0.8), shape=(8, 8), blockSize=(2, 2), randshift=False, fullyOverlapping=True), x.copy())
+    os.environ["RLS_BATCH_MIN_K"] = "2"
+    A, _ = rand_matrix(np.complex64, 200, 128, 53)
+    G = rls.B200NormalOp(rls.B200Matrix.from_numpy(A, ctx=ctx, layout="row"), form="gram")
+    xs = [rls.B200Vector.from_numpy(rand_vector(np.complex64, 128, 60 + k), ctx) for k in range(5)]
+    G.apply_batch(xs)
+    print("svt + gram batch ok", flush=True)
+
+if want("linop"):
+    N = 96
+    idx = np.arange(1, N * N + 1)[::3]
+    op = rls.SamplingOp(np.complex64, pattern=idx, shape=(N, N), ctx=ctx) * rls.FFTOp(np.complex64, shape=(N, N), ctx=ctx)
+    b = rand_vector(np.complex64, idx.size, 70)
+    rls.solve_(rls.FISTA(op, reg=rls.TVRegularization(np.float32(1e-2), shape=(N, N)), iterations=3, rho=np.float32(0.9), relTol=0.0), b)
+    print("linop ok", flush=True)
