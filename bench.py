@@ -279,16 +279,19 @@ def run_b200(args):
             x1_f = rls.solve_(rls.FISTA(Af, reg=rls.L1Regularization(LAMBDA), iterations=20, rho=rho_t, relTol=0.0, ctx=solo), bf)
             x1_c = rls.solve_(rls.CGNR(Af, reg=rls.L2Regularization(LAMBDA), iterations=10, relTol=0.0, ctx=solo), bf)
             rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
-            # noise floor: the same single-GPU solve with the two-sweep form of A'(A x) — another order of the same sums
+            # noise floor: the same single-GPU solve on the COLUMN-major copy (two-sweep gemv kernels) — other kernels, another
+            # order of the same sums, no sharding involved
             try:
-                floor = rel(rls.solve_(rls.FISTA(Af, reg=rls.L1Regularization(LAMBDA), iterations=20, rho=rho_t, relTol=0.0,
+                Ac = rls.B200Matrix.philox(dt, TWIN_M, N_COLS, seed=SEED + 1, scale=sc, ctx=solo, layout="col")
+                floor = rel(rls.solve_(rls.FISTA(Ac, reg=rls.L1Regularization(LAMBDA), iterations=20, rho=rho_t, relTol=0.0,
                                                  normal="twopass", ctx=solo), bf), x1_f)
+                del Ac
             except Exception as e:                                  # informative only
                 floor = f"not measured: {e}"
             f_rel, c_rel = rel(xs_f, x1_f), rel(xs_c, x1_c)
             parity = {"twin": f"{TWIN_M}x{N_COLS} ComplexF32, row-sharded over {world} GPUs vs the same system on one GPU",
                       "fista_l1_20_iterations_rel_l2": f_rel, "cgnr_10_iterations_rel_l2": c_rel,
-                      "single_gpu_onepass_vs_twosweep_fista_rel_l2": floor, "tolerance": TWIN_TOL,
+                      "single_gpu_rowmajor_onepass_vs_colmajor_twosweep_fista_rel_l2": floor, "tolerance": TWIN_TOL,
                       "tolerance_is": "2 x 1e-5: the sharded and the single-GPU solve are two Float32 renderings of the same "
                                       "iteration that differ only in the order of the row sums (N partial vectors added by the "
                                       "all-reduce); each is held to 1e-5 against the oracle by tests/test_gpu_configs.py, so "
