@@ -156,6 +156,7 @@ int32_t rls_gemv_c_raw(rls_mat_s* A, const void* y, void* g, const int* gate);
 int32_t rls_normal_from_function(rls_ctx_s* ctx, int32_t dtype, int64_t n, int32_t (*apply)(void*, const void*, void*, void*),
                                  void (*release)(void*), void* user, const char* name, rls_normal_t* out);
 int32_t rls_normal_shape(rls_normal_t op, int64_t* n, int32_t* dtype);
+bool rls_normal_graph_safe(rls_normal_t op);   // the apply is a fixed sequence of plain kernel launches (stream capture)
 rls_ctx_s* rls_normal_ctx(rls_normal_t op);
 rls_mat_s* rls_normal_matrix(rls_normal_t op);
 int32_t rls_normal_check_abort(rls_normal_t op);
@@ -206,6 +207,7 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 bool rls_pdl_enabled();
+void rls_pdl_suppress(bool on);
 // RLS_TRACE_EVENTS=1: CUDA events around selected launches, dumped (durations and gaps, ms) by rls_trace_dump()
 bool rls_trace_enabled();
 void rls_trace_begin(cudaStream_t st, const char* name);

@@ -89,10 +89,12 @@ bool rls_env_flag(const char* name, bool dflt) {
   return (e && *e) ? atoi(e) != 0 : dflt;
 }
 
+static thread_local int rls_pdl_suppressed = 0;
+void rls_pdl_suppress(bool on) { rls_pdl_suppressed += on ? 1 : -1; }   // stream capture: plain (fully serialising) graph edges
 bool rls_pdl_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("RLS_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }
-  return on != 0;
+  return on != 0 && rls_pdl_suppressed == 0;
 }
 extern "C" int32_t rls_abi_version(void) { return RLS_B200_ABI_VERSION; }
 

@@ -652,6 +652,15 @@ int32_t rls_normal_shape(rls_normal_t op, int64_t* n, int32_t* dtype) {
 
 rls_mat_s* rls_normal_matrix(rls_normal_t op) { return op->A; }
 
+// May the applies of this operator be recorded into a CUDA graph?  Yes for the column-major two-sweep form and the Gram
+// form on one rank (plain kernels whose arguments do not change from launch to launch); no for the L2-lag one-pass kernel
+// (its exchange tags advance per launch), callbacks (anything may happen inside) and row shards (collectives).
+bool rls_normal_graph_safe(rls_normal_t op) {
+  if (!op || op->ctx->nranks > 1 || op->row || op->tma) return false;
+  if (op->form == RLS_NORMAL_GRAM) return op->G != nullptr;
+  return op->form == RLS_NORMAL_TWOPASS && op->A && op->A->layout == RLS_LAYOUT_COLMAJOR;
+}
+
 rls_ctx_s* rls_normal_ctx(rls_normal_t op) { return op->ctx; }
 
 static int32_t launch_onepass(rls_normal_s* op, const void* x, void* res, const int* gate) {

@@ -592,6 +592,14 @@ struct rls_solver_s {
   std::vector<void*> batch_res;
   std::vector<const int*> batch_gate;
   rls_vec_s* b_dev = nullptr;      // staging for host b
+  // L2-resident systems are launch-latency bound (C1: five kernels per CGNR iteration, 2.7 us per boundary): the fixed
+  // launch sequence of a callback-free solve! — every kernel is gated on the device-side done() flag — is recorded into a
+  // CUDA graph on the second solve and replayed by ONE launch afterwards
+  cudaGraphExec_t graph = nullptr;
+  int64_t graph_launches = 0;      // kernels inside the graph (added to ctx->launches at every replay)
+  const void* graph_scratch = nullptr;  // context scratch pointer baked into the recorded gemv launches
+  bool graph_off = false;          // capture failed once: stay on the plain path
+  int plain_solves = 0;            // solves enqueued launch by launch so far (the first one allocates scratch: not capturable)
   void* pin_b = nullptr;
   void* pin_x = nullptr;
   size_t pin_b_bytes = 0, pin_x_bytes = 0;
@@ -1156,6 +1164,7 @@ extern "C" int32_t rls_solver_destroy(rls_solver_t s) {
   RlsDeviceGuard g(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
   for (Lane& L : s->lanes) free_lane(L);
+  if (s->graph) cudaGraphExecDestroy(s->graph);
   rls_tv_work_free(&s->tv);
   if (s->b_dev) rls_vec_destroy(s->b_dev);
   if (s->pin_b) cudaFreeHost(s->pin_b);
@@ -1231,11 +1240,64 @@ extern "C" int32_t rls_solver_iterate(rls_solver_t s, int32_t* advanced, rls_sol
   return RLS_OK;
 }
 
-static int32_t run_lane_async(rls_solver_s* s, Lane& L, int already_done) {
-  const int cap = iteration_cap(s->desc, s->n);
-  for (int it = already_done; it < cap; ++it) RLS_TRY(enqueue_iteration(s, L));
+// CUDA-graph replay of the iteration loop.  Eligible: CGNR (no host-side buffer rotation between iterations) on one rank
+// with an operator whose applies are plain launches, a system small enough to be latency-bound, RLS_SOLVE_GRAPH != 0.
+static bool graph_eligible(rls_solver_s* s) {
+  if (s->graph_off || s->desc.kind != RLS_CGNR || s->ctx->nranks > 1 || s->lanes.size() != 1) return false;
+  if (!rls_env_flag("RLS_SOLVE_GRAPH", true) || rls_trace_enabled() || !rls_normal_graph_safe(s->AHA)) return false;
+  const double bytes = (double)(s->A ? s->A->m : s->n) * (double)s->n * (double)rls_elem_size(s->dtype);
+  return bytes <= 512.0 * 1024 * 1024;
+}
+
+static void graph_drop(rls_solver_s* s) {
+  if (s->graph) cudaGraphExecDestroy(s->graph);
+  s->graph = nullptr;
+}
+
+static int32_t enqueue_all_iterations(rls_solver_s* s, Lane& L, int from, int cap) {
+  for (int it = from; it < cap; ++it) RLS_TRY(enqueue_iteration(s, L));
   if (s->desc.kind == RLS_CGNR && s->desc.proj_mask)
     RLS_TRY(rls_proj_launch(s->ctx, s->dtype, L.v[V_X]->d, s->n, s->desc.proj_mask, nullptr));
+  return RLS_OK;
+}
+
+static int32_t capture_iterations(rls_solver_s* s, Lane& L, int cap) {
+  rls_ctx_s* c = s->ctx;
+  const int64_t l0 = c->launches;
+  if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return RLS_ERR_UNSUPPORTED; }
+  rls_pdl_suppress(true);
+  const int32_t status = enqueue_all_iterations(s, L, 0, cap);
+  rls_pdl_suppress(false);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(c->stream, &g);       // always: a stream must not be left capturing
+  const int64_t recorded = c->launches - l0;
+  c->launches = l0;
+  if (status != RLS_OK || e != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    return RLS_ERR_UNSUPPORTED;
+  }
+  const cudaError_t ei = cudaGraphInstantiate(&s->graph, g, 0);
+  cudaGraphDestroy(g);
+  if (ei != cudaSuccess) { cudaGetLastError(); s->graph = nullptr; return RLS_ERR_UNSUPPORTED; }
+  s->graph_launches = recorded;
+  s->graph_scratch = c->gemv_scratch;
+  return RLS_OK;
+}
+
+static int32_t run_lane_async(rls_solver_s* s, Lane& L, int already_done) {
+  const int cap = iteration_cap(s->desc, s->n);
+  if (already_done == 0 && cap > 0 && s->plain_solves >= 1 && graph_eligible(s)) {
+    if (s->graph && s->graph_scratch != s->ctx->gemv_scratch) graph_drop(s);   // another operator grew the shared scratch
+    if (!s->graph && capture_iterations(s, L, cap) != RLS_OK) { s->graph_off = true; s->graph = nullptr; }
+    if (s->graph) {
+      RLS_CUDA(cudaGraphLaunch(s->graph, s->ctx->stream));
+      s->ctx->launches += s->graph_launches;
+      return RLS_OK;
+    }
+  }
+  RLS_TRY(enqueue_all_iterations(s, L, already_done, cap));
+  if (already_done == 0) s->plain_solves++;
   return RLS_OK;
 }
 

@@ -411,6 +411,41 @@ def test_multi_rhs_more_columns_than_one_gemm_tile(rls, ctx):
         assert np.array_equal(Xb[:, k], rls.solve_(S, B[:, k].copy()))
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("form", ["twopass", "gram"])
+def test_cgnr_whole_solve_graph_replay(rls, ctx, dtype, form, monkeypatch):
+    """L2-resident systems are launch-latency bound (C1): from the second callback-free solve! on, the fixed launch
+    sequence of a CGNR solve (every kernel gated on the device-side done() flag) is replayed from a CUDA graph.  Replays
+    must be bit-identical to the launch-by-launch path for every right-hand side, including solves that stop early."""
+    m, n = 96, 256
+    A, _, _ = problem(dtype, m, n)
+    Ad = rls.B200Matrix.from_numpy(A, ctx, layout="col")
+    bs = [(A @ sparse_truth(dtype, n, 700 + k, every=5 + k)).astype(dtype) for k in range(4)]
+    bs.append(np.zeros(m, dtype) + dtype(1e-3))
+    kw = dict(reg=rls.L2Regularization(np.float32(1e-3)), iterations=25, relTol=np.float32(1e-4), normal=form)
+    monkeypatch.setenv("RLS_SOLVE_GRAPH", "0")
+    S0 = rls.CGNR(Ad, **kw)
+    ref = [(rls.solve_(S0, b).copy(), S0.iteration) for b in bs]
+    monkeypatch.setenv("RLS_SOLVE_GRAPH", "1")
+    S1 = rls.CGNR(Ad, **kw)
+    l0 = ctx.launch_count()
+    x_first = rls.solve_(S1, bs[0])
+    per_solve = ctx.launch_count() - l0                       # launch by launch (also sizes the scratch buffers)
+    for rep in range(2):
+        for b, (xr, itr) in zip(bs, ref):
+            l0 = ctx.launch_count()
+            x = rls.solve_(S1, b)                              # recorded on the first pass of this loop, replayed afterwards
+            assert np.array_equal(x, xr) and S1.iteration == itr, (rep, itr, S1.iteration)
+            assert ctx.launch_count() - l0 == per_solve        # the kernels inside the graph are counted
+    assert np.array_equal(x_first, ref[0][0])
+    assert len({itr for _, itr in ref}) > 1, "the right-hand sides were meant to stop at different iterations"
+    # stepping through init! / iterate afterwards still works (no graph involved) and lands on the same iterates
+    S1.init_(bs[1])
+    while S1.iterate():
+        pass
+    assert np.array_equal(S1.x, ref[1][0])
+
+
 # ---------------------------------------------------------------- row-major device layout (one-pass cluster kernel)
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("solver,kw", [("FISTA", dict(restart="none")), ("FISTA", dict(restart="gradient")),

@@ -53,11 +53,16 @@ def c1():
     A = rls.B200Matrix.philox(np.complex64, m, n, seed=12345, dist=0, ctx=ctx)
     xt = rls.B200Vector(ctx, np.complex64, n).fill_philox(12345, stream=5, dist=0)
     b = A.mul(xt)
-    S = rls.CGNR(A, reg=rls.L2Regularization(np.float32(1e-3)), iterations=its, relTol=0.0)
-    ms, done = timed_solve(S, b, 20)
-    emit({"config": "C1 CGNR + L2, ComplexF32 1024x4096, 50 iterations (L2-resident, latency-bound)", "iterations": done,
-          "ms_per_solve": ms, "us_per_iteration": 1e3 * ms / its, "iterations_per_s": its / ms * 1e3,
-          "note": "33.6 MB of A stays in L2; per-iteration time is launch/latency, not HBM"})
+    for graph in ("1", "0"):
+        os.environ["RLS_SOLVE_GRAPH"] = graph
+        S = rls.CGNR(A, reg=rls.L2Regularization(np.float32(1e-3)), iterations=its, relTol=0.0)
+        timed_solve(S, b, 2)                                   # first solve launch by launch, second one records the graph
+        ms, done = timed_solve(S, b, 20)
+        emit({"config": "C1 CGNR + L2, ComplexF32 1024x4096, 50 iterations (L2-resident, latency-bound)", "iterations": done,
+              "whole_solve_cuda_graph": graph == "1", "ms_per_solve": ms, "us_per_iteration": 1e3 * ms / its,
+              "iterations_per_s": its / ms * 1e3, "normal_operator": S.AHA.describe(),
+              "note": "33.6 MB of A stays in L2; per-iteration time is launch/latency, not HBM; ms_per_solve includes init! (A'b)"})
+    os.environ.pop("RLS_SOLVE_GRAPH")
 
 
 def c3():
