@@ -354,6 +354,255 @@ __global__ void __launch_bounds__(EB) cgnr_p_kernel(T* __restrict__ p, const T* 
   grid_reduce_finalize<1, EB>(acc, partials, ticket, [=](double* t) { scalar_step(S, STEP_CGNR_POST, 0, t); });
 }
 
+
+// ================================ CGNR: one cooperative kernel per solve ==============================================
+// L2-resident systems (BASELINE config C1: 1024 x 4096 ComplexF32 = 33.6 MB) spend a CGNR iteration in five dependent kernels:
+// two sweeps over the matrix and three grid reductions whose results steer the next kernel (p.v -> alpha; r.r -> beta;
+// |p|^2), 30 us per iteration even when the whole launch sequence is replayed from a CUDA graph (profiles/r02_c1_latency.txt).
+// Here the whole solve! (CGNR.jl:143-185, every iteration until done()) is ONE cooperative launch: CTA c owns the columns
+// [c*CN, (c+1)*CN) of the column-major A for the whole solve, and with them the entries p_j, x_j, r_j, v_j of the
+// n-vectors (shared memory); per iteration
+//   A  y_c = sum_{j own} A[:,j] p_j           partial m-vector of this CTA -> global          | grid barrier
+//   B  y[i] = sum_c y_c[i]                     rows dealt out to the CTAs, fixed order         | grid barrier
+//   C  v_j = A[:,j]' y  (own columns);  partials of p.v and |p|^2                             | grid barrier
+//   D  alpha (every CTA, same fixed-order sum => bit-identical);  x_j += alpha p_j,  r_j -= alpha v_j (- lambda alpha p_j);
+//      partial |r|^2                                                                         | grid barrier
+//   E  beta, iteration += 1, done();  p_j = beta p_j + r_j
+// i.e. four grid-wide exchanges per iteration and two sweeps over the L2-resident matrix.  The scalar recurrences are
+// the SAME device code as the chained path (scalar_step: Float32, individually rounded, complex Smith division), evaluated
+// redundantly by every CTA on a private copy of the DevState; CTA 0 writes the state back at the end.  The element updates are
+// those of cgnr_update_kernel / cgnr_p_kernel.  What differs from the chained path is only the order of the sums inside
+// A p, A' y and the three dot products (per CTA, then over the CTAs), i.e. rounding of the size the parity bound allows.
+// The grid barrier is a monotone counter in global memory (cooperative launch guarantees co-residency); every wait is
+// bounded (abort flag -> RLS_ERR_CUDA).
+constexpr int PK_THREADS = 1024;
+constexpr int PK_MAXROWS = 4;      // rows per thread: m <= 4096
+constexpr int PK_MAXCN = 64;       // columns per CTA
+
+struct PkArgs {
+  const void* A; int64_t ld; int m, n, CN;
+  void *x, *r, *p, *v;            // n-vectors of the lane (V_X, V_X0, V_P, V_V)
+  DevState* S;
+  void* ypart;                    // [grid][m]
+  void* y;                        // [m]
+  double* dpart;                  // [2][grid][4]
+  unsigned* bar;                  // monotone barrier counter (zeroed before the launch)
+  int* abort_flag;
+  int cap;
+};
+
+__device__ __forceinline__ void pk_barrier(unsigned* bar, unsigned& target, int* abort_flag, volatile int* s_abort) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const long long t0 = clock64();
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (clock64() - t0 > 2000000000ll) { *s_abort = 1; atomicExch(abort_flag, 1); break; }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <typename T> __device__ __forceinline__ T pk_ldcg(const T* p);
+template <> __device__ __forceinline__ float pk_ldcg<float>(const float* p) { return __ldcg(p); }
+template <> __device__ __forceinline__ float2 pk_ldcg<float2>(const float2* p) { return __ldcg(p); }
+// FMA-contracted multiply-accumulate for the matrix sweeps (as a BLAS gemv would)
+__device__ __forceinline__ void pk_fma(float& acc, float a, float b) { acc = fmaf(a, b, acc); }
+__device__ __forceinline__ void pk_fma(float2& acc, float2 a, float2 b) {          // acc += a*b
+  acc.x = fmaf(a.x, b.x, fmaf(-a.y, b.y, acc.x));
+  acc.y = fmaf(a.x, b.y, fmaf(a.y, b.x, acc.y));
+}
+__device__ __forceinline__ void pk_fmac(float& acc, float a, float b) { acc = fmaf(a, b, acc); }
+__device__ __forceinline__ void pk_fmac(float2& acc, float2 a, float2 b) {         // acc += conj(a)*b
+  acc.x = fmaf(a.x, b.x, fmaf(a.y, b.y, acc.x));
+  acc.y = fmaf(a.x, b.y, fmaf(-a.y, b.x, acc.y));
+}
+__device__ __forceinline__ float pk_shfl(float v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ float2 pk_shfl(float2 v, int o) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o));
+}
+template <typename T> __device__ __forceinline__ T pk_plain_add(T a, T b);
+template <> __device__ __forceinline__ float pk_plain_add<float>(float a, float b) { return a + b; }
+template <> __device__ __forceinline__ float2 pk_plain_add<float2>(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+
+// fixed-order sum over the CTAs of NV doubles per CTA (dpart[c*4 + k]); every thread of warp 0 returns the totals
+template <int NV>
+__device__ __forceinline__ void pk_total(const double* dpart, double (&t)[NV]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double a = 0.0;
+    for (unsigned c = lane; c < gridDim.x; c += 32) a += __ldcg(&dpart[(size_t)c * 4 + k]);
+    t[k] = warp_sum(a);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(PK_THREADS, 1) cgnr_persistent_kernel(PkArgs a) {
+  extern __shared__ __align__(16) unsigned char pk_smem[];
+  __shared__ DevState Sl;
+  __shared__ int s_abort;
+  T* ys = reinterpret_cast<T*>(pk_smem);          // [m]
+  T* ps = ys + a.m;                                // [CN] each: p, x, r, v of the own columns
+  T* xs = ps + a.CN;
+  T* rs = xs + a.CN;
+  T* vs = rs + a.CN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = blockIdx.x, P = gridDim.x;
+  const int j0 = c * a.CN;
+  const int nown = max(0, min(a.CN, a.n - j0));
+  const T* A = reinterpret_cast<const T*>(a.A);
+  T* ypart = reinterpret_cast<T*>(a.ypart);
+  T* yg = reinterpret_cast<T*>(a.y);
+  unsigned target = 0;
+  constexpr bool cplx = Elem<T>::is_complex;
+
+  if (tid == 0) { Sl = *a.S; s_abort = 0; }
+  for (int j = tid; j < nown; j += PK_THREADS) {
+    ps[j] = reinterpret_cast<const T*>(a.p)[j0 + j];
+    xs[j] = reinterpret_cast<const T*>(a.x)[j0 + j];
+    rs[j] = reinterpret_cast<const T*>(a.r)[j0 + j];
+    vs[j] = reinterpret_cast<const T*>(a.v)[j0 + j];
+  }
+  __syncthreads();
+  const int RM = (a.m + P - 1) / P;                // rows of y this CTA reduces in phase B
+
+  for (int it = 0; it < a.cap; ++it) {
+    if (Sl.done || s_abort) break;                 // identical in every CTA: same state, same arithmetic
+    // ---- A: partial y over the own columns -----------------------------------------------------------------------
+    {
+      T acc[PK_MAXROWS];
+#pragma unroll
+      for (int q = 0; q < PK_MAXROWS; ++q) acc[q] = Elem<T>::zero();
+#pragma unroll 4
+      for (int j = 0; j < nown; ++j) {
+        const T pj = ps[j];
+        const T* col = A + (int64_t)(j0 + j) * a.ld;
+#pragma unroll
+        for (int q = 0; q < PK_MAXROWS; ++q) {
+          const int i = tid + q * PK_THREADS;
+          if (i < a.m) pk_fma(acc[q], __ldg(col + i), pj);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < PK_MAXROWS; ++q) {
+        const int i = tid + q * PK_THREADS;
+        if (i < a.m) ypart[(size_t)c * a.m + i] = acc[q];
+      }
+    }
+    pk_barrier(a.bar, target, a.abort_flag, &s_abort);
+    // ---- B: y rows [c*RM, (c+1)*RM): one warp per row, partials added in CTA order ----------------------------------
+    for (int rr_ = warp; rr_ < RM; rr_ += PK_THREADS / 32) {
+      const int i = c * RM + rr_;
+      if (i < a.m) {
+        T sacc = Elem<T>::zero();
+        for (int cc = lane; cc < P; cc += 32) sacc = pk_plain_add(sacc, pk_ldcg(ypart + (size_t)cc * a.m + i));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc = pk_plain_add(sacc, pk_shfl(sacc, o));
+        if (lane == 0) yg[i] = sacc;
+      }
+    }
+    pk_barrier(a.bar, target, a.abort_flag, &s_abort);
+    // ---- C: v_j = A[:,j]' y for the own columns; partials of p.v and |p|^2 -----------------------------------------
+    for (int i = tid; i < a.m; i += PK_THREADS) ys[i] = pk_ldcg(yg + i);
+    __syncthreads();
+    for (int j = warp; j < nown; j += PK_THREADS / 32) {
+      const T* col = A + (int64_t)(j0 + j) * a.ld;
+      T sacc = Elem<T>::zero();
+#pragma unroll 8
+      for (int i = lane; i < a.m; i += 32) pk_fmac(sacc, __ldg(col + i), ys[i]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sacc = pk_plain_add(sacc, pk_shfl(sacc, o));
+      if (lane == 0) vs[j] = sacc;
+    }
+    __syncthreads();
+    double* dp = a.dpart + (size_t)(it & 1) * P * 4;
+    if (warp == 0) {
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+      for (int j = lane; j < nown; j += 32) {
+        Elem<T>::dotc(ps[j], vs[j], d0, d1);                               // dot(pl, vl)   CGNR.jl:154
+        d2 += Elem<T>::abs2(ps[j]);
+      }
+      d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
+      if (lane == 0) { dp[c * 4 + 0] = d0; dp[c * 4 + 1] = d1; dp[c * 4 + 2] = d2; }
+    }
+    pk_barrier(a.bar, target, a.abort_flag, &s_abort);
+    // ---- D: alpha; x, r update on the own columns; partial |r|^2 ---------------------------------------------------
+    if (warp == 0) {
+      double t[3];
+      pk_total<3>(dp, t);
+      if (lane == 0) {
+        Sl.pp = t[2];
+        scalar_step(&Sl, STEP_CGNR_ALPHA, cplx ? 1 : 0, t);
+      }
+    }
+    __syncthreads();
+    double* dq = a.dpart + (size_t)(2 + (it & 1)) * P * 4;
+    {
+      const T al = scal<T>(Sl.cg_alpha);
+      const T nal = negs(al);
+      const bool lam_pos = Sl.lam_is_f64[0] ? (Sl.lam64[0] > 0.0) : (Sl.lam[0] > 0.f);
+      const float lam = Sl.lam_is_f64[0] ? (float)Sl.lam64[0] : Sl.lam[0];
+      double racc = 0.0;
+      if (warp == 0) {
+        for (int j = lane; j < nown; j += 32) {
+          const T pv = ps[j];
+          xs[j] = Elem<T>::add(xs[j], cmul(pv, al));                       // x += p*α          :163
+          T rv = Elem<T>::add(rs[j], cmul(vs[j], nal));                    // x₀ += v*(-α)      :165
+          if (lam_pos) rv = Elem<T>::add(rv, cmul(Elem<T>::scale(pv, -lam), al));  // x₀ += (p*-λ)*α :168
+          rs[j] = rv;
+          racc += Elem<T>::abs2(rv);
+        }
+        racc = warp_sum(racc);
+        if (lane == 0) dq[c * 4 + 0] = racc;
+      }
+    }
+    pk_barrier(a.bar, target, a.abort_flag, &s_abort);
+    // ---- E: beta, iteration count, done(); p update ------------------------------------------------------------------
+    if (warp == 0) {
+      double t[1];
+      pk_total<1>(dq, t);
+      if (lane == 0) {
+        scalar_step(&Sl, STEP_CGNR_BETA, cplx ? 1 : 0, t);
+        double keep = Sl.pp;                                               // |p|^2 of the new p is summed with the next p.v
+        scalar_step(&Sl, STEP_CGNR_POST, 0, &keep);
+      }
+    }
+    __syncthreads();
+    {
+      const T be = scal<T>(Sl.cg_beta);
+      for (int j = tid; j < nown; j += PK_THREADS) ps[j] = Elem<T>::add(cmul(ps[j], be), rs[j]);   // rmul!(pl, β); pl += x₀ :173-174
+    }
+    __syncthreads();
+  }
+  // ---- write back: vectors of the own columns, |p|^2 of the final p, the state --------------------------------------
+  for (int j = tid; j < nown; j += PK_THREADS) {
+    reinterpret_cast<T*>(a.p)[j0 + j] = ps[j];
+    reinterpret_cast<T*>(a.x)[j0 + j] = xs[j];
+    reinterpret_cast<T*>(a.r)[j0 + j] = rs[j];
+    reinterpret_cast<T*>(a.v)[j0 + j] = vs[j];
+  }
+  double* df = a.dpart + (size_t)4 * P * 4;
+  if (warp == 0) {
+    double d2 = 0.0;
+    for (int j = lane; j < nown; j += 32) d2 += Elem<T>::abs2(ps[j]);
+    d2 = warp_sum(d2);
+    if (lane == 0) df[c * 4 + 0] = d2;
+  }
+  pk_barrier(a.bar, target, a.abort_flag, &s_abort);
+  if (c == 0 && warp == 0) {
+    double t[1];
+    pk_total<1>(df, t);
+    if (lane == 0) { Sl.pp = t[0]; *a.S = Sl; }
+  }
+}
+
 // ================================ ADMM ===============================================
 // β = (first ? β_y : β); β = ρ z + β; β = (-ρ) u + β        (identity regTrafo)  ADMM.jl:236-241
 template <typename T>
@@ -600,6 +849,10 @@ struct rls_solver_s {
   const void* graph_scratch = nullptr;  // context scratch pointer baked into the recorded gemv launches
   bool graph_off = false;          // capture failed once: stay on the plain path
   int plain_solves = 0;            // solves enqueued launch by launch so far (the first one allocates scratch: not capturable)
+  // one cooperative kernel per CGNR solve (cgnr_persistent_kernel, RLS_CGNR_PERSISTENT=1): exchange buffers
+  void* pk_mem = nullptr;
+  size_t pk_bytes = 0;
+  bool pk_off = false, pk_used = false;
   void* pin_b = nullptr;
   void* pin_x = nullptr;
   size_t pin_b_bytes = 0, pin_x_bytes = 0;
@@ -688,6 +941,12 @@ static int32_t pull_state(rls_solver_s* s, Lane& L) {
   RLS_CUDA(cudaMemcpyAsync(L.hS, L.dS, sizeof(DevState), cudaMemcpyDeviceToHost, s->ctx->stream));
   RLS_CUDA(cudaStreamSynchronize(s->ctx->stream));
   RLS_CUDA(cudaGetLastError());
+  if (s->pk_used) {                 // the cooperative whole-solve kernel ran: a timed-out grid barrier sets its abort flag
+    s->pk_used = false;
+    int flag = 0;
+    RLS_CUDA(cudaMemcpy(&flag, (char*)s->pk_mem + s->pk_bytes - 8, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) { s->pk_off = true; rls_set_error("CGNR whole-solve kernel timed out on a grid barrier (abort flag set)"); return RLS_ERR_CUDA; }
+  }
   return rls_normal_check_abort(s->AHA);
 }
 
@@ -1165,6 +1424,7 @@ extern "C" int32_t rls_solver_destroy(rls_solver_t s) {
   cudaStreamSynchronize(s->ctx->stream);
   for (Lane& L : s->lanes) free_lane(L);
   if (s->graph) cudaGraphExecDestroy(s->graph);
+  if (s->pk_mem) cudaFree(s->pk_mem);
   rls_tv_work_free(&s->tv);
   if (s->b_dev) rls_vec_destroy(s->b_dev);
   if (s->pin_b) cudaFreeHost(s->pin_b);
@@ -1285,8 +1545,72 @@ static int32_t capture_iterations(rls_solver_s* s, Lane& L, int cap) {
   return RLS_OK;
 }
 
+// ONE cooperative kernel for the whole CGNR solve of an L2-resident column-major system (cgnr_persistent_kernel above).
+// Opt-in (RLS_CGNR_PERSISTENT=1): its sums run in another order than the chained kernels', so iterates agree with them to
+// rounding, not bit for bit.
+static bool persistent_eligible(rls_solver_s* s) {
+  if (s->pk_off || s->desc.kind != RLS_CGNR || s->ctx->nranks > 1 || s->lanes.size() != 1) return false;
+  if (!rls_env_flag("RLS_CGNR_PERSISTENT", false) || rls_trace_enabled()) return false;
+  rls_mat_s* A = s->A;
+  if (!A || A->layout != RLS_LAYOUT_COLMAJOR || rls_normal_matrix(s->AHA) != A) return false;
+  int32_t form = -1;
+  rls_normal_form(s->AHA, &form);
+  if (form != RLS_NORMAL_TWOPASS && form != RLS_NORMAL_ONEPASS) return false;      // the lazy A'(A x) on this very matrix
+  if (A->m < 1 || A->n < 1 || A->m > PK_THREADS * PK_MAXROWS) return false;
+  const int64_t cn = (A->n + s->ctx->sm_count - 1) / s->ctx->sm_count;
+  if (cn > PK_MAXCN) return false;
+  return (double)A->m * (double)A->n * (double)rls_elem_size(A->dtype) <= 96.0 * 1024 * 1024;   // stays in the 126 MB L2
+}
+
+static int32_t run_persistent(rls_solver_s* s, Lane& L, int cap, bool* launched) {
+  *launched = false;
+  rls_ctx_s* c = s->ctx;
+  rls_mat_s* A = s->A;
+  const int P = c->sm_count;
+  const size_t es = rls_elem_size(A->dtype);
+  const int CN = (int)((A->n + P - 1) / P);
+  const size_t smem = ((size_t)A->m + 4 * (size_t)CN) * es;
+  const void* fn = A->dtype == RLS_C32 ? (const void*)cgnr_persistent_kernel<float2> : (const void*)cgnr_persistent_kernel<float>;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PK_THREADS, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    s->pk_off = true;
+    return RLS_OK;
+  }
+  // [ypart P*m][y m][dpart 5*P*4 doubles][barrier counter][abort flag]
+  const size_t o_y = (size_t)P * A->m * es, o_d = ((o_y + (size_t)A->m * es + 15) / 16) * 16, o_b = o_d + (size_t)5 * P * 4 * 8;
+  const size_t need = o_b + 16;
+  if (s->pk_bytes < need) {
+    if (s->pk_mem) RLS_CUDA(cudaFree(s->pk_mem));
+    s->pk_mem = nullptr; s->pk_bytes = 0;
+    if (cudaMalloc(&s->pk_mem, need) != cudaSuccess) { cudaGetLastError(); s->pk_off = true; return RLS_OK; }
+    s->pk_bytes = need;
+  }
+  char* base = (char*)s->pk_mem;
+  RLS_CUDA(cudaMemsetAsync(base + o_b, 0, 16, c->stream));
+  PkArgs a{};
+  a.A = A->d; a.ld = A->ld; a.m = (int)A->m; a.n = (int)A->n; a.CN = CN;
+  a.x = L.v[V_X]->d; a.r = L.v[V_X0]->d; a.p = L.v[V_P]->d; a.v = L.v[V_V]->d;
+  a.S = L.dS;
+  a.ypart = base; a.y = base + o_y; a.dpart = (double*)(base + o_d);
+  a.bar = (unsigned*)(base + o_b); a.abort_flag = (int*)(base + o_b + 8);
+  a.cap = cap;
+  void* args[] = {&a};
+  RLS_CUDA(cudaLaunchCooperativeKernel(fn, dim3(P), dim3(PK_THREADS), args, smem, c->stream));
+  c->launches++;
+  s->pk_used = true;
+  *launched = true;
+  if (s->desc.proj_mask) RLS_TRY(rls_proj_launch(c, s->dtype, L.v[V_X]->d, s->n, s->desc.proj_mask, nullptr));   // CGNR.jl:146-149
+  return RLS_OK;
+}
+
 static int32_t run_lane_async(rls_solver_s* s, Lane& L, int already_done) {
   const int cap = iteration_cap(s->desc, s->n);
+  if (already_done == 0 && cap > 0 && persistent_eligible(s)) {
+    bool launched = false;
+    RLS_TRY(run_persistent(s, L, cap, &launched));
+    if (launched) return RLS_OK;
+  }
   if (already_done == 0 && cap > 0 && s->plain_solves >= 1 && graph_eligible(s)) {
     if (s->graph && s->graph_scratch != s->ctx->gemv_scratch) graph_drop(s);   // another operator grew the shared scratch
     if (!s->graph && capture_iterations(s, L, cap) != RLS_OK) { s->graph_off = true; s->graph = nullptr; }

@@ -446,6 +446,44 @@ def test_cgnr_whole_solve_graph_replay(rls, ctx, dtype, form, monkeypatch):
     assert np.array_equal(S1.x, ref[1][0])
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,lam,reltol", [((96, 256), 1e-3, 1e-4), ((96, 256), 0.0, 0.0), ((300, 1000), 1e-2, 0.0),
+                                               ((1024, 4096), 1e-3, 0.0), ((1500, 700), 1e-3, 1e-5), ((33, 2), 1e-3, 0.0)])
+def test_cgnr_persistent_whole_solve_kernel(rls, ctx, dtype, shape, lam, reltol, monkeypatch):
+    """RLS_CGNR_PERSISTENT=1: the whole CGNR solve of an L2-resident column-major system as ONE cooperative kernel (columns of
+    A pinned to CTAs, four grid-wide exchanges per iteration, the chained path's scalar code on a private copy of the
+    state).  Its sums run in another order than the chained kernels': same iteration count and stopping decision, iterates
+    within the parity bound of the oracle (or as close to the Float64 recurrence as the Float32 oracle is)."""
+    m, n = shape
+    A, _, b = problem(dtype, m, n)
+    its = min(30, n)
+    reg = rls.L2Regularization(np.float32(lam)) if lam > 0 else None
+    oreg = O.L2Regularization(np.float32(lam)) if lam > 0 else None
+    kw = dict(iterations=its, relTol=np.float32(reltol))
+    Ad = rls.B200Matrix.from_numpy(A, ctx, layout="col")
+    monkeypatch.setenv("RLS_CGNR_PERSISTENT", "0")
+    Sc = rls.CGNR(Ad, reg=reg, **kw)
+    xc = rls.solve_(Sc, b)
+    monkeypatch.setenv("RLS_CGNR_PERSISTENT", "1")
+    Sp = rls.CGNR(Ad, reg=reg, **kw)
+    l0 = ctx.launch_count()
+    xp = rls.solve_(Sp, b)
+    launches = ctx.launch_count() - l0
+    assert launches < 12, f"{launches} launches: the whole-solve kernel did not run"
+    assert Sp.iteration == Sc.iteration, (Sp.iteration, Sc.iteration)
+    R = O.CGNR(A, reg=oreg, **kw)
+    x32 = R.solve(b)
+    x64 = O.CGNR(up64(A), reg=(O.L2Regularization(float(np.float32(lam))) if lam > 0 else None), iterations=its,
+                 relTol=float(np.float32(reltol))).solve(up64(b))
+    assert Sp.iteration == R.iteration
+    e = rel(xp, x32)
+    assert e < TOL or rel(xp, x64) <= 1.5 * rel(x32, x64), (e, rel(xp, x64), rel(x32, x64), rel(xc, x64))
+    assert rel(xp, xc) < 5e-5
+    assert abs(Sp._scalars.rel_res_norm - Sc._scalars.rel_res_norm) <= 1e-4 * max(Sc._scalars.rel_res_norm, 1e-6)
+    xp2 = rls.solve_(Sp, b)                                    # deterministic, and the state it leaves behind is reusable
+    assert np.array_equal(xp2, xp)
+
+
 # ---------------------------------------------------------------- row-major device layout (one-pass cluster kernel)
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("solver,kw", [("FISTA", dict(restart="none")), ("FISTA", dict(restart="gradient")),

@@ -53,16 +53,19 @@ def c1():
     A = rls.B200Matrix.philox(np.complex64, m, n, seed=12345, dist=0, ctx=ctx)
     xt = rls.B200Vector(ctx, np.complex64, n).fill_philox(12345, stream=5, dist=0)
     b = A.mul(xt)
-    for graph in ("1", "0"):
+    for graph, persistent in (("1", "0"), ("0", "0"), ("0", "1")):
         os.environ["RLS_SOLVE_GRAPH"] = graph
+        os.environ["RLS_CGNR_PERSISTENT"] = persistent
         S = rls.CGNR(A, reg=rls.L2Regularization(np.float32(1e-3)), iterations=its, relTol=0.0)
         timed_solve(S, b, 2)                                   # first solve launch by launch, second one records the graph
         ms, done = timed_solve(S, b, 20)
         emit({"config": "C1 CGNR + L2, ComplexF32 1024x4096, 50 iterations (L2-resident, latency-bound)", "iterations": done,
-              "whole_solve_cuda_graph": graph == "1", "ms_per_solve": ms, "us_per_iteration": 1e3 * ms / its,
+              "whole_solve_cuda_graph": graph == "1", "whole_solve_cooperative_kernel": persistent == "1",
+              "rel_res_norm": S._scalars.rel_res_norm, "ms_per_solve": ms, "us_per_iteration": 1e3 * ms / its,
               "iterations_per_s": its / ms * 1e3, "normal_operator": S.AHA.describe(),
               "note": "33.6 MB of A stays in L2; per-iteration time is launch/latency, not HBM; ms_per_solve includes init! (A'b)"})
     os.environ.pop("RLS_SOLVE_GRAPH")
+    os.environ.pop("RLS_CGNR_PERSISTENT")
 
 
 def c3():
