@@ -381,6 +381,7 @@ constexpr int PK_MAXCN = 64;       // columns per CTA
 
 struct PkArgs {
   const void* A; int64_t ld; int m, n, CN;
+  int ncache;                     // own columns kept in shared memory for the whole solve (the others stream from L2)
   void *x, *r, *p, *v;            // n-vectors of the lane (V_X, V_X0, V_P, V_V)
   DevState* S;
   void* ypart;                    // [grid][m]
@@ -453,6 +454,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) cgnr_persistent_kernel(PkArgs a
   T* xs = ps + a.CN;
   T* rs = xs + a.CN;
   T* vs = rs + a.CN;
+  T* As = vs + a.CN;                               // [ncache][m]: the first ncache own columns of A, resident for the whole solve
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = blockIdx.x, P = gridDim.x;
   const int j0 = c * a.CN;
@@ -470,6 +472,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) cgnr_persistent_kernel(PkArgs a
     rs[j] = reinterpret_cast<const T*>(a.r)[j0 + j];
     vs[j] = reinterpret_cast<const T*>(a.v)[j0 + j];
   }
+  const int ncache = min(a.ncache, nown);
+  for (int idx = tid; idx < ncache * a.m; idx += PK_THREADS) {
+    const int j = idx / a.m, i = idx - j * a.m;
+    As[idx] = __ldg(A + (int64_t)(j0 + j) * a.ld + i);
+  }
   __syncthreads();
   const int RM = (a.m + P - 1) / P;                // rows of y this CTA reduces in phase B
 
@@ -481,7 +488,17 @@ __global__ void __launch_bounds__(PK_THREADS, 1) cgnr_persistent_kernel(PkArgs a
 #pragma unroll
       for (int q = 0; q < PK_MAXROWS; ++q) acc[q] = Elem<T>::zero();
 #pragma unroll 4
-      for (int j = 0; j < nown; ++j) {
+      for (int j = 0; j < ncache; ++j) {           // columns resident in shared memory
+        const T pj = ps[j];
+        const T* col = As + j * a.m;
+#pragma unroll
+        for (int q = 0; q < PK_MAXROWS; ++q) {
+          const int i = tid + q * PK_THREADS;
+          if (i < a.m) pk_fma(acc[q], col[i], pj);
+        }
+      }
+#pragma unroll 4
+      for (int j = ncache; j < nown; ++j) {        // the rest streams from L2
         const T pj = ps[j];
         const T* col = A + (int64_t)(j0 + j) * a.ld;
 #pragma unroll
@@ -513,10 +530,16 @@ __global__ void __launch_bounds__(PK_THREADS, 1) cgnr_persistent_kernel(PkArgs a
     for (int i = tid; i < a.m; i += PK_THREADS) ys[i] = pk_ldcg(yg + i);
     __syncthreads();
     for (int j = warp; j < nown; j += PK_THREADS / 32) {
-      const T* col = A + (int64_t)(j0 + j) * a.ld;
       T sacc = Elem<T>::zero();
+      if (j < ncache) {
+        const T* col = As + j * a.m;
 #pragma unroll 8
-      for (int i = lane; i < a.m; i += 32) pk_fmac(sacc, __ldg(col + i), ys[i]);
+        for (int i = lane; i < a.m; i += 32) pk_fmac(sacc, col[i], ys[i]);
+      } else {
+        const T* col = A + (int64_t)(j0 + j) * a.ld;
+#pragma unroll 8
+        for (int i = lane; i < a.m; i += 32) pk_fmac(sacc, __ldg(col + i), ys[i]);
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sacc = pk_plain_add(sacc, pk_shfl(sacc, o));
       if (lane == 0) vs[j] = sacc;
@@ -1569,8 +1592,17 @@ static int32_t run_persistent(rls_solver_s* s, Lane& L, int cap, bool* launched)
   const int P = c->sm_count;
   const size_t es = rls_elem_size(A->dtype);
   const int CN = (int)((A->n + P - 1) / P);
-  const size_t smem = ((size_t)A->m + 4 * (size_t)CN) * es;
+  const size_t fixed = ((size_t)A->m + 4 * (size_t)CN) * es;
   const void* fn = A->dtype == RLS_C32 ? (const void*)cgnr_persistent_kernel<float2> : (const void*)cgnr_persistent_kernel<float>;
+  // as many own columns of A as fit stay in shared memory for the whole solve (C1: 27 of the 28 columns of a CTA)
+  int optin = 0;
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+  cudaFuncAttributes fa{};
+  if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) { cudaGetLastError(); s->pk_off = true; return RLS_OK; }
+  const size_t budget = (size_t)optin > fa.sharedSizeBytes + fixed ? (size_t)optin - fa.sharedSizeBytes - fixed : 0;
+  const int ncache = (int)std::min<size_t>((size_t)CN, budget / ((size_t)A->m * es));
+  const size_t smem = fixed + (size_t)ncache * (size_t)A->m * es;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); s->pk_off = true; return RLS_OK; }
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PK_THREADS, smem) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
@@ -1589,7 +1621,7 @@ static int32_t run_persistent(rls_solver_s* s, Lane& L, int cap, bool* launched)
   char* base = (char*)s->pk_mem;
   RLS_CUDA(cudaMemsetAsync(base + o_b, 0, 16, c->stream));
   PkArgs a{};
-  a.A = A->d; a.ld = A->ld; a.m = (int)A->m; a.n = (int)A->n; a.CN = CN;
+  a.A = A->d; a.ld = A->ld; a.m = (int)A->m; a.n = (int)A->n; a.CN = CN; a.ncache = ncache;
   a.x = L.v[V_X]->d; a.r = L.v[V_X0]->d; a.p = L.v[V_P]->d; a.v = L.v[V_V]->d;
   a.S = L.dS;
   a.ypart = base; a.y = base + o_y; a.dpart = (double*)(base + o_d);

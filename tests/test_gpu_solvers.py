@@ -478,8 +478,11 @@ def test_cgnr_persistent_whole_solve_kernel(rls, ctx, dtype, shape, lam, reltol,
     assert Sp.iteration == R.iteration
     e = rel(xp, x32)
     assert e < TOL or rel(xp, x64) <= 1.5 * rel(x32, x64), (e, rel(xp, x64), rel(x32, x64), rel(xc, x64))
-    assert rel(xp, xc) < 5e-5
-    assert abs(Sp._scalars.rel_res_norm - Sc._scalars.rel_res_norm) <= 1e-4 * max(Sc._scalars.rel_res_norm, 1e-6)
+    # against the chained kernels: equal to rounding — or, where CG has run into the Float32 floor and every rounding is
+    # amplified (the Float32 oracle itself is then that far from its Float64 run), both within that noise
+    noise = 1.5 * rel(x32, x64)
+    assert rel(xp, xc) < 5e-5 or (rel(xp, x64) <= noise and rel(xc, x64) <= noise), (rel(xp, xc), rel(xp, x64), rel(xc, x64), noise)
+    assert abs(Sp._scalars.rel_res_norm - Sc._scalars.rel_res_norm) <= 1e-4 * Sc._scalars.rel_res_norm + 2e-6   # Float32 floor of ‖r‖/‖A'b‖
     xp2 = rls.solve_(Sp, b)                                    # deterministic, and the state it leaves behind is reusable
     assert np.array_equal(xp2, xp)
 
