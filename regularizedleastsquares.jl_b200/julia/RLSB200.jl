@@ -126,16 +126,16 @@ Base.size(A::B200Matrix) = (A.m, A.n)
 
 "AHA for a device matrix: `normalOperator(A)` / `A'*A` both resolve to the library's normal operator"
 mutable struct B200NormalOp{T}
-  handle::Ptr{Cvoid}; A::B200Matrix{T}
+  handle::Ptr{Cvoid}; n::Int; keep::Any      # keep: what the operator was built from (a matrix, a matrix-free operator, a callback)
 end
 function B200NormalOp(A::B200Matrix{T}; form = RLS_NORMAL_AUTO) where T
   h = Ref{Ptr{Cvoid}}(C_NULL)
   check(ccall((:rls_normal_create, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), A.handle, form, h))
-  finalizer(o -> ccall((:rls_normal_destroy, LIB), Int32, (Ptr{Cvoid},), o.handle), B200NormalOp{T}(h[], A))
+  finalizer(o -> ccall((:rls_normal_destroy, LIB), Int32, (Ptr{Cvoid},), o.handle), B200NormalOp{T}(h[], A.n, A))
 end
 Base.:*(At::Adjoint{T,B200Matrix{T}}, A::B200Matrix{T}) where T = B200NormalOp(parent(At))   # FISTA.jl:58 `AHA = A'*A`
 Base.eltype(::B200NormalOp{T}) where T = T
-Base.size(op::B200NormalOp, d...) = size(op.A, 2)
+Base.size(op::B200NormalOp, d...) = op.n
 function LinearAlgebra.mul!(res::B200Vector, op::B200NormalOp, x::B200Vector)                # FISTA.jl:152
   check(ccall((:rls_normal_apply, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), op.handle, x.handle, res.handle)); res
 end
@@ -179,14 +179,14 @@ end
 function B200SamplingOp(::Type{T}; pattern::AbstractVector{<:Integer}, shape) where T
   h = Ref{Ptr{Cvoid}}(); pat = collect(Int64, pattern)
   check(ccall((:rls_linop_sampling_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Int64}, Ptr{Ptr{Cvoid}}),
-              default_ctx().handle, T <: Complex ? RLS_C32 : RLS_F32, prod(shape), length(pat), pat, h))
+              ctx().handle, T <: Complex ? RLS_C32 : RLS_F32, prod(shape), length(pat), pat, h))
   L = B200LinOp{T}(h[], length(pat), prod(shape), nothing)
   finalizer(l -> ccall((:rls_linop_destroy, LIB), Int32, (Ptr{Cvoid},), l.handle), L)
 end
 function B200FFTOp(::Type{ComplexF32}; shape, shift::Bool = true, unitary::Bool = true)
   h = Ref{Ptr{Cvoid}}(); shp = collect(Int64, shape)
   check(ccall((:rls_linop_fft_create, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, Int32, Int32, Ptr{Ptr{Cvoid}}),
-              default_ctx().handle, length(shp), shp, shift, unitary, h))
+              ctx().handle, length(shp), shp, shift, unitary, h))
   L = B200LinOp{ComplexF32}(h[], prod(shape), prod(shape), nothing)
   finalizer(l -> ccall((:rls_linop_destroy, LIB), Int32, (Ptr{Cvoid},), l.handle), L)
 end
@@ -205,7 +205,7 @@ LinearAlgebra.mul!(x::B200Vector, At::Adjoint{T,B200LinOp{T}}, y::B200Vector) wh
 function LinearOperatorCollection.normalOperator(A::B200LinOp{T}) where T
   h = Ref{Ptr{Cvoid}}()
   check(ccall((:rls_normal_from_linop, LIB), Int32, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), A.handle, h))
-  B200NormalOp{T}(h[], A.n)
+  finalizer(o -> ccall((:rls_normal_destroy, LIB), Int32, (Ptr{Cvoid},), o.handle), B200NormalOp{T}(h[], A.n, A))
 end
 # any other LinearOperator (NFFT, Radon, wavelets on the GPU, ...): AHA as a @cfunction on device pointers + stream
 #   apply(user, x::Ptr{Cvoid}, res::Ptr{Cvoid}, stream::Ptr{Cvoid})::Int32 = (my_gpu_normal_op!(res, x, stream); Int32(0))
@@ -213,8 +213,8 @@ end
 function B200NormalOp(fn::Ptr{Cvoid}, ::Type{T}, n::Integer; user::Ptr{Cvoid} = C_NULL) where T
   h = Ref{Ptr{Cvoid}}()
   check(ccall((:rls_normal_from_callback, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
-              default_ctx().handle, T <: Complex ? RLS_C32 : RLS_F32, n, fn, user, h))
-  B200NormalOp{T}(h[], n)
+              ctx().handle, T <: Complex ? RLS_C32 : RLS_F32, n, fn, user, h))
+  finalizer(o -> ccall((:rls_normal_destroy, LIB), Int32, (Ptr{Cvoid},), o.handle), B200NormalOp{T}(h[], n, (fn, user)))
 end
 
 # ---- solvers: one library-side solver object per Julia solver, keyed by objectid ---------------------
