@@ -7,7 +7,7 @@
 // Here the thresholding never forms U: with the q x q Gram matrix of the SHORT side, G = X'X = V S² V',
 //     SVT_λ(X) = U max(S-λ,0) V' = X · W,      W = V diag(max(s_i-λ,0)/s_i) V'   (q x q),
 // so the work is two streaming passes over X (Gram, then X·W) around a small Hermitian eigenproblem:
-//   svt_gram_kernel   partial Gram matrices of 64-row chunks, accumulated in Float64          (HBM / L2 bound)
+//   svt_gram_kernel   partial Gram matrices over 64-row chunks (a CTA walks several), accumulated in Float64   (HBM / L2 bound)
 //   svt_eig_kernel    one warp per problem: sums the partials, cyclic two-sided Jacobi in Float64 in shared memory
 //                     (lane k owns row / column k of every rotation), builds W                  (latency bound, q <= 64)
 //   svt_apply_kernel  out = X·W chunk by chunk, in place (or accumulated for the overlapping LLR)  (HBM / L2 bound)
@@ -103,7 +103,10 @@ __device__ __forceinline__ void svt_stage(const T* __restrict__ x, const SvtGeom
   }
 }
 
-// Gpart[(prob - p0) * nchunk + chunk][a][b] = sum_l conj(X[l][a]) X[l][b] over the chunk
+// Gpart[(prob - p0) * gridDim.y + blockIdx.y][a][b] = sum over the chunks blockIdx.y, blockIdx.y + gridDim.y, ... of
+// sum_l conj(X[l][a]) X[l][b]: a CTA walks its chunks with the q*q/256 pair sums of every thread in registers, so a long
+// matrix (NuclearRegularization with 10^6 rows) leaves a few hundred partial Gram matrices, not one per 64 rows
+constexpr int SVT_NP = SVT_MAXQ * SVT_MAXQ / SVT_THREADS;   // pairs per thread at q = 64
 template <typename T>
 __global__ void __launch_bounds__(SVT_THREADS) svt_gram_kernel(const T* __restrict__ x, SvtGeom g, int64_t p0, int nchunk, double2* __restrict__ Gpart,
                                                                double* __restrict__ rowmax, const int* __restrict__ gate) {
@@ -111,36 +114,56 @@ __global__ void __launch_bounds__(SVT_THREADS) svt_gram_kernel(const T* __restri
   __shared__ float2 xs[SVT_CH * SVT_MAXQ];
   __shared__ double wmax[2];
   const int64_t prob = p0 + blockIdx.x;
-  const int chunk = blockIdx.y;
   const int q = g.q;
-  svt_stage<T>(x, g, prob, (int64_t)chunk * SVT_CH, xs);
-  __syncthreads();
-  if (rowmax && threadIdx.x < SVT_CH) {
-    // largest squared norm of a long-side row: in the transposed LLR view these are the FRAMES, i.e. the diagonal of
-    // the frames x frames Gram matrix whose largest |entry| the reference's shortcut needs (a Gram matrix has it on the diagonal)
-    double r2 = 0.0;
-    for (int i = 0; i < q; ++i) {
-      const float2 v = xs[threadIdx.x * q + i];
-      r2 = fma((double)v.x, (double)v.x, fma((double)v.y, (double)v.y, r2));
+  double2 acc[SVT_NP];
+#pragma unroll
+  for (int k = 0; k < SVT_NP; ++k) acc[k] = make_double2(0.0, 0.0);
+  double rmax = 0.0;
+  for (int chunk = blockIdx.y; chunk < nchunk; chunk += gridDim.y) {
+    __syncthreads();                       // the previous chunk has been consumed
+    svt_stage<T>(x, g, prob, (int64_t)chunk * SVT_CH, xs);
+    __syncthreads();
+    if (rowmax && threadIdx.x < SVT_CH) {
+      // largest squared norm of a long-side row: in the transposed LLR view these are the FRAMES, i.e. the diagonal of
+      // the frames x frames Gram matrix whose largest |entry| the reference's shortcut needs (a Gram matrix has it on the diagonal)
+      double r2 = 0.0;
+      for (int i = 0; i < q; ++i) {
+        const float2 v = xs[threadIdx.x * q + i];
+        r2 = fma((double)v.x, (double)v.x, fma((double)v.y, (double)v.y, r2));
+      }
+      rmax = fmax(rmax, r2);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, o));
-    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = r2;
-  }
-  __syncthreads();
-  if (rowmax && threadIdx.x == 0) rowmax[(int64_t)blockIdx.x * nchunk + chunk] = fmax(wmax[0], wmax[1]);
-  double2* out = Gpart + ((int64_t)blockIdx.x * nchunk + chunk) * (int64_t)(q * q);
-  for (int idx = threadIdx.x; idx < q * q; idx += SVT_THREADS) {
-    const int a = idx / q, b = idx - a * q;
-    double2 s = make_double2(0.0, 0.0);
+    for (int k = 0; k < SVT_NP; ++k) {
+      const int idx = threadIdx.x + k * SVT_THREADS;
+      if (idx < q * q) {
+        const int a = idx / q, b = idx - a * q;
+        double2 s = acc[k];
 #pragma unroll 4
-    for (int l = 0; l < SVT_CH; ++l) {
-      const float2 uf = xs[l * q + a], vf = xs[l * q + b];
-      const double ux = uf.x, uy = uf.y, vx = vf.x, vy = vf.y;
-      s.x = fma(ux, vx, fma(uy, vy, s.x));
-      s.y = fma(ux, vy, fma(-uy, vx, s.y));
+        for (int l = 0; l < SVT_CH; ++l) {
+          const float2 uf = xs[l * q + a], vf = xs[l * q + b];
+          const double ux = uf.x, uy = uf.y, vx = vf.x, vy = vf.y;
+          s.x = fma(ux, vx, fma(uy, vy, s.x));
+          s.y = fma(ux, vy, fma(-uy, vx, s.y));
+        }
+        acc[k] = s;
+      }
     }
-    out[idx] = s;
+  }
+  if (rowmax) {
+    if (threadIdx.x < SVT_CH) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+      if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = rmax;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) rowmax[(int64_t)blockIdx.x * gridDim.y + blockIdx.y] = fmax(wmax[0], wmax[1]);
+  }
+  double2* out = Gpart + ((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * (int64_t)(q * q);
+#pragma unroll
+  for (int k = 0; k < SVT_NP; ++k) {
+    const int idx = threadIdx.x + k * SVT_THREADS;
+    if (idx < q * q) out[idx] = acc[k];
   }
 }
 
@@ -274,7 +297,7 @@ __global__ void svt_eig_kernel(const double2* __restrict__ Gpart, const double* 
 // out(l, j) = sum_i X(l, i) W[i][j] for the chunk.  acc == NULL: written in place over x; else acc[off] += value
 // (fully overlapping LLR: every shift's result is summed, ProxLLR.jl:188-191).
 template <typename T>
-__global__ void __launch_bounds__(SVT_THREADS) svt_apply_kernel(T* __restrict__ x, SvtGeom g, int64_t p0, const double2* __restrict__ Wmat,
+__global__ void __launch_bounds__(SVT_THREADS) svt_apply_kernel(T* __restrict__ x, SvtGeom g, int64_t p0, int nchunk, const double2* __restrict__ Wmat,
                                                                 T* __restrict__ acc, const int* __restrict__ gate) {
   if (gate && *gate) return;
   extern __shared__ double2 svt_apply_smem[];
@@ -282,27 +305,30 @@ __global__ void __launch_bounds__(SVT_THREADS) svt_apply_kernel(T* __restrict__ 
   double2* Ws = svt_apply_smem;                                     // [q][q]
   float2* xs = reinterpret_cast<float2*>(svt_apply_smem + q * q);   // [SVT_CH][q]
   const int64_t prob = p0 + blockIdx.x;
-  const int64_t l0 = (int64_t)blockIdx.y * SVT_CH;
   const double2* W = Wmat + (int64_t)blockIdx.x * (q * q);
   for (int idx = threadIdx.x; idx < q * q; idx += SVT_THREADS) Ws[idx] = W[idx];
-  svt_stage<T>(x, g, prob, l0, xs);
-  __syncthreads();     // the whole chunk is on chip: the in-place stores below cannot disturb a later read
-  const int total = SVT_CH * q;
-  for (int idx = threadIdx.x; idx < total; idx += SVT_THREADS) {
-    int l, j;
-    if (g.mode & 1) { j = idx % q; l = idx / q; }
-    else { l = idx % SVT_CH; j = idx / SVT_CH; }
-    if (l0 + l >= g.L) continue;
-    const int64_t off = svt_offset(g, prob, l0 + l, j);
-    if (off < 0) continue;
-    double2 s = make_double2(0.0, 0.0);
-    for (int i = 0; i < q; ++i) {
-      const float2 xf = xs[l * q + i];
-      s = cfma(make_double2((double)xf.x, (double)xf.y), Ws[i * q + j], s);
+  for (int chunk = blockIdx.y; chunk < nchunk; chunk += gridDim.y) {     // W is loaded once per CTA, chunks are walked
+    const int64_t l0 = (int64_t)chunk * SVT_CH;
+    __syncthreads();     // the previous chunk has been written out
+    svt_stage<T>(x, g, prob, l0, xs);
+    __syncthreads();     // the whole chunk is on chip: the in-place stores below cannot disturb a later read
+    const int total = SVT_CH * q;
+    for (int idx = threadIdx.x; idx < total; idx += SVT_THREADS) {
+      int l, j;
+      if (g.mode & 1) { j = idx % q; l = idx / q; }
+      else { l = idx % SVT_CH; j = idx / SVT_CH; }
+      if (l0 + l >= g.L) continue;
+      const int64_t off = svt_offset(g, prob, l0 + l, j);
+      if (off < 0) continue;
+      double2 s = make_double2(0.0, 0.0);
+      for (int i = 0; i < q; ++i) {
+        const float2 xf = xs[l * q + i];
+        s = cfma(make_double2((double)xf.x, (double)xf.y), Ws[i * q + j], s);
+      }
+      const T v = SvtElem<T>::make(s, g.mode & 1);
+      if (acc) acc[off] = SvtElem<T>::add(acc[off], v);
+      else x[off] = v;
     }
-    const T v = SvtElem<T>::make(s, g.mode & 1);
-    if (acc) acc[off] = SvtElem<T>::add(acc[off], v);
-    else x[off] = v;
   }
 }
 
@@ -329,15 +355,17 @@ template <typename T>
 int32_t svt_run(rls_ctx_s* c, T* x, const SvtGeom& g, int64_t nprob, float lam, const float* lam_dev, int llr, T* acc, const int* gate) {
   const int q = g.q;
   const int64_t nchunk64 = (g.L + SVT_CH - 1) / SVT_CH;
-  RLS_CHECK_ARG(nchunk64 <= 65535, "singular-value thresholding: long side %lld too large", (long long)g.L);
+  RLS_CHECK_ARG(nchunk64 <= 0x7fffffff, "singular-value thresholding: long side %lld too large", (long long)g.L);
   const int nchunk = (int)nchunk64;
-  const size_t per_prob = (size_t)(nchunk + 1) * q * q * sizeof(double2) + (size_t)nchunk * sizeof(double);
+  // CTAs per problem along the long side: one per chunk, but no more than ~4 waves of the device in total
+  const int gy = (int)std::max<int64_t>(1, std::min<int64_t>(nchunk, (4 * (int64_t)c->sm_count + nprob - 1) / nprob));
+  const size_t per_prob = (size_t)(gy + 1) * q * q * sizeof(double2) + (size_t)gy * sizeof(double);
   int64_t batch = (int64_t)std::max<size_t>(1, ((size_t)128 << 20) / per_prob);
   if (batch > nprob) batch = nprob;
   if (batch > 0x3fffffff) batch = 0x3fffffff;
   RLS_TRY(ensure_scratch(c, (size_t)batch * per_prob));
   double2* Gpart = (double2*)c->svt_scratch;
-  double2* Wm = Gpart + (size_t)batch * nchunk * q * q;
+  double2* Wm = Gpart + (size_t)batch * gy * q * q;
   double* rowmax = g.mode == 3 ? (double*)(Wm + (size_t)batch * q * q) : nullptr;
   const int wpb = q > 16 ? 1 : 4;
   const size_t eig_smem = (size_t)wpb * 2 * q * (q + 1) * sizeof(double2);
@@ -347,9 +375,9 @@ int32_t svt_run(rls_ctx_s* c, T* x, const SvtGeom& g, int64_t nprob, float lam, 
     RLS_CUDA(cudaFuncSetAttribute((const void*)svt_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
   for (int64_t p0 = 0; p0 < nprob; p0 += batch) {
     const int64_t np = std::min(batch, nprob - p0);
-    svt_gram_kernel<T><<<dim3((unsigned)np, (unsigned)nchunk), SVT_THREADS, 0, c->stream>>>(x, g, p0, nchunk, Gpart, rowmax, gate);
-    svt_eig_kernel<<<(unsigned)((np + wpb - 1) / wpb), 32 * wpb, eig_smem, c->stream>>>(Gpart, rowmax, nchunk, q, np, lam, lam_dev, llr, Wm, gate);
-    svt_apply_kernel<T><<<dim3((unsigned)np, (unsigned)nchunk), SVT_THREADS, apply_smem, c->stream>>>(x, g, p0, Wm, acc, gate);
+    svt_gram_kernel<T><<<dim3((unsigned)np, (unsigned)gy), SVT_THREADS, 0, c->stream>>>(x, g, p0, nchunk, Gpart, rowmax, gate);
+    svt_eig_kernel<<<(unsigned)((np + wpb - 1) / wpb), 32 * wpb, eig_smem, c->stream>>>(Gpart, rowmax, gy, q, np, lam, lam_dev, llr, Wm, gate);
+    svt_apply_kernel<T><<<dim3((unsigned)np, (unsigned)gy), SVT_THREADS, apply_smem, c->stream>>>(x, g, p0, nchunk, Wm, acc, gate);
     c->launches += 3;
   }
   RLS_CUDA(cudaGetLastError());
