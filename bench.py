@@ -382,24 +382,71 @@ def run_b200(args):
     # secondary: round 1's line — FISTA-L1 on one Float32 16384 x 65536 shard per GPU (weak scaling)
     secondary = None
     if not args.no_secondary:
-        m2 = 16384
-        A2 = rls.B200Matrix.philox(np.float32, m2, N_COLS, seed=SEED, scale=1.0 / np.sqrt(m2 * world), row_offset=rank * m2,
-                                   m_global=m2 * world, ctx=ctx)
-        x2 = rls.B200Vector(ctx, np.float32, N_COLS).fill_philox(SEED, stream=11, dist=0)
-        h2 = x2.to_numpy(); h2[np.arange(N_COLS) % 100 != 0] = 0; x2.upload(h2)
-        b2 = A2.mul(x2)
-        op2 = rls.B200NormalOp(A2, form=args.normal)
-        rho2 = np.float32(0.95 / op2.power_iterations(rls.B200Vector(ctx, np.float32, N_COLS).fill_philox(SEED, stream=13, dist=1), maxiter=30))
-        S2 = rls.FISTA(A2, AHA=op2, reg=rls.L1Regularization(LAMBDA), iterations=200, rho=rho2, relTol=0.0)
-        call2 = lambda: capi.call("rls_solver_solve", S2._handle, b2.handle, None, C.byref(it), C.byref(S2._scalars))
-        for _ in range(3):
-            call2()
-        ms2 = timed(call2, 5)
-        secondary = {"workload": "C2 shard per GPU: FISTA-L1, Float32 16384x65536, 200 iterations per solve (weak scaling, "
-                                 "round-1 bench line)", "shard_iterations_per_s_per_gpu": 5 * 200 / (ms2 * 1e-3),
-                     "ms_per_iteration": ms2 / 5 / 200, "frac_of_measured_hbm": m2 * N_COLS * 4 / (ms2 / 5 / 200 * 1e-3) / 1e9 / peak,
-                     "normal_operator": op2.describe()}
-        del S2, op2, A2
+        try:
+            m2 = 16384
+            A2 = rls.B200Matrix.philox(np.float32, m2, N_COLS, seed=SEED, scale=1.0 / np.sqrt(m2 * world), row_offset=rank * m2,
+                                       m_global=m2 * world, ctx=ctx)
+            x2 = rls.B200Vector(ctx, np.float32, N_COLS).fill_philox(SEED, stream=11, dist=0)
+            h2 = x2.to_numpy(); h2[np.arange(N_COLS) % 100 != 0] = 0; x2.upload(h2)
+            b2 = A2.mul(x2)
+            op2 = rls.B200NormalOp(A2, form=args.normal)
+            rho2 = np.float32(0.95 / op2.power_iterations(rls.B200Vector(ctx, np.float32, N_COLS).fill_philox(SEED, stream=13, dist=1), maxiter=30))
+            S2 = rls.FISTA(A2, AHA=op2, reg=rls.L1Regularization(LAMBDA), iterations=200, rho=rho2, relTol=0.0)
+            call2 = lambda: capi.call("rls_solver_solve", S2._handle, b2.handle, None, C.byref(it), C.byref(S2._scalars))
+            for _ in range(3):
+                call2()
+            ms2 = timed(call2, 5)
+            secondary = {"workload": "C2 shard per GPU: FISTA-L1, Float32 16384x65536, 200 iterations per solve (weak scaling, "
+                                     "round-1 bench line)", "shard_iterations_per_s_per_gpu": 5 * 200 / (ms2 * 1e-3),
+                         "ms_per_iteration": ms2 / 5 / 200, "frac_of_measured_hbm": m2 * N_COLS * 4 / (ms2 / 5 / 200 * 1e-3) / 1e9 / peak,
+                         "normal_operator": op2.describe()}
+            del S2, op2, A2
+        except Exception as e:                                      # never at the price of the main line
+            if multi:
+                raise                                               # ranks must not part ways in front of a collective
+            secondary = {"error": f"{type(e).__name__}: {e}"}
+
+    # secondary: BASELINE config C4 — 64 frames sharing one ComplexF32 A 32768 x 16384 (MultiThreading.jl path) on the tensor
+    # cores, A-form (two GEMMs per batched iteration) and Gram form (the reference's default AHA = A'*A: one GEMM over G)
+    secondary_c4 = None
+    if not args.no_secondary and world == 1:
+        try:
+            m4, n4, K4, its4 = 32768, 16384, 64, 50
+            A4 = rls.B200Matrix.philox(dt, m4, n4, seed=4321, scale=1.0 / np.sqrt(m4), ctx=ctx)
+            X4 = np.zeros((n4, K4), np.complex64, order="F")
+            rng4 = np.random.default_rng(4)
+            for k in range(K4):
+                i4 = rng4.integers(0, n4, 160)
+                X4[i4, k] = (rng4.random(160) + 1j * rng4.random(160)).astype(np.complex64)
+            B4 = np.empty((m4, K4), np.complex64, order="F")
+            for k in range(K4):
+                B4[:, k] = A4.mul(rls.B200Vector.from_numpy(X4[:, k].copy(), ctx)).to_numpy()
+            op4 = rls.B200NormalOp(A4, form="auto")
+            rho4 = np.float32(0.95 / op4.power_iterations(rls.B200Vector(ctx, dt, n4).fill_philox(9, stream=1, dist=1)))
+            secondary_c4 = {"workload": "C4: multi-RHS FISTA-L1, 64 frames sharing ComplexF32 A 32768x16384, 50 iterations per solve; one "
+                                        "step = solve!(solver, B) with host B in and host X out (tcgen05 split-precision GEMMs)"}
+            for form, opf in (("a_form", op4), ("gram_form", None)):
+                ctx.sync()
+                t0 = time.perf_counter()
+                if opf is None:
+                    opf = rls.B200NormalOp(A4, form="gram")
+                    ctx.sync()
+                    secondary_c4["gram_build_s"] = time.perf_counter() - t0
+                S4 = rls.FISTA(A4, AHA=opf, reg=rls.L1Regularization(LAMBDA), iterations=its4, rho=rho4, relTol=0.0)
+                Xs4 = None
+
+                def solve4():
+                    nonlocal Xs4
+                    Xs4 = rls.solve_(S4, B4)
+                solve4()                                            # lane allocation and the GEMM plans are one-time costs
+                ms4 = timed(solve4, 3) / 3
+                secondary_c4[form] = {"frame_iterations_per_s": K4 * its4 / (ms4 * 1e-3), "ms_per_batched_iteration": ms4 / its4,
+                                      "rel_err_vs_truth": float(np.linalg.norm(Xs4 - X4) / np.linalg.norm(X4)),
+                                      "normal_operator": opf.describe()}
+                del S4
+            del op4, opf, A4
+        except Exception as e:                                      # a secondary line must never cost the bench its main line
+            secondary_c4 = {"error": f"{type(e).__name__}: {e}"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -449,6 +496,8 @@ def run_b200(args):
             line["parity"] = parity
         if secondary is not None:
             line["secondary_c2"] = secondary
+        if secondary_c4 is not None:
+            line["secondary_c4"] = secondary_c4
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
