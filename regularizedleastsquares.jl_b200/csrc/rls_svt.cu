@@ -232,14 +232,15 @@ __global__ void svt_eig_kernel(const double2* __restrict__ Gpart, const double* 
         const double ab2 = b.x * b.x + b.y * b.y;
         if (ab2 <= tol2) continue;                          // warp-uniform: every lane reads the same shared values
         rotated = 1;
-        const double app = G[p * pitch + p].x, arr = G[r * pitch + r].x;
-        const double ab = sqrt(ab2);
-        const double2 ph = make_double2(b.x / ab, b.y / ab);
-        const double tau = (arr - app) / (2.0 * ab);
-        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-        const double c = 1.0 / sqrt(1.0 + t * t);
-        const double s = t * c;
-        const double2 sph = make_double2(s * ph.x, s * ph.y);     // s e^{iφ}
+        // with d = G[r][r] - G[p][p], τ = d / (2|b|), t = sgn(τ) / (|τ| + sqrt(1 + τ²)), c = 1/sqrt(1 + t²), s = t c.  Written
+        // without |b| and τ — h = sqrt(d² + 4|b|²), w = 1/(|d| + h): t² = 4|b|² w², s e^{iφ} = b · 2 sgn(d) w c — the dependent
+        // chain is one sqrt, one division and one rsqrt instead of three square roots and five divisions
+        const double d = G[r * pitch + r].x - G[p * pitch + p].x;
+        const double h = sqrt(fma(d, d, 4.0 * ab2));
+        const double w = 1.0 / (fabs(d) + h);
+        const double c = rsqrt(fma(4.0 * ab2, w * w, 1.0));
+        const double k = (d >= 0.0 ? 2.0 : -2.0) * w * c;
+        const double2 sph = make_double2(k * b.x, k * b.y);       // s e^{iφ}
         const double2 sphc = make_double2(sph.x, -sph.y);         // s e^{-iφ}
         __syncwarp();
         for (int k = lane; k < q; k += 32) {   // columns p, r of G and V (k = row):  col_p' = c col_p - s e^{-iφ} col_r,  col_r' = s e^{iφ} col_p + c col_r
@@ -398,7 +399,7 @@ int32_t rls_prox_nuclear_launch(rls_ctx_s* c, int32_t dtype, void* x, int64_t n,
   }
   SvtGeom g{};
   g.M = rows;
-  if (cols <= rows || cols <= SVT_MAXQ) { g.mode = 0; g.q = (int)cols; g.L = rows; }
+  if (cols <= rows) { g.mode = 0; g.q = (int)cols; g.L = rows; }          // the Gram matrix of the SHORTER side
   else { g.mode = 1; g.q = (int)rows; g.L = cols; }
   if (dtype == RLS_C32) return svt_run<float2>(c, (float2*)x, g, 1, lam, lam_dev, 0, nullptr, gate);
   return svt_run<float>(c, (float*)x, g, 1, lam, lam_dev, 0, nullptr, gate);
@@ -420,7 +421,7 @@ static int32_t llr_pass(rls_ctx_s* c, int32_t dtype, void* x, int64_t n, int32_t
   }
   g.npix = npix;
   const int64_t K = n / npix;
-  if (K <= ppix || K <= SVT_MAXQ) { g.mode = 2; g.q = (int)K; g.L = ppix; }     // short side = frames
+  if (K <= ppix) { g.mode = 2; g.q = (int)K; g.L = ppix; }                     // short side = frames
   else { g.mode = 3; g.q = (int)ppix; g.L = K; }                               // short side = pixels of a patch
   if (dtype == RLS_C32) return svt_run<float2>(c, (float2*)x, g, nprob, lam, lam_dev, 1, (float2*)acc, gate);
   return svt_run<float>(c, (float*)x, g, nprob, lam, lam_dev, 1, (float*)acc, gate);

@@ -28,13 +28,13 @@ def jacobi_w(G, thr):
                     continue
                 rotated = True
                 app, arr = G[p, p].real, G[r, r].real
-                ab = np.sqrt(ab2)
-                ph = complex(b.real / ab, b.imag / ab)
-                tau = (arr - app) / (2.0 * ab)
-                t = (1.0 if tau >= 0 else -1.0) / (abs(tau) + np.sqrt(1.0 + tau * tau))
-                c = 1.0 / np.sqrt(1.0 + t * t)
-                s = t * c
-                sph, sphc = s * ph, s * np.conj(ph)
+                d = arr - app
+                h = np.sqrt(d * d + 4.0 * ab2)
+                w = 1.0 / (abs(d) + h)
+                c = 1.0 / np.sqrt(4.0 * ab2 * w * w + 1.0)
+                k = (2.0 if d >= 0 else -2.0) * w * c
+                sph = k * b
+                sphc = np.conj(sph)
                 gp, gr = G[:, p].copy(), G[:, r].copy()
                 G[:, p] = c * gp - sphc * gr
                 G[:, r] = sph * gp + c * gr
@@ -73,7 +73,7 @@ def prox_nuclear(x, lam, rows, cols):
     assert min(rows, cols) <= MAXQ
     up = np.complex128 if np.iscomplexobj(x) else np.float64
     X = x.reshape((rows, cols), order="F").astype(up)
-    if cols <= rows or cols <= MAXQ:
+    if cols <= rows:
         out = svt_tall(X, lam)
     else:
         out = svt_tall(X.conj().T, lam).conj().T
@@ -89,7 +89,7 @@ def _llr_pass(x, lam, shape, block, shift):
     stride = [int(np.prod(shape[:d])) for d in range(nd)]
     nblk = [(shape[d] + block[d] - 1) // block[d] for d in range(nd)]
     sh = [((shift[d] if shift is not None else 0) % shape[d] + shape[d]) % shape[d] for d in range(nd)]
-    transposed = not (K <= ppix or K <= MAXQ)
+    transposed = not (K <= ppix)
     assert (ppix if transposed else K) <= MAXQ
     up = np.complex128 if np.iscomplexobj(x) else np.float64
     out = x.copy()
