@@ -39,6 +39,40 @@ def test_reg_desc_resolution(rls):
     assert abs(d.rho - 0.2) < 1e-7
     G = rls.GradientOp(np.float32, (16, 8))
     assert G.rows == O.grad_rows((16, 8), (1, 2)) == 15 * 8 + 16 * 7
+    # SVD-type terms ride in the TV fields of the POD struct (include/rls_b200.h, RLS_REG_NUCLEAR / RLS_REG_LLR)
+    d = reg_desc(rls.NuclearRegularization(np.float32(0.3), svtShape=(4096, 16)))
+    assert (d.kind, d.tv_ndims, list(d.tv_shape)[:2]) == (rls._capi.RLS_REG_NUCLEAR, 2, [4096, 16])
+    d = reg_desc(rls.LLRRegularization(np.float32(0.3), shape=(64, 48), blockSize=(4, 2), randshift=True, fullyOverlapping=True, seed=11))
+    assert (d.kind, d.tv_ndims, list(d.tv_shape)[:2], list(d.tv_dims)[:2]) == (rls._capi.RLS_REG_LLR, 2, [64, 48], [4, 2])
+    assert d.tv_iterations == rls._capi.RLS_LLR_RANDSHIFT | rls._capi.RLS_LLR_OVERLAPPING and d.slices == 11
+    d = reg_desc(rls.LLRRegularization(np.float32(0.3), shape=(8, 8, 8), randshift=False))
+    assert list(d.tv_dims)[:3] == [2, 2, 2] and d.tv_iterations == 0          # blockSize defaults to 2 per dimension (ProxLLR.jl:27)
+    with pytest.raises(ValueError):
+        rls.NuclearRegularization(np.float32(0.3), svtShape=(4, 4, 4))
+    r = rls.LLRRegularization(np.float32(0.3), shape=(8, 8), blockSize=(4, 2), seed=5)
+    shifts = [r.next_shift() for _ in range(20)]
+    assert all(1 <= a <= 4 and 1 <= b <= 2 for a, b in shifts) and len(set(shifts)) > 1     # rand(CartesianIndices(blockSize))
+    assert rls.LLRRegularization(np.float32(0.3), shape=(8, 8), randshift=False).next_shift() == (0, 0)
+
+
+def test_bench_host_thread_count_respects_affinity():
+    """bench.py sizes the BLAS pool of its CPU legs to the threads the process is granted, not to os.cpu_count()"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    try:
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        n = mod.host_threads()
+        assert 1 <= n <= len(os.sched_getaffinity(0))
+        assert os.environ["OMP_NUM_THREADS"] == str(n)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def test_row_ranges_tile_the_matrix(rls):
