@@ -8,8 +8,8 @@
 //     SVT_λ(X) = U max(S-λ,0) V' = X · W,      W = V diag(max(s_i-λ,0)/s_i) V'   (q x q),
 // so the work is two streaming passes over X (Gram, then X·W) around a small Hermitian eigenproblem:
 //   svt_gram_kernel   partial Gram matrices over 64-row chunks (a CTA walks several), accumulated in Float64   (HBM / L2 bound)
-//   svt_eig_kernel    one warp per problem: sums the partials, cyclic two-sided Jacobi in Float64 in shared memory
-//                     (lane k owns row / column k of every rotation), builds W                  (latency bound, q <= 64)
+//   svt_eig_kernel    one warp per problem: sums the partials, two-sided Jacobi in Float64 in shared memory with the round-robin
+//                     ordering (q/2 disjoint pairs rotated per round), builds W                     (latency bound, q <= 64)
 //   svt_apply_kernel  out = X·W chunk by chunk, in place (or accumulated for the overlapping LLR)  (HBM / L2 bound)
 // Forming G squares the condition number, which is why G, V and W live in Float64: the inputs are Float32, so G is
 // exact to 2^-53 relative and singular values down to 1e-7 s_max keep full Float32 accuracy.
@@ -180,7 +180,7 @@ __global__ void svt_eig_kernel(const double2* __restrict__ Gpart, const double* 
   const int64_t pl = (int64_t)blockIdx.x * wpb + warp;   // problem index inside this launch
   if (pl >= nprob) return;
   const int pitch = q + 1;
-  double2* G = svt_smem + (size_t)warp * 2 * q * pitch;
+  double2* G = svt_smem + (size_t)warp * (2 * q * pitch + 64);     // + 64 double2: the rotation table of a round
   double2* V = G + q * pitch;
   const double thr = (double)(lam_dev ? *lam_dev : lam);
 
@@ -221,54 +221,88 @@ __global__ void svt_eig_kernel(const double2* __restrict__ Gpart, const double* 
     return;
   }
 
-  // cyclic Jacobi: for every pair (p, r) the unitary J = [[c, s e^{iφ}], [-s e^{-iφ}, c]] with G[p][r] = |b| e^{iφ}
-  // annihilates G[p][r]:  G <- J' G J, V <- V J
+  // Jacobi with the round-robin ("circle") ordering: a sweep is q-1 rounds (q rounded up to even), every round rotates q/2
+  // DISJOINT pairs at once.  Lane k computes the parameters of pair k — for the pair (p, r) the unitary
+  // [[c, s e^{iφ}], [-s e^{-iφ}, c]] with G[p][r] = |b| e^{iφ} annihilates G[p][r] — then all lanes apply the round's
+  // rotations: G <- G J (lane = row), V <- V J, G <- J' G (lane = column).  One parameter chain and three warp
+  // synchronisations per ROUND instead of per pair (q = 64: 63 instead of 2016 per sweep).
+  double2* rot_s = V + q * pitch;                            // [32] s e^{iφ} of the round's pairs
+  double* rot_c = reinterpret_cast<double*>(rot_s + 32);     // [32] c
+  int* rot_p = reinterpret_cast<int*>(rot_c + 32);           // [32] p (-1: nothing to rotate)
+  int* rot_r = rot_p + 32;                                   // [32] r
   const double tol2 = (1e-15 * tr) * (1e-15 * tr);
+  const int qe = q + (q & 1), n1 = qe - 1, npairs = qe >> 1;
   for (int sweep = 0; sweep < 40; ++sweep) {
-    int rotated = 0;
-    for (int p = 0; p < q - 1; ++p) {
-      for (int r = p + 1; r < q; ++r) {
-        const double2 b = G[p * pitch + r];
-        const double ab2 = b.x * b.x + b.y * b.y;
-        if (ab2 <= tol2) continue;                          // warp-uniform: every lane reads the same shared values
-        rotated = 1;
-        // with d = G[r][r] - G[p][p], τ = d / (2|b|), t = sgn(τ) / (|τ| + sqrt(1 + τ²)), c = 1/sqrt(1 + t²), s = t c.  Written
-        // without |b| and τ — h = sqrt(d² + 4|b|²), w = 1/(|d| + h): t² = 4|b|² w², s e^{iφ} = b · 2 sgn(d) w c — the dependent
-        // chain is one sqrt, one division and one rsqrt instead of three square roots and five divisions
-        const double d = G[r * pitch + r].x - G[p * pitch + p].x;
-        const double h = sqrt(fma(d, d, 4.0 * ab2));
-        const double w = 1.0 / (fabs(d) + h);
-        const double c = rsqrt(fma(4.0 * ab2, w * w, 1.0));
-        const double k = (d >= 0.0 ? 2.0 : -2.0) * w * c;
-        const double2 sph = make_double2(k * b.x, k * b.y);       // s e^{iφ}
-        const double2 sphc = make_double2(sph.x, -sph.y);         // s e^{-iφ}
-        __syncwarp();
-        for (int k = lane; k < q; k += 32) {   // columns p, r of G and V (k = row):  col_p' = c col_p - s e^{-iφ} col_r,  col_r' = s e^{iφ} col_p + c col_r
-          const double2 gpv = G[k * pitch + p], grv = G[k * pitch + r];
-          const double2 a1 = cmul(sphc, grv), a2 = cmul(sph, gpv);
-          G[k * pitch + p] = make_double2(c * gpv.x - a1.x, c * gpv.y - a1.y);
-          G[k * pitch + r] = make_double2(a2.x + c * grv.x, a2.y + c * grv.y);
-          const double2 vpv = V[k * pitch + p], vrv = V[k * pitch + r];
-          const double2 b1 = cmul(sphc, vrv), b2 = cmul(sph, vpv);
-          V[k * pitch + p] = make_double2(c * vpv.x - b1.x, c * vpv.y - b1.y);
-          V[k * pitch + r] = make_double2(b2.x + c * vrv.x, b2.y + c * vrv.y);
+    unsigned rotated = 0;
+    for (int rr = 0; rr < n1; ++rr) {
+      int pa = -1, pb = -1;
+      double c = 1.0;
+      double2 sph = make_double2(0.0, 0.0);
+      if (lane < npairs) {
+        const int a = lane == 0 ? rr : (rr + lane) % n1;
+        const int b2 = lane == 0 ? n1 : (rr - lane + n1) % n1;
+        if (a < q && b2 < q) {                               // (the padding index of an odd q sits out)
+          const int lo = min(a, b2), hi = max(a, b2);
+          const double2 b = G[lo * pitch + hi];
+          const double ab2 = b.x * b.x + b.y * b.y;
+          if (ab2 > tol2) {
+            // with d = G[r][r] - G[p][p], τ = d / (2|b|), t = sgn(τ) / (|τ| + sqrt(1 + τ²)), c = 1/sqrt(1 + t²), s = t c.  Written
+            // without |b| and τ — h = sqrt(d² + 4|b|²), w = 1/(|d| + h): t² = 4|b|² w², s e^{iφ} = b · 2 sgn(d) w c — the dependent
+            // chain is one sqrt, one division and one rsqrt
+            const double d = G[hi * pitch + hi].x - G[lo * pitch + lo].x;
+            const double h = sqrt(fma(d, d, 4.0 * ab2));
+            const double w = 1.0 / (fabs(d) + h);
+            c = rsqrt(fma(4.0 * ab2, w * w, 1.0));
+            const double k = (d >= 0.0 ? 2.0 : -2.0) * w * c;
+            sph = make_double2(k * b.x, k * b.y);
+            pa = lo; pb = hi;
+          }
         }
-        __syncwarp();
-        for (int k = lane; k < q; k += 32) {   // rows p, r of G (k = column):  row_p' = c row_p - s e^{iφ} row_r,  row_r' = s e^{-iφ} row_p + c row_r
-          const double2 rp = G[p * pitch + k], rr = G[r * pitch + k];
-          const double2 a1 = cmul(sph, rr), a2 = cmul(sphc, rp);
-          G[p * pitch + k] = make_double2(c * rp.x - a1.x, c * rp.y - a1.y);
-          G[r * pitch + k] = make_double2(a2.x + c * rr.x, a2.y + c * rr.y);
-        }
-        __syncwarp();
-        if (lane == 0) {
-          G[p * pitch + r] = make_double2(0.0, 0.0);
-          G[r * pitch + p] = make_double2(0.0, 0.0);
-          G[p * pitch + p].y = 0.0;
-          G[r * pitch + r].y = 0.0;
-        }
-        __syncwarp();
       }
+      rot_p[lane] = pa; rot_r[lane] = pb; rot_c[lane] = c; rot_s[lane] = sph;
+      const unsigned active = __ballot_sync(0xffffffffu, pa >= 0);
+      __syncwarp();
+      if (active == 0) continue;                             // warp-uniform
+      rotated |= active;
+      for (int row = lane; row < q; row += 32) {             // columns p, r of G and V:  col_p' = c col_p - s e^{-iφ} col_r,  col_r' = s e^{iφ} col_p + c col_r
+        for (int k = 0; k < npairs; ++k) {
+          const int p = rot_p[k];
+          if (p < 0) continue;
+          const int r = rot_r[k];
+          const double ck = rot_c[k];
+          const double2 sk = rot_s[k], skc = make_double2(sk.x, -sk.y);
+          const double2 gpv = G[row * pitch + p], grv = G[row * pitch + r];
+          const double2 a1 = cmul(skc, grv), a2 = cmul(sk, gpv);
+          G[row * pitch + p] = make_double2(ck * gpv.x - a1.x, ck * gpv.y - a1.y);
+          G[row * pitch + r] = make_double2(a2.x + ck * grv.x, a2.y + ck * grv.y);
+          const double2 vpv = V[row * pitch + p], vrv = V[row * pitch + r];
+          const double2 b1 = cmul(skc, vrv), b3 = cmul(sk, vpv);
+          V[row * pitch + p] = make_double2(ck * vpv.x - b1.x, ck * vpv.y - b1.y);
+          V[row * pitch + r] = make_double2(b3.x + ck * vrv.x, b3.y + ck * vrv.y);
+        }
+      }
+      __syncwarp();
+      for (int col = lane; col < q; col += 32) {             // rows p, r of G:  row_p' = c row_p - s e^{iφ} row_r,  row_r' = s e^{-iφ} row_p + c row_r
+        for (int k = 0; k < npairs; ++k) {
+          const int p = rot_p[k];
+          if (p < 0) continue;
+          const int r = rot_r[k];
+          const double ck = rot_c[k];
+          const double2 sk = rot_s[k], skc = make_double2(sk.x, -sk.y);
+          const double2 rp = G[p * pitch + col], rw = G[r * pitch + col];
+          const double2 a1 = cmul(sk, rw), a2 = cmul(skc, rp);
+          G[p * pitch + col] = make_double2(ck * rp.x - a1.x, ck * rp.y - a1.y);
+          G[r * pitch + col] = make_double2(a2.x + ck * rw.x, a2.y + ck * rw.y);
+        }
+      }
+      __syncwarp();
+      if (pa >= 0) {
+        G[pa * pitch + pb] = make_double2(0.0, 0.0);
+        G[pb * pitch + pa] = make_double2(0.0, 0.0);
+        G[pa * pitch + pa].y = 0.0;
+        G[pb * pitch + pb].y = 0.0;
+      }
+      __syncwarp();
     }
     if (!rotated) break;
   }
@@ -369,7 +403,7 @@ int32_t svt_run(rls_ctx_s* c, T* x, const SvtGeom& g, int64_t nprob, float lam, 
   double2* Wm = Gpart + (size_t)batch * gy * q * q;
   double* rowmax = g.mode == 3 ? (double*)(Wm + (size_t)batch * q * q) : nullptr;
   const int wpb = q > 16 ? 1 : 4;
-  const size_t eig_smem = (size_t)wpb * 2 * q * (q + 1) * sizeof(double2);
+  const size_t eig_smem = (size_t)wpb * (2 * (size_t)q * (q + 1) + 64) * sizeof(double2);
   const size_t apply_smem = (size_t)q * q * sizeof(double2) + (size_t)SVT_CH * q * sizeof(float2);
   if (eig_smem > 48 * 1024) RLS_CUDA(cudaFuncSetAttribute((const void*)svt_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem));
   if (apply_smem > 48 * 1024)

@@ -1,5 +1,5 @@
 """NumPy mirror of csrc/rls_svt.cu (test infrastructure): the same decomposition — Float64 Gram matrix of the short side,
-cyclic two-sided Jacobi with the kernel's rotation formulas and tolerance, W = V diag(max(s-λ,0)/s) V', out = X·W — and
+two-sided Jacobi with the kernel's round-robin ordering, rotation formulas and tolerance, W = V diag(max(s-λ,0)/s) V', out = X·W — and
 the same index arithmetic (svt_offset) for the LLR patch views.  It lets the CPU suite check the ALGORITHM of the device
 path against the oracle's LAPACK-SVD restatement of the reference; the -m gpu tests then check the kernels themselves."""
 import numpy as np
@@ -11,29 +11,46 @@ def _down(a, dtype):
     return a.astype(dtype) if np.iscomplexobj(np.empty(0, dtype)) else np.real(a).astype(dtype)
 
 
+def pairs_of_round(q, rr):
+    """the round-robin ("circle") ordering of svt_eig_kernel: round rr of a sweep rotates these disjoint pairs at once"""
+    qe = q + (q & 1)
+    n1 = qe - 1
+    out = []
+    for k in range(qe // 2):
+        a, b = (rr, n1) if k == 0 else ((rr + k) % n1, (rr - k + n1) % n1)
+        if a < q and b < q:                    # the padding index of an odd q sits out
+            out.append((min(a, b), max(a, b)))
+    return out
+
+
 def jacobi_w(G, thr):
-    """svt_eig_kernel: eigen-decomposition of the Hermitian G (complex128) and W = V D V'"""
+    """svt_eig_kernel: eigen-decomposition of the Hermitian G (complex128) by Jacobi rotations — a sweep is q-1 rounds of
+    q/2 disjoint pairs, each round G <- J' G J, V <- V J with J the direct sum of the pairs' rotations — and W = V D V'"""
     q = G.shape[0]
     G = G.astype(np.complex128).copy()
     V = np.eye(q, dtype=np.complex128)
     tr = float(np.real(np.trace(G)))
     tol2 = (1e-15 * tr) ** 2
+    qe = q + (q & 1)
     for _ in range(40):
         rotated = False
-        for p in range(q - 1):
-            for r in range(p + 1, q):
+        for rr in range(qe - 1):
+            rots = []
+            for (p, r) in pairs_of_round(q, rr):
                 b = G[p, r]
                 ab2 = b.real * b.real + b.imag * b.imag
                 if ab2 <= tol2:
                     continue
-                rotated = True
-                app, arr = G[p, p].real, G[r, r].real
-                d = arr - app
+                d = G[r, r].real - G[p, p].real
                 h = np.sqrt(d * d + 4.0 * ab2)
                 w = 1.0 / (abs(d) + h)
                 c = 1.0 / np.sqrt(4.0 * ab2 * w * w + 1.0)
                 k = (2.0 if d >= 0 else -2.0) * w * c
-                sph = k * b
+                rots.append((p, r, c, k * b))
+            if not rots:
+                continue
+            rotated = True
+            for p, r, c, sph in rots:              # columns of G and V
                 sphc = np.conj(sph)
                 gp, gr = G[:, p].copy(), G[:, r].copy()
                 G[:, p] = c * gp - sphc * gr
@@ -41,9 +58,12 @@ def jacobi_w(G, thr):
                 vp, vr = V[:, p].copy(), V[:, r].copy()
                 V[:, p] = c * vp - sphc * vr
                 V[:, r] = sph * vp + c * vr
-                rp, rr = G[p, :].copy(), G[r, :].copy()
-                G[p, :] = c * rp - sph * rr
-                G[r, :] = sphc * rp + c * rr
+            for p, r, c, sph in rots:              # rows of G
+                sphc = np.conj(sph)
+                rp, rw = G[p, :].copy(), G[r, :].copy()
+                G[p, :] = c * rp - sph * rw
+                G[r, :] = sphc * rp + c * rw
+            for p, r, c, sph in rots:
                 G[p, r] = 0.0
                 G[r, p] = 0.0
                 G[p, p] = G[p, p].real

@@ -101,6 +101,19 @@ def test_oracle_llr_shortcut_uses_the_largest_entry_of_the_gram_matrix():
     assert np.allclose(out, (np.sqrt(12) - 1.5) / np.sqrt(12), rtol=1e-6)
 
 
+def test_round_robin_ordering_visits_every_pair_once_per_sweep():
+    for q in (1, 2, 3, 5, 8, 16, 31, 32, 33, 63, 64):
+        qe = q + (q & 1)
+        seen = set()
+        for rr in range(qe - 1):
+            ps = M.pairs_of_round(q, rr)
+            flat = [i for pr in ps for i in pr]
+            assert len(flat) == len(set(flat)) and len(ps) <= 32          # disjoint within a round, one lane per pair
+            assert not (seen & set(ps))
+            seen |= set(ps)
+        assert len(seen) == q * (q - 1) // 2
+
+
 def _rnd(rng, n, dt):
     return (rng.standard_normal(n) + (1j * rng.standard_normal(n) if np.dtype(dt).kind == "c" else 0)).astype(dt)
 
